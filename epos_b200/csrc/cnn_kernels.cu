@@ -1,0 +1,440 @@
+// HBM-bound CNN kernels of the EPOS forward pass (everything except the tensor-core pointwise GEMM):
+// entry convs, depthwise 3x3 (strided / atrous), f32->split-bf16, global mean, bilinear resize,
+// softmax/argmax, plus an fp32 SIMT GEMM used for validation and for tiny (M = batch) GEMMs.
+// Reference call sites are cited in include/epos_b200.h next to each entry point.
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace epos {
+
+static thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv1_1: preprocessing + 3x3 s2 conv (pad 1/1, VALID) + bias + ReLU.  8 threads per output pixel,
+// 4 output channels each (Cout = 32).
+// ------------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(256) conv3x3_rgb_s2_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, float* __restrict__ y,
+                                                             int B, int H, int W, int Ho, int Wo) {
+  __shared__ float sw[27 * COUT];
+  __shared__ float sb[COUT];
+  for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias[i];
+  __syncthreads();
+  constexpr int G = COUT / 4;
+  const long long total = (long long)B * Ho * Wo * G;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % G);
+    long long p = idx / G;
+    const int ox = (int)(p % Wo);
+    p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    float acc[4] = {sb[g * 4 + 0], sb[g * 4 + 1], sb[g * 4 + 2], sb[g * 4 + 3]};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * 2 - 1 + ky;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * 2 - 1 + kx;
+        if (ix < 0 || ix >= W) continue;
+        const float* px = x + (((long long)b * H + iy) * W + ix) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float v = (2.0f / 255.0f) * __ldg(px + c) - 1.0f;   // feature.py:171-174
+          const float* ww = sw + ((ky * 3 + kx) * 3 + c) * COUT + g * 4;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] = fmaf(v, ww[j], acc[j]);
+        }
+      }
+    }
+    float4 o = make_float4(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+    *reinterpret_cast<float4*>(y + (((long long)b * Ho + oy) * Wo + ox) * COUT + g * 4) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv1_2: dense 3x3 s1 SAME + bias + ReLU.  One CTA = 16x16 output pixels x COUT channels; the
+// 18x18xCIN halo tile and the whole filter bank live in shared memory.
+// ------------------------------------------------------------------------------------------------
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256) conv3x3_dense_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, float* __restrict__ y,
+                                                            int H, int W) {
+  extern __shared__ float smem[];
+  constexpr int PS = CIN + 1;                      // padded pixel stride: conflict-free across tx
+  float* s_in = smem;                              // [18*18][PS]
+  float* s_w = smem + 18 * 18 * PS;                // [9*CIN][COUT]
+  const int b = blockIdx.z;
+  const int ty0 = blockIdx.y * 16, tx0 = blockIdx.x * 16;
+  for (int i = threadIdx.x; i < 9 * CIN * COUT / 4; i += 256)
+    reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
+  for (int i = threadIdx.x; i < 18 * 18 * (CIN / 4); i += 256) {
+    const int c4 = i % (CIN / 4);
+    const int p = i / (CIN / 4);
+    const int iy = ty0 - 1 + p / 18, ix = tx0 - 1 + p % 18;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+      v = __ldg(reinterpret_cast<const float4*>(x + (((long long)b * H + iy) * W + ix) * CIN) + c4);
+    float* d = s_in + p * PS + c4 * 4;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  __syncthreads();
+  const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
+  float acc[COUT];
+#pragma unroll
+  for (int j = 0; j < COUT; ++j) acc[j] = 0.f;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) {
+      const float* pin = s_in + ((ty + ky) * 18 + tx + kx) * PS;
+      const float* pw = s_w + (ky * 3 + kx) * CIN * COUT;
+#pragma unroll 4
+      for (int c = 0; c < CIN; ++c) {
+        const float a = pin[c];
+        const float4* w4 = reinterpret_cast<const float4*>(pw + c * COUT);
+#pragma unroll
+        for (int j = 0; j < COUT / 4; ++j) {
+          const float4 ww = w4[j];
+          acc[4 * j + 0] = fmaf(a, ww.x, acc[4 * j + 0]);
+          acc[4 * j + 1] = fmaf(a, ww.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(a, ww.z, acc[4 * j + 2]);
+          acc[4 * j + 3] = fmaf(a, ww.w, acc[4 * j + 3]);
+        }
+      }
+    }
+  const int oy = ty0 + ty, ox = tx0 + tx;
+  if (oy < H && ox < W) {
+    float4* out = reinterpret_cast<float4*>(y + (((long long)b * H + oy) * W + ox) * COUT);
+#pragma unroll
+    for (int j = 0; j < COUT / 4; ++j) {
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + j);
+      out[j] = make_float4(fmaxf(acc[4 * j + 0] + bb.x, 0.f), fmaxf(acc[4 * j + 1] + bb.y, 0.f),
+                           fmaxf(acc[4 * j + 2] + bb.z, 0.f), fmaxf(acc[4 * j + 3] + bb.w, 0.f));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Depthwise 3x3: one thread = one output pixel x 4 channels; consecutive threads walk the channel
+// axis (coalesced float4 loads, 9 taps served by L1/L2), output as f32 and/or split-bf16.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dwconv3x3_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ y_f32,
+                                                        uint16_t* __restrict__ y_split, long long plane_stride,
+                                                        int B, int H, int W, int C, int Ho, int Wo, int stride, int rate,
+                                                        int relu_in, int relu_out) {
+  const int G = C >> 2;
+  const long long total = (long long)B * Ho * Wo * G;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % G);
+    long long p = idx / G;
+    const int ox = (int)(p % Wo);
+    long long q = p / Wo;
+    const int oy = (int)(q % Ho);
+    const int b = (int)(q / Ho);
+    float4 acc = __ldg(reinterpret_cast<const float4*>(bias) + g);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * stride - rate + ky * rate;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * stride - rate + kx * rate;
+        if (ix < 0 || ix >= W) continue;
+        float4 v = __ldg(reinterpret_cast<const float4*>(x + (((long long)b * H + iy) * W + ix) * ldx) + g);
+        if (relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        const float4 ww = __ldg(reinterpret_cast<const float4*>(w + (ky * 3 + kx) * C) + g);
+        acc.x = fmaf(v.x, ww.x, acc.x); acc.y = fmaf(v.y, ww.y, acc.y);
+        acc.z = fmaf(v.z, ww.z, acc.z); acc.w = fmaf(v.w, ww.w, acc.w);
+      }
+    }
+    if (relu_out) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+    if (y_f32) *(reinterpret_cast<float4*>(y_f32 + p * C) + g) = acc;
+    if (y_split) {
+      __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+      split_bf16(acc.x, h0, l0); split_bf16(acc.y, h1, l1); split_bf16(acc.z, h2, l2); split_bf16(acc.w, h3, l3);
+      uint2 hi = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+      uint2 lo = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+      *(reinterpret_cast<uint2*>(y_split + p * C) + g) = hi;
+      *(reinterpret_cast<uint2*>(y_split + plane_stride + p * C) + g) = lo;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, int ldx, uint16_t* __restrict__ y,
+                                                         int ldy, long long plane_stride, int B, int H, int W, int C,
+                                                         int Ho, int Wo, int sub, int relu) {
+  const int G = C >> 2;
+  const long long total = (long long)B * Ho * Wo * G;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % G);
+    long long p = idx / G;
+    const int ox = (int)(p % Wo);
+    long long q = p / Wo;
+    const int oy = (int)(q % Ho);
+    const int b = (int)(q / Ho);
+    float4 v = __ldg(reinterpret_cast<const float4*>(x + (((long long)b * H + oy * sub) * W + ox * sub) * ldx) + g);
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+    split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1); split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+    *(reinterpret_cast<uint2*>(y + p * ldy) + g) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+    *(reinterpret_cast<uint2*>(y + plane_stride + p * ldy) + g) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+  }
+}
+
+// x [B][HW][C] -> y [B][C].  Block = 32 channels x 8 row lanes.
+__global__ void __launch_bounds__(256) global_mean_kernel(const float* __restrict__ x, float* __restrict__ y, int HW, int C) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int b = blockIdx.y;
+  float s = 0.f;
+  if (c < C)
+    for (int r = threadIdx.y; r < HW; r += 8) s += __ldg(x + ((long long)b * HW + r) * C + c);
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    y[(long long)b * C + c] = t / (float)HW;
+  }
+}
+
+// tf.image.resize_bilinear(align_corners=True): src = dst * (in-1)/(out-1), lerp in f32.
+__global__ void __launch_bounds__(256) resize_bilinear_kernel(const float* __restrict__ x, float* __restrict__ y, int ldy,
+                                                              int B, int Hi, int Wi, int Ho, int Wo, int C) {
+  const int G = C >> 2;
+  const float sy = (Ho > 1) ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
+  const float sx = (Wo > 1) ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
+  const long long total = (long long)B * Ho * Wo * G;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % G);
+    long long p = idx / G;
+    const int ox = (int)(p % Wo);
+    long long q = p / Wo;
+    const int oy = (int)(q % Ho);
+    const int b = (int)(q / Ho);
+    const float fy = oy * sy, fx = ox * sx;
+    const int y0 = (int)floorf(fy), x0 = (int)floorf(fx);
+    const int y1 = min(y0 + 1, Hi - 1), x1 = min(x0 + 1, Wi - 1);
+    const float ly = fy - y0, lx = fx - x0;
+    const float4* base = reinterpret_cast<const float4*>(x + (long long)b * Hi * Wi * C) + g;
+    const float4 tl = __ldg(base + ((long long)y0 * Wi + x0) * G), tr = __ldg(base + ((long long)y0 * Wi + x1) * G);
+    const float4 bl = __ldg(base + ((long long)y1 * Wi + x0) * G), br = __ldg(base + ((long long)y1 * Wi + x1) * G);
+    float4 o;
+#define EPOS_LERP(f)                                   \
+  {                                                    \
+    const float top = tl.f + (tr.f - tl.f) * lx;       \
+    const float bot = bl.f + (br.f - bl.f) * lx;       \
+    o.f = top + (bot - top) * ly;                      \
+  }
+    EPOS_LERP(x) EPOS_LERP(y) EPOS_LERP(z) EPOS_LERP(w)
+#undef EPOS_LERP
+    *(reinterpret_cast<float4*>(y + p * ldy) + g) = o;
+  }
+}
+
+// Softmax over rows of length n, in place; one warp per row.  Optional argmax (first maximum).
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x, int64_t* __restrict__ labels,
+                                                           long long rows, int n) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    float* row = x + r * n;
+    float m = -INFINITY;
+    for (int i = lane; i < n; i += 32) m = fmaxf(m, row[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int i = lane; i < n; i += 32) s += expf(row[i] - m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    float best = -1.f;
+    int besti = 0x7fffffff;
+    for (int i = lane; i < n; i += 32) {
+      const float v = expf(row[i] - m) / s;
+      row[i] = v;
+      if (v > best) { best = v; besti = i; }
+    }
+    if (labels) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+      }
+      if (lane == 0) labels[r] = besti;
+    }
+  }
+}
+
+// fp32 SIMT GEMM: D = act(A W^T + bias) (+ residual).  64x64 tile, 256 threads, 4x4 per thread.
+__global__ void __launch_bounds__(256) pwconv_simt_kernel(const float* __restrict__ a, int lda, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, int bias_group_rows,
+                                                          const float* __restrict__ residual, int ldr, float* __restrict__ d,
+                                                          int ldd, int M, int N, int K, int relu) {
+  __shared__ float sa[16][64 + 4];
+  __shared__ float sb[16][64 + 4];
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int r = i / 16, k = i % 16;
+      sa[k][r] = (m0 + r < M && k0 + k < K) ? a[(long long)(m0 + r) * lda + k0 + k] : 0.f;
+      sb[k][r] = (n0 + r < N && k0 + k < K) ? w[(long long)(n0 + r) * K + k0 + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { av[i] = sa[k][ty * 4 + i]; bv[i] = sb[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const float* brow = bias ? bias + (bias_group_rows > 0 ? (long long)(m / bias_group_rows) * N : 0) : nullptr;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (brow ? brow[n] : 0.f);
+      if (relu) v = fmaxf(v, 0.f);
+      if (residual) v += residual[(long long)m * ldr + n];
+      d[(long long)m * ldd + n] = v;
+    }
+  }
+}
+
+static inline int grid_for(long long total, int block = 256) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148LL * 16;     // 16 resident CTAs of 256 threads x 148 SMs; grid-stride beyond
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace epos
+
+using namespace epos;
+
+extern "C" {
+
+const char* epos_last_error(void) { return g_err; }
+int epos_version(void) { return 1; }
+int epos_compiled_arch(void) { return 100; }
+uint64_t epos_launch_count(void) { return (uint64_t)g_launches.load(); }
+
+int epos_conv3x3_rgb_s2(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Cout,
+                        void* stream) {
+  EPOS_CHECK_ARG(x && w && bias && y && B > 0 && H > 0 && W > 0);
+  if (Cout != 32) { set_error("epos_conv3x3_rgb_s2: Cout=%d unsupported (32)", Cout); return EPOS_ERR_UNSUPPORTED; }
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long total = (long long)B * Ho * Wo * (Cout / 4);
+  conv3x3_rgb_s2_kernel<32><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, B, H, W, Ho, Wo);
+  EPOS_LAUNCH_CHECK();
+  return EPOS_OK;
+}
+
+int epos_conv3x3_dense(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Cin,
+                       int Cout, void* stream) {
+  EPOS_CHECK_ARG(x && w && bias && y && B > 0 && H > 0 && W > 0);
+  if (Cin != 32 || Cout != 64) {
+    set_error("epos_conv3x3_dense: (Cin,Cout)=(%d,%d) unsupported (32,64)", Cin, Cout);
+    return EPOS_ERR_UNSUPPORTED;
+  }
+  constexpr int smem = (18 * 18 * 33 + 9 * 32 * 64) * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    EPOS_CUDA(cudaFuncSetAttribute(conv3x3_dense_kernel<32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(W, 16), ceil_div(H, 16), B);
+  conv3x3_dense_kernel<32, 64><<<grid, 256, smem, (cudaStream_t)stream>>>(x, w, bias, y, H, W);
+  EPOS_LAUNCH_CHECK();
+  return EPOS_OK;
+}
+
+int epos_dwconv3x3(const float* x, int ldx, const float* w, const float* bias, float* y_f32, uint16_t* y_split, int B,
+                   int H, int W, int C, int stride, int rate, int relu_in, int relu_out, void* stream) {
+  EPOS_CHECK_ARG(x && w && bias && (y_f32 || y_split));
+  EPOS_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && (C % 4) == 0 && (ldx % 4) == 0 && ldx >= C);
+  EPOS_CHECK_ARG((stride == 1 || stride == 2) && rate >= 1);
+  const int Ho = stride == 1 ? H : (H - 1) / 2 + 1, Wo = stride == 1 ? W : (W - 1) / 2 + 1;
+  const long long total = (long long)B * Ho * Wo * (C / 4);
+  dwconv3x3_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, ldx, w, bias, y_f32, y_split,
+                                                                      (long long)B * Ho * Wo * C, B, H, W, C, Ho, Wo,
+                                                                      stride, rate, relu_in, relu_out);
+  EPOS_LAUNCH_CHECK();
+  return EPOS_OK;
+}
+
+int epos_split_bf16(const float* x, int ldx, uint16_t* y_split, int ldy, size_t y_plane_stride, int B, int H, int W,
+                    int C, int subsample, int relu, void* stream) {
+  EPOS_CHECK_ARG(x && y_split && B > 0 && H > 0 && W > 0 && C > 0 && (C % 4) == 0 && (ldx % 4) == 0 && (ldy % 4) == 0);
+  EPOS_CHECK_ARG(subsample == 1 || subsample == 2);
+  const int Ho = (H - 1) / subsample + 1, Wo = (W - 1) / subsample + 1;
+  const long long total = (long long)B * Ho * Wo * (C / 4);
+  split_bf16_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, ldx, y_split, ldy, (long long)y_plane_stride,
+                                                                       B, H, W, C, Ho, Wo, subsample, relu);
+  EPOS_LAUNCH_CHECK();
+  return EPOS_OK;
+}
+
+int epos_global_mean(const float* x, float* y, int B, int HW, int C, void* stream) {
+  EPOS_CHECK_ARG(x && y && B > 0 && HW > 0 && C > 0);
+  dim3 grid(ceil_div(C, 32), B), block(32, 8);
+  global_mean_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, y, HW, C);
+  EPOS_LAUNCH_CHECK();
+  return EPOS_OK;
+}
+
+int epos_resize_bilinear(const float* x, float* y, int ldy, int B, int Hi, int Wi, int Ho, int Wo, int C, void* stream) {
+  EPOS_CHECK_ARG(x && y && B > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && C > 0 && (C % 4) == 0 && (ldy % 4) == 0);
+  const long long total = (long long)B * Ho * Wo * (C / 4);
+  resize_bilinear_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, y, ldy, B, Hi, Wi, Ho, Wo, C);
+  EPOS_LAUNCH_CHECK();
+  return EPOS_OK;
+}
+
+int epos_softmax_rows(float* x, int64_t* labels, size_t rows, int n, void* stream) {
+  EPOS_CHECK_ARG(x && rows > 0 && n > 0);
+  const long long blocks = ((long long)rows + 7) / 8;
+  softmax_rows_kernel<<<(int)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+      x, labels, (long long)rows, n);
+  EPOS_LAUNCH_CHECK();
+  return EPOS_OK;
+}
+
+int epos_pwconv_simt(const float* a, int lda, const float* w, const float* bias, int bias_group_rows,
+                     const float* residual, int ldr, float* d, int ldd, int M, int N, int K, int relu, void* stream) {
+  EPOS_CHECK_ARG(a && w && d && M > 0 && N > 0 && K > 0 && lda >= K && ldd >= N);
+  dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
+  pwconv_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, lda, w, bias, bias_group_rows, residual, ldr, d, ldd, M,
+                                                            N, K, relu);
+  EPOS_LAUNCH_CHECK();
+  return EPOS_OK;
+}
+
+}  // extern "C"

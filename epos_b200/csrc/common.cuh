@@ -1,0 +1,53 @@
+// Shared helpers for the epos_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include "../../include/epos_b200.h"
+
+namespace epos {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<unsigned long long> g_launches;
+
+inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+#define EPOS_CHECK_ARG(cond)                                                     \
+  do {                                                                           \
+    if (!(cond)) {                                                               \
+      epos::set_error("%s:%d: invalid argument: %s", __FILE__, __LINE__, #cond); \
+      return EPOS_ERR_INVALID_ARG;                                               \
+    }                                                                            \
+  } while (0)
+
+#define EPOS_CUDA(expr)                                                                         \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      epos::set_error("%s:%d: CUDA error %s: %s", __FILE__, __LINE__, cudaGetErrorName(e__),    \
+                      cudaGetErrorString(e__));                                                 \
+      return EPOS_ERR_CUDA;                                                                     \
+    }                                                                                           \
+  } while (0)
+
+#define EPOS_LAUNCH_CHECK()            \
+  do {                                 \
+    epos::count_launch();              \
+    EPOS_CUDA(cudaPeekAtLastError());  \
+  } while (0)
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// fp32 -> (hi, lo) bf16 pair with hi + lo ~= x to 16-17 significant bits.
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+}  // namespace epos

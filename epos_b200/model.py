@@ -1,0 +1,325 @@
+"""B200-native `model.predict` for EPOS (DeepLab-v3+ / Xception-65), drop-in for
+/root/reference/epos_lib/model.py:629-687.
+
+Host side only: PyTorch provides device memory and streams; every op is a hand-written sm_100a kernel
+reached through the C ABI (include/epos_b200.h).  The layer sequence mirrors
+  net_xception.py:396-483,593-657 (xception_65, output_stride 8 -> stride-to-atrous conversion :362-393),
+  model.py:150-265 (ASPP), :268-393 (decoder), :396-458 (logit heads), :668-685 (softmax / argmax),
+with inference BatchNorm folded into the conv weights/bias at load time and 1x1 convolutions executed
+as split-bf16 (error-compensated) tcgen05 GEMMs.
+
+Output contract (same keys / shapes / dtypes / channel order as the reference):
+  pred_obj_conf  [B,h,w,O+1] f32 (softmax)      pred_obj_label [B,h,w] i64
+  pred_frag_conf [B,h,w,O,F] f32 (softmax on F) pred_frag_loc  [B,h,w,O,F,3] f32 (raw)
+as torch CUDA tensors.
+"""
+import collections
+
+import numpy as np
+import torch
+
+from . import _lib
+from .weights import XC, XCEPTION65_BLOCKS, head_channels
+
+PRED_OBJ_CONF = 'pred_obj_conf'        # common.py:24-27
+PRED_OBJ_LABEL = 'pred_obj_label'
+PRED_FRAG_CONF = 'pred_frag_conf'
+PRED_FRAG_LOC = 'pred_frag_loc'
+
+EPS_BACKBONE = 1e-3                    # feature.py:304
+EPS_HEAD = 1e-5                        # model.py:197,310
+DECODER_END_POINT = 'entry_flow/block2/unit_1/xception_module/separable_conv2_pointwise'  # feature.py:61-66
+
+_BLOCK_STRIDES = {'entry_flow/block1': 2, 'entry_flow/block2': 2, 'entry_flow/block3': 2,
+                  'middle_flow/block1': 1, 'exit_flow/block1': 2, 'exit_flow/block2': 1}
+_RELU_INSIDE = {'exit_flow/block2'}    # activation_fn_in_separable_conv=True, net_xception.py:640-647
+
+
+class ModelOptions(collections.namedtuple('ModelOptions', [
+        'outputs_to_num_channels', 'crop_size', 'atrous_rates', 'encoder_output_stride',
+        'decoder_output_stride', 'model_variant'])):
+    """Subset of common.ModelOptions (common.py:206-290) that the inference path reads."""
+    __slots__ = ()
+
+    def __new__(cls, outputs_to_num_channels, crop_size=(640, 480), atrous_rates=(12, 24, 36),
+                encoder_output_stride=8, decoder_output_stride=(4,), model_variant='xception_65'):
+        return super().__new__(cls, outputs_to_num_channels, tuple(crop_size), tuple(atrous_rates),
+                               encoder_output_stride, tuple(decoder_output_stride), model_variant)
+
+
+def scale_dimension(dim, scale):
+    """model.py:100-114."""
+    return int((float(dim) - 1.0) * scale + 1.0)
+
+
+def _bn_fold(w, scope, eps):
+    g, b, m, v = (np.asarray(w['%s/BatchNorm/%s' % (scope, k)], np.float64)
+                  for k in ('gamma', 'beta', 'moving_mean', 'moving_variance'))
+    scale = g / np.sqrt(v + eps)
+    return scale, b - m * scale
+
+
+def _split(t):
+    """f32 [N,K] -> bf16 [2,N,K] (hi, lo)."""
+    hi = t.to(torch.bfloat16)
+    lo = (t - hi.float()).to(torch.bfloat16)
+    return torch.stack([hi, lo]).contiguous()
+
+
+class Gemm:
+    """Folded 1x1 conv: split-bf16 weights [2,N,K], f32 bias [N] (and f32 weights for the SIMT check path)."""
+
+    def __init__(self, w_nk, bias, device, keep_f32):
+        w32 = torch.from_numpy(np.ascontiguousarray(w_nk, dtype=np.float32)).to(device)
+        self.N, self.K = w32.shape
+        self.w_split = _split(w32)
+        self.w_f32 = w32 if keep_f32 else None
+        self.bias = None if bias is None else torch.from_numpy(np.ascontiguousarray(bias, dtype=np.float32)).to(device)
+
+
+class EposNet:
+    def __init__(self, weights, num_objs, num_frags, device='cuda', model_options=None, keep_f32=False):
+        self.lib = _lib.lib()
+        self.dev = torch.device(device)
+        self.O, self.F = num_objs, num_frags
+        self.opts = model_options or ModelOptions(head_channels(num_objs, num_frags))
+        if self.opts.model_variant != 'xception_65' or self.opts.encoder_output_stride != 8:
+            raise NotImplementedError('only xception_65 at output stride 8 is built')
+        self.keep_f32 = keep_f32
+        self.impl = 'tcgen05'            # 'simt' = fp32 validation path (needs keep_f32=True)
+        self.end_points = {}
+        self._prepare(weights)
+
+    # -- weight preparation ---------------------------------------------------------------------------
+    def _dev(self, a):
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.dev)
+
+    def _conv_bn(self, w, scope, eps):
+        k = np.asarray(w[scope + '/weights'], np.float64)                  # [kh,kw,Cin,Cout]
+        scale, shift = _bn_fold(w, scope, eps)
+        return k * scale[None, None, None, :], shift
+
+    def _pw(self, w, scope, eps, keep_f32=None):
+        k, shift = self._conv_bn(w, scope, eps)
+        return Gemm(k[0, 0].T, shift, self.dev, self.keep_f32 if keep_f32 is None else keep_f32)   # [Cout, Cin]
+
+    def _dw(self, w, scope, eps):
+        k = np.asarray(w[scope + '/depthwise_weights'], np.float64)[:, :, :, 0]   # [3,3,C]
+        scale, shift = _bn_fold(w, scope, eps)
+        return self._dev((k * scale[None, None, :]).reshape(9, -1)), self._dev(shift)
+
+    def _prepare(self, w):
+        p = {}
+        k, b = self._conv_bn(w, XC + '/entry_flow/conv1_1', EPS_BACKBONE)
+        p['conv1_1'] = (self._dev(k), self._dev(b))
+        k, b = self._conv_bn(w, XC + '/entry_flow/conv1_2', EPS_BACKBONE)
+        p['conv1_2'] = (self._dev(k), self._dev(b))
+        for scope, depths, skip, units in XCEPTION65_BLOCKS:
+            for u in range(1, units + 1):
+                base = '%s/%s/unit_%d/xception_module' % (XC, scope, u)
+                for i in range(3):
+                    p['%s/dw%d' % (base, i)] = self._dw(w, '%s/separable_conv%d_depthwise' % (base, i + 1), EPS_BACKBONE)
+                    p['%s/pw%d' % (base, i)] = self._pw(w, '%s/separable_conv%d_pointwise' % (base, i + 1), EPS_BACKBONE)
+                if skip == 'conv':
+                    p[base + '/shortcut'] = self._pw(w, base + '/shortcut', EPS_BACKBONE)
+        p['image_pooling'] = self._pw(w, 'image_pooling', EPS_HEAD, keep_f32=True)   # M = batch: fp32 SIMT kernel
+        p['aspp0'] = self._pw(w, 'aspp0', EPS_HEAD)
+        for i in (1, 2, 3):
+            p['aspp%d_dw' % i] = self._dw(w, 'aspp%d_depthwise' % i, EPS_HEAD)
+            p['aspp%d_pw' % i] = self._pw(w, 'aspp%d_pointwise' % i, EPS_HEAD)
+        # concat_projection: input order [image_pooling, aspp0, aspp1, aspp2, aspp3] (model.py:233-256).
+        k, shift = self._conv_bn(w, 'concat_projection', EPS_HEAD)
+        wk = k[0, 0].T                                                      # [256, 1280]
+        p['concat_proj_img'] = Gemm(wk[:, :256], shift, self.dev, True)     # image-level part -> per-image bias
+        p['concat_proj'] = Gemm(wk[:, 256:], None, self.dev, self.keep_f32)
+        p['feature_projection0'] = self._pw(w, 'decoder/feature_projection0', EPS_HEAD)
+        for i in (0, 1):
+            p['decoder_conv%d_dw' % i] = self._dw(w, 'decoder/decoder_conv%d_depthwise' % i, EPS_HEAD)
+            p['decoder_conv%d_pw' % i] = self._pw(w, 'decoder/decoder_conv%d_pointwise' % i, EPS_HEAD)
+        for name in (PRED_OBJ_CONF, PRED_FRAG_CONF, PRED_FRAG_LOC):
+            k = np.asarray(w['logits/%s/weights' % name], np.float64)[0, 0].T
+            p['logits/' + name] = Gemm(k, w['logits/%s/biases' % name], self.dev, self.keep_f32)
+        self.p = p
+
+    # -- op wrappers ----------------------------------------------------------------------------------
+    def _s(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def dwconv(self, x, B, H, W, C, ldx, wb, stride, rate, relu_in, relu_out, want_f32=False):
+        Ho = H if stride == 1 else (H - 1) // 2 + 1
+        Wo = W if stride == 1 else (W - 1) // 2 + 1
+        y_split = torch.empty((2, B * Ho * Wo, C), dtype=torch.bfloat16, device=self.dev)
+        y32 = torch.empty((B * Ho * Wo, C), dtype=torch.float32, device=self.dev) if want_f32 else None
+        _lib.check(self.lib.epos_dwconv3x3(x.data_ptr(), ldx, wb[0].data_ptr(), wb[1].data_ptr(), _lib.ptr(y32),
+                                           y_split.data_ptr(), B, H, W, C, stride, rate, int(relu_in), int(relu_out),
+                                           self._s()), 'epos_dwconv3x3')
+        return (y_split, y32, Ho, Wo) if want_f32 else (y_split, Ho, Wo)
+
+    def split(self, x, B, H, W, C, ldx, subsample=1, relu=False):
+        Ho, Wo = (H - 1) // subsample + 1, (W - 1) // subsample + 1
+        y = torch.empty((2, B * Ho * Wo, C), dtype=torch.bfloat16, device=self.dev)
+        _lib.check(self.lib.epos_split_bf16(x.data_ptr(), ldx, y.data_ptr(), C, y[0].numel(), B, H, W, C, subsample,
+                                            int(relu), self._s()), 'epos_split_bf16')
+        return y
+
+    def gemm(self, a_split, g, M, relu, residual=None, out_f32=True, out_split=False, d_f32=None, ldd=None,
+             d_split=None, ldd_split=None, bias=None, bias_group_rows=0, a_f32=None):
+        """a_split [2,M,lda] bf16.  Returns (d_f32 or None, d_split or None)."""
+        lda = a_split.shape[2]
+        N, K = g.N, g.K
+        bias_t = g.bias if bias is None else bias
+        if out_f32 and d_f32 is None:
+            d_f32 = torch.empty((M, N), dtype=torch.float32, device=self.dev)
+            ldd = N
+        if out_split and d_split is None:
+            d_split = torch.empty((2, M, N), dtype=torch.bfloat16, device=self.dev)
+            ldd_split = N
+        plane = 0 if d_split is None else d_split.stride(0)
+        if self.impl == 'simt':
+            # fp32 validation path: reconstruct A from the split planes, run the SIMT GEMM, then split.
+            a32 = (a_split[0].float() + a_split[1].float()).contiguous()
+            tmp = d_f32 if d_f32 is not None else torch.empty((M, N), dtype=torch.float32, device=self.dev)
+            tl = ldd if d_f32 is not None else N
+            _lib.check(self.lib.epos_pwconv_simt(a32.data_ptr(), a32.shape[1], g.w_f32.data_ptr(), _lib.ptr(bias_t),
+                                                 bias_group_rows, _lib.ptr(residual),
+                                                 0 if residual is None else residual.shape[-1], tmp.data_ptr(), tl,
+                                                 M, N, K, int(relu), self._s()), 'epos_pwconv_simt')
+            if d_split is not None:
+                src = tmp if tl == N else torch.as_strided(tmp, (M, N), (tl, 1))
+                hi = src.to(torch.bfloat16)
+                torch.as_strided(d_split, (M, N), (ldd_split, 1), d_split.storage_offset()).copy_(hi)
+                torch.as_strided(d_split, (M, N), (ldd_split, 1), d_split.storage_offset() + plane).copy_(
+                    (src - hi.float()).to(torch.bfloat16))
+            return d_f32, d_split
+        _lib.check(self.lib.epos_pwconv_gemm(
+            a_split.data_ptr(), lda, a_split.stride(0), g.w_split.data_ptr(), _lib.ptr(bias_t), bias_group_rows,
+            _lib.ptr(residual), 0 if residual is None else residual.shape[-1],
+            _lib.ptr(d_f32), ldd or 0, _lib.ptr(d_split), ldd_split or 0, plane, M, N, K, int(relu), self._s()),
+            'epos_pwconv_gemm')
+        return d_f32, d_split
+
+    def small_fc(self, a, w_f32, bias, relu):
+        M, K = a.shape
+        N = w_f32.shape[0]
+        d = torch.empty((M, N), dtype=torch.float32, device=self.dev)
+        _lib.check(self.lib.epos_pwconv_simt(a.data_ptr(), K, w_f32.data_ptr(), _lib.ptr(bias), 0, None, 0,
+                                             d.data_ptr(), N, M, N, K, int(relu), self._s()), 'epos_pwconv_simt')
+        return d
+
+    # -- network --------------------------------------------------------------------------------------
+    def xception_module(self, x, B, H, W, cin, base, depths, skip, stride, rate, relu_inside):
+        """x: f32 [B*H*W, cin].  net_xception.py:198-323."""
+        r, c, h, w = x, cin, H, W
+        for i in range(3):
+            s = stride if i == 2 else 1
+            a, ho, wo = self.dwconv(r, B, h, w, c, c, self.p['%s/dw%d' % (base, i)], s, rate,
+                                    relu_in=not relu_inside, relu_out=relu_inside)
+            M = B * ho * wo
+            g = self.p['%s/pw%d' % (base, i)]
+            res = None
+            if i == 2 and skip == 'conv':
+                xs = self.split(x, B, H, W, cin, cin, subsample=stride)
+                res, _ = self.gemm(xs, self.p[base + '/shortcut'], M, relu=False)
+            elif i == 2 and skip == 'sum':
+                res = x
+            r, _ = self.gemm(a, g, M, relu=relu_inside, residual=res)
+            c, h, w = depths[i], ho, wo
+            self.end_points['%s/separable_conv%d_pointwise' % (base.replace(XC + '/', ''), i + 1)] = (r, h, w, c)
+        return r, h, w, c
+
+    def forward_features(self, images):
+        """images [B,H,W,3] f32 cuda in [0,255] -> decoder features (split-bf16 [2,M,256]) and (B,h,w)."""
+        lib, p = self.lib, self.p
+        B, H, W, _ = images.shape
+        images = images.contiguous()
+        self.end_points = {}
+        H1, W1 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        c1 = torch.empty((B * H1 * W1, 32), dtype=torch.float32, device=self.dev)
+        _lib.check(lib.epos_conv3x3_rgb_s2(images.data_ptr(), p['conv1_1'][0].data_ptr(), p['conv1_1'][1].data_ptr(),
+                                           c1.data_ptr(), B, H, W, 32, self._s()), 'epos_conv3x3_rgb_s2')
+        c2 = torch.empty((B * H1 * W1, 64), dtype=torch.float32, device=self.dev)
+        _lib.check(lib.epos_conv3x3_dense(c1.data_ptr(), p['conv1_2'][0].data_ptr(), p['conv1_2'][1].data_ptr(),
+                                          c2.data_ptr(), B, H1, W1, 32, 64, self._s()), 'epos_conv3x3_dense')
+        x, h, w, c = c2, H1, W1, 64
+        target = self.opts.encoder_output_stride // 2              # net_xception.py:455-458
+        current_stride, rate = 1, 1
+        for scope, depths, skip, units in XCEPTION65_BLOCKS:
+            stride = _BLOCK_STRIDES[scope]
+            for u in range(1, units + 1):
+                base = '%s/%s/unit_%d/xception_module' % (XC, scope, u)
+                if current_stride == target:                       # net_xception.py:374-385
+                    x, h, w, c = self.xception_module(x, B, h, w, c, base, depths, skip, 1, rate, scope in _RELU_INSIDE)
+                    rate *= stride
+                else:
+                    x, h, w, c = self.xception_module(x, B, h, w, c, base, depths, skip, stride, 1, scope in _RELU_INSIDE)
+                    current_stride *= stride
+        self.end_points['backbone'] = (x, h, w, c)
+        # ---- ASPP (model.py:217-258) ----
+        M = B * h * w
+        pooled = torch.empty((B, c), dtype=torch.float32, device=self.dev)
+        _lib.check(lib.epos_global_mean(x.data_ptr(), pooled.data_ptr(), B, h * w, c, self._s()), 'epos_global_mean')
+        ip = self.small_fc(pooled, p['image_pooling'].w_f32, p['image_pooling'].bias, relu=True)       # [B,256]
+        cp_bias = self.small_fc(ip, p['concat_proj_img'].w_f32, p['concat_proj_img'].bias, relu=False)  # [B,256]
+        nb = 1 + len(self.opts.atrous_rates)
+        cat = torch.empty((2, M, 256 * nb), dtype=torch.bfloat16, device=self.dev)
+        xs = self.split(x, B, h, w, c, c)
+        self.gemm(xs, p['aspp0'], M, relu=True, out_f32=False, d_split=cat, ldd_split=256 * nb)
+        for i, r_ in enumerate(self.opts.atrous_rates, 1):
+            a, _, _ = self.dwconv(x, B, h, w, c, c, p['aspp%d_dw' % i], 1, r_, relu_in=False, relu_out=True)
+            self.gemm(a, p['aspp%d_pw' % i], M, relu=True, out_f32=False, d_split=cat[:, :, 256 * i:],
+                      ldd_split=256 * nb)
+        aspp, _ = self.gemm(cat, p['concat_proj'], M, relu=True, bias=cp_bias, bias_group_rows=h * w)
+        self.end_points['aspp'] = (aspp, h, w, 256)
+        # ---- decoder (model.py:325-380) ----
+        skip, sh, sw, sc = self.end_points[DECODER_END_POINT]
+        dstride = self.opts.decoder_output_stride[0]
+        dw_ = scale_dimension(W, 1.0 / dstride)     # crop_size == image size at inference (infer.py:650-654)
+        dh_ = scale_dimension(H, 1.0 / dstride)
+        if (sh, sw) != (dh_, dw_):
+            raise NotImplementedError('skip feature %dx%d != decoder size %dx%d' % (sh, sw, dh_, dw_))
+        Md = B * dh_ * dw_
+        dcat = torch.empty((Md, 304), dtype=torch.float32, device=self.dev)
+        ss = self.split(skip, B, sh, sw, sc, sc)
+        self.gemm(ss, p['feature_projection0'], Md, relu=True, d_f32=dcat[:, 256:], ldd=304)
+        _lib.check(lib.epos_resize_bilinear(aspp.data_ptr(), dcat.data_ptr(), 304, B, h, w, dh_, dw_, 256, self._s()),
+                   'epos_resize_bilinear')
+        a, _, _ = self.dwconv(dcat, B, dh_, dw_, 304, 304, p['decoder_conv0_dw'], 1, 1, False, True)
+        y0, _ = self.gemm(a, p['decoder_conv0_pw'], Md, relu=True)
+        a, _, _ = self.dwconv(y0, B, dh_, dw_, 256, 256, p['decoder_conv1_dw'], 1, 1, False, True)
+        y1, y1s = self.gemm(a, p['decoder_conv1_pw'], Md, relu=True, out_f32=self.keep_f32, out_split=True)
+        self.end_points['decoder'] = (y1, dh_, dw_, 256)
+        return y1s, B, dh_, dw_
+
+    def heads(self, feat_split, B, h, w):
+        """Logit heads + softmax/argmax in materialising mode (model.py:448-456, 676-685)."""
+        M = B * h * w
+        O, F = self.O, self.F
+        obj, _ = self.gemm(feat_split, self.p['logits/' + PRED_OBJ_CONF], M, relu=False)
+        fc, _ = self.gemm(feat_split, self.p['logits/' + PRED_FRAG_CONF], M, relu=False)
+        fl, _ = self.gemm(feat_split, self.p['logits/' + PRED_FRAG_LOC], M, relu=False)
+        labels = torch.empty((M,), dtype=torch.int64, device=self.dev)
+        _lib.check(self.lib.epos_softmax_rows(obj.data_ptr(), labels.data_ptr(), M, O + 1, self._s()), 'epos_softmax_rows')
+        _lib.check(self.lib.epos_softmax_rows(fc.data_ptr(), None, M * O, F, self._s()), 'epos_softmax_rows')
+        return {PRED_OBJ_CONF: obj.view(B, h, w, O + 1), PRED_OBJ_LABEL: labels.view(B, h, w),
+                PRED_FRAG_CONF: fc.view(B, h, w, O, F), PRED_FRAG_LOC: fl.view(B, h, w, O, F, 3)}
+
+    def predict(self, images):
+        feat, B, h, w = self.forward_features(images)
+        return self.heads(feat, B, h, w)
+
+
+_NETS = {}
+
+
+def predict(images, model_options=None, upsample_logits=False, image_pyramid=None, num_objs=None, num_frags=None,
+            frag_cls_agnostic=False, frag_loc_agnostic=False, weights=None, net=None):
+    """Signature of model.predict (model.py:629-687) + `weights`/`net` (the reference reads variables from
+    the TF graph; here they are passed explicitly).  Returns a dict of torch CUDA tensors."""
+    if upsample_logits or image_pyramid or frag_cls_agnostic or frag_loc_agnostic:
+        raise NotImplementedError('only the default inference configuration of scripts/infer.py is built')
+    if net is None:
+        key = id(weights)
+        if key not in _NETS:
+            _NETS[key] = EposNet(weights, num_objs, num_frags, images.device, model_options)
+        net = _NETS[key]
+    return net.predict(images)

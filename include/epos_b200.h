@@ -1,0 +1,163 @@
+/*
+ * epos_b200.h -- C ABI of the B200-native EPOS inference hot path.
+ *
+ * The reference (thodan/epos) has no FFI for this path except the pybind11 module
+ * `pyprogressivex`; everything else is Python calling TensorFlow-1.12 graph ops.  Each entry point
+ * below replaces the reference interface cited next to it and is what a maintainer would bind
+ * (ctypes stub in INTEGRATION.md).  Conventions:
+ *   - plain pointers and sizes only; all tensor pointers are DEVICE pointers unless named *_host;
+ *   - the caller owns every buffer, the library never frees caller memory;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), except where noted;
+ *   - return 0 on success, negative epos_status otherwise; never throws; epos_last_error() gives text;
+ *   - activations are NHWC, fp32, or "split-bf16": two bf16 planes [2][rows][ld] (hi, lo) with
+ *     value = float(hi) + float(lo) (the operand format of the error-compensated tensor-core GEMM).
+ */
+#ifndef EPOS_B200_H_
+#define EPOS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  EPOS_OK = 0,
+  EPOS_ERR_INVALID_ARG = -1,
+  EPOS_ERR_CUDA = -2,
+  EPOS_ERR_UNSUPPORTED = -3,
+  EPOS_ERR_NO_DEVICE = -4
+} epos_status;
+
+/* Text of the last error on the calling thread. */
+const char* epos_last_error(void);
+/* Library/ABI version, compiled arch (100 for sm_100a). */
+int epos_version(void);
+int epos_compiled_arch(void);
+/* Number of kernels launched by this library since load (bench.py's gpu_launches). */
+uint64_t epos_launch_count(void);
+
+/* ---- CNN ops: replace the TF ops built by model.predict (epos_lib/model.py:629-687) ---------------- */
+
+/* entry_flow/conv1_1: (2/255)x-1 preprocessing (feature.py:171-174) + 3x3 stride-2 conv with explicit
+ * padding (resnet_utils.conv2d_same, external/slim/nets/resnet_utils.py:77-122) + folded BN + ReLU.
+ * x [B,H,W,3] f32 in [0,255]; w [3][3][3][Cout] (HWIO, BN scale folded); y [B,H/2,W/2,Cout] f32. */
+int epos_conv3x3_rgb_s2(const float* x, const float* w, const float* bias, float* y,
+                        int B, int H, int W, int Cout, void* stream);
+
+/* Dense 3x3 stride-1 SAME conv + folded BN + ReLU (entry_flow/conv1_2).  w [3][3][Cin][Cout]. */
+int epos_conv3x3_dense(const float* x, const float* w, const float* bias, float* y,
+                       int B, int H, int W, int Cin, int Cout, void* stream);
+
+/* Depthwise 3x3 conv (net_xception.py:167-177 separable_conv2d_same depthwise half; model.py:80-89):
+ * optional ReLU on the input (xception_module pre-activation, net_xception.py:276), dilation `rate`,
+ * stride 1 (TF SAME) or 2 (fixed_padding then VALID), folded BN bias, optional ReLU on the output.
+ * x [B,H,W,ldx] f32 (first C channels used); w [9][C] f32; y_f32 [B,Ho,Wo,C] and/or y_split [2][B*Ho*Wo][C]
+ * (either may be NULL). */
+int epos_dwconv3x3(const float* x, int ldx, const float* w, const float* bias,
+                   float* y_f32, uint16_t* y_split,
+                   int B, int H, int W, int C, int stride, int rate, int relu_in, int relu_out,
+                   void* stream);
+
+/* Pointwise (1x1) convolution = GEMM on tcgen05 tensor cores with split-bf16 operands (3 MMAs per
+ * product: hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM):
+ *   D[m][n] = act( sum_k A[m][k] * Wt[n][k] + bias[(m / bias_group_rows)][n] ) (+ residual[m][n])
+ * Replaces slim.conv2d 1x1 + BatchNorm (+ReLU) (+ residual add), net_xception.py:178-182,297-313,
+ * model.py:90-97,223-258,350-352,448-456.
+ * a_split [2][M][lda] bf16; w_split [2][N][K] bf16; bias [groups][N] f32 (bias_group_rows = 0: one row);
+ * residual f32 with leading dim ldr or NULL; outputs: d_f32 (leading dim ldd) and/or d_split
+ * ([2][M][ldd_split], plane stride = split_plane_stride elements), either may be NULL. */
+int epos_pwconv_gemm(const uint16_t* a_split, int lda, size_t a_plane_stride,
+                     const uint16_t* w_split, const float* bias, int bias_group_rows,
+                     const float* residual, int ldr,
+                     float* d_f32, int ldd,
+                     uint16_t* d_split, int ldd_split, size_t d_plane_stride,
+                     int M, int N, int K, int relu, void* stream);
+
+/* Same contract computed by an fp32 SIMT kernel from f32 operands (validation / tiny shapes):
+ * a [M][lda] f32, w [N][K] f32. */
+int epos_pwconv_simt(const float* a, int lda, const float* w, const float* bias, int bias_group_rows,
+                     const float* residual, int ldr, float* d, int ldd,
+                     int M, int N, int K, int relu, void* stream);
+
+/* f32 -> split-bf16 conversion, optional spatial stride-2 subsample (for the stride-2 1x1 shortcut
+ * convs, net_xception.py:297-302) and optional ReLU.  x [B,H,W,ldx] (first C channels). */
+int epos_split_bf16(const float* x, int ldx, uint16_t* y_split, int ldy, size_t y_plane_stride,
+                    int B, int H, int W, int C, int subsample, int relu, void* stream);
+
+/* Global average pool over the spatial axes (model.py:220). x [B,HW,C] -> y [B,C]. */
+int epos_global_mean(const float* x, float* y, int B, int HW, int C, void* stream);
+
+/* tf.image.resize_bilinear(align_corners=True) (misc.py:94-107) of x [B,Hi,Wi,C] into channels
+ * [0,C) of y [B,Ho,Wo,ldy]. */
+int epos_resize_bilinear(const float* x, float* y, int ldy, int B, int Hi, int Wi, int Ho, int Wo, int C,
+                         void* stream);
+
+/* Softmax over the last axis, in place (model.py:676-678); rows x n.  If labels != NULL also writes
+ * argmax as int64 (model.py:683). */
+int epos_softmax_rows(float* x, int64_t* labels, size_t rows, int n, void* stream);
+
+/* ---- correspondences: replaces corresp.establish_many_to_many (epos_lib/corresp.py:9-101) and the
+ * top-K selection of scripts/infer.py:425-440 ------------------------------------------------------ */
+
+/* For every (image b, object slot j): pixels with obj_conf[b,p,obj_ids[j]] > min_obj_conf, fragments with
+ * frag_conf > min_frag_rel_conf * max_f; emits rows in row-major pixel then fragment order.
+ * Outputs per (b,j) segment of capacity `cap`: coord_2d [cap][2] f64, coord_3d [cap][3] f64, conf [cap] f32,
+ * conf_obj, conf_frag f32, px [cap] i32 (linear output pixel), frag [cap] i32; counts[b*J+j] = N (untruncated
+ * count; rows beyond cap are dropped and must be treated as an error by the caller unless top-K is used).
+ * If max_corr > 0 the segment is reduced to the max_corr most confident rows in descending confidence
+ * (ties: descending emission index), as np.argsort(conf)[::-1][:max_corr].
+ * frag_centers [num_objs][F][3] f64, frag_sizes [num_objs][F] f64 indexed by obj_id-1. */
+int epos_corresp(const float* obj_conf, const float* frag_conf, const float* frag_loc,
+                 int B, int h, int w, int num_objs, int num_frags,
+                 const int32_t* obj_ids, int J,
+                 const double* frag_centers, const double* frag_sizes,
+                 double output_scale, float min_obj_conf, float min_frag_rel_conf,
+                 int cap, int max_corr,
+                 double* coord_2d, double* coord_3d, float* conf, float* conf_obj, float* conf_frag,
+                 int32_t* px, int32_t* frag, int32_t* counts,
+                 void* workspace, size_t workspace_bytes, void* stream);
+size_t epos_corresp_workspace_bytes(int B, int J, int cap);
+
+/* ---- pose fitting: replaces pyprogressivex.find6DPoses
+ * (external/progressive-x/src/pyprogressivex/src/bindings.cpp:9-118, progressivex_python.cpp:36-336),
+ * single-instance branch (GC-RANSAC + final LM), batched over P independent problems. --------------- */
+typedef struct {
+  double threshold;                  /* inlier threshold in px (infer.py inlier_thresh, 4.0) */
+  double spatial_coherence_weight;   /* 0.1 */
+  double neighborhood_ball_radius;   /* 20.0 */
+  double scaling_from_millimeters;   /* 0.1 */
+  double min_triangle_area;          /* 0.0 */
+  double min_coverage;               /* 0.5 */
+  int32_t max_iters;                 /* 400 */
+  int32_t min_iters;                 /* 10  (progressivex_python.cpp:230) */
+  int32_t min_iters_before_lo;       /* 20  (settings.h:80) */
+  int32_t max_lo_trials;             /* 20  (progressivex_python.cpp:228) */
+  int32_t max_graph_cuts;            /* 10  (settings.h:78) */
+  int32_t max_lsq_iters;             /* 10  (settings.h:79) */
+  int32_t max_unsuccessful;          /* 100 (settings.h:85) */
+  int32_t max_neighbors;             /* 5: deterministic stand-in for FLANN checks=6 */
+  int32_t apply_numerical_optimization; /* 1 */
+  int32_t reserved;
+} epos_fit_params;
+
+void epos_fit_params_default(epos_fit_params* p);
+
+/* One record per problem: pose[12] row-major [R|t], then n_inliers, iterations, valid, graph_cuts. */
+#define EPOS_POSE_RECORD_DOUBLES 16
+
+/* P problems; problem i owns rows [offsets[i], offsets[i]+counts[i]) of coord_2d [*,2] / coord_3d [*,3]
+ * (f64, device).  K [P][9] f64 row-major.  seeds [P] u64: RANSAC stream key (counter-based generator).
+ * Outputs: poses [P][16] f64, labeling [total rows] i32 (1 = inlier). */
+int epos_fit_poses(const double* coord_2d, const double* coord_3d,
+                   const int32_t* offsets, const int32_t* counts, int P,
+                   const double* K, const uint64_t* seeds, const epos_fit_params* params,
+                   double* poses, int32_t* labeling,
+                   void* workspace, size_t workspace_bytes, void* stream);
+size_t epos_fit_workspace_bytes(int P, int max_points, const epos_fit_params* params);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPOS_B200_H_ */

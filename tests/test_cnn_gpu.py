@@ -1,0 +1,216 @@
+"""GPU parity tests of the CNN kernels against the oracle (oracle/cnn.py), through the C ABI.
+
+Tolerance (north_star): output maps within 1e-3 relative (to the per-tensor max-abs) of the f32 oracle."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    b = np.asarray(b, np.float64)
+    return float(np.abs(np.asarray(a, np.float64) - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope='module')
+def env():
+    from epos_b200 import _lib
+    return _lib.lib(), torch.device('cuda:0')
+
+
+def split(t):
+    hi = t.to(torch.bfloat16)
+    return torch.stack([hi, (t - hi.float()).to(torch.bfloat16)]).contiguous()
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (300, 256, 128), (4800, 728, 728), (1000, 22, 256),
+                                   (777, 48, 256), (2500, 1344, 256), (600, 256, 1280), (384, 1024, 2048),
+                                   (129, 304, 304)])
+@pytest.mark.parametrize('mode', ['plain', 'relu_res', 'split_out'])
+def test_pw_gemm(env, M, N, K, mode):
+    from epos_b200 import _lib
+    lib, dev = env
+    g = torch.Generator(device='cpu').manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, generator=g).to(dev)
+    w = (torch.randn(N, K, generator=g) * 0.1).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    res = torch.randn(M, N, generator=g).to(dev) if mode == 'relu_res' else None
+    relu = mode != 'plain'
+    ref = a.double() @ w.double().T + bias.double()
+    if relu:
+        ref = ref.clamp_min(0)
+    if res is not None:
+        ref = ref + res.double()
+    a_s, w_s = split(a), split(w)
+    d = torch.full((M, N), float('nan'), device=dev) if mode != 'split_out' else None
+    ds = torch.zeros((2, M, N), dtype=torch.bfloat16, device=dev) if mode == 'split_out' else None
+    rc = lib.epos_pwconv_gemm(a_s.data_ptr(), K, a_s.stride(0), w_s.data_ptr(), bias.data_ptr(), 0,
+                              _lib.ptr(res), N, _lib.ptr(d), N, _lib.ptr(ds), N, 0 if ds is None else ds.stride(0),
+                              M, N, K, int(relu), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, 'gemm')
+    torch.cuda.synchronize()
+    got = d if d is not None else ds[0].float() + ds[1].float()
+    tol = 2e-5 if d is not None else 5e-5
+    assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) < tol
+
+
+def test_pw_gemm_grouped_bias_and_slices(env):
+    """per-image bias rows (image-pooling fold) and strided output slices (concat buffers)."""
+    from epos_b200 import _lib
+    lib, dev = env
+    M, N, K, G = 960, 48, 256, 4
+    a = torch.randn(M, K, device=dev)
+    w = torch.randn(N, K, device=dev) * 0.05
+    bias = torch.randn(G, N, device=dev)
+    buf = torch.zeros(M, 304, device=dev)
+    a_s, w_s = split(a), split(w)
+    rc = lib.epos_pwconv_gemm(a_s.data_ptr(), K, a_s.stride(0), w_s.data_ptr(), bias.data_ptr(), M // G, None, 0,
+                              buf[:, 256:].data_ptr(), 304, None, 0, 0, M, N, K, 1,
+                              torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, 'gemm')
+    ref = (a.double() @ w.double().T + bias.double().repeat_interleave(M // G, 0)).clamp_min(0)
+    assert rel_err(buf[:, 256:].cpu().numpy(), ref.cpu().numpy()) < 2e-5
+    assert float(buf[:, :256].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('C,H,W,stride,rate,relu_in,relu_out', [
+    (64, 24, 32, 1, 1, True, False), (128, 24, 32, 2, 1, True, False), (728, 15, 20, 1, 2, True, False),
+    (1024, 15, 20, 1, 4, False, True), (2048, 15, 20, 1, 12, False, True), (304, 30, 40, 1, 1, False, True),
+    (256, 9, 11, 2, 1, True, False), (2048, 15, 20, 1, 36, False, True)])
+def test_dwconv(env, C, H, W, stride, rate, relu_in, relu_out):
+    from epos_b200 import _lib
+    from oracle import cnn
+    lib, dev = env
+    B = 2
+    rng = np.random.default_rng(C + rate)
+    x = rng.standard_normal((B, H, W, C)).astype(np.float32)
+    k = rng.standard_normal((3, 3, C, 1)).astype(np.float32)
+    b = rng.standard_normal(C).astype(np.float32)
+    o = cnn.Oracle({'s/depthwise_weights': k})
+    xt = torch.from_numpy(x).permute(0, 3, 1, 2)
+    if relu_in:
+        xt = xt.clamp_min(0)
+    if stride == 1:
+        y = o.depthwise(xt, 's', 1, rate, 'SAME')
+    else:
+        y = o.depthwise(o.fixed_padding(xt, 3, rate), 's', stride, rate, 'VALID')
+    y = y + torch.from_numpy(b).view(1, -1, 1, 1)
+    if relu_out:
+        y = y.clamp_min(0)
+    ref = y.permute(0, 2, 3, 1).numpy()
+    Ho, Wo = ref.shape[1:3]
+    xd = torch.from_numpy(x).to(dev)
+    wd = torch.from_numpy(k[:, :, :, 0].reshape(9, C).copy()).to(dev)
+    bd = torch.from_numpy(b).to(dev)
+    y32 = torch.empty((B * Ho * Wo, C), device=dev)
+    ys = torch.empty((2, B * Ho * Wo, C), dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.epos_dwconv3x3(xd.data_ptr(), C, wd.data_ptr(), bd.data_ptr(), y32.data_ptr(), ys.data_ptr(), B, H, W,
+                                  C, stride, rate, int(relu_in), int(relu_out),
+                                  torch.cuda.current_stream().cuda_stream), 'dw')
+    torch.cuda.synchronize()
+    assert rel_err(y32.cpu().numpy().reshape(ref.shape), ref) < 1e-5
+    assert rel_err((ys[0].float() + ys[1].float()).cpu().numpy().reshape(ref.shape), ref) < 3e-5
+
+
+def test_entry_convs(env):
+    from epos_b200 import _lib, weights as W
+    from oracle import cnn
+    lib, dev = env
+    w = {k: v for k, v in W.random_init(1, 1, seed=5, bn='random').items() if 'entry_flow/conv1_' in k}
+    img = W.synthetic_images(2, seed=5, height=64, width=96)
+    o = cnn.Oracle(w)
+    x = torch.from_numpy(img).permute(0, 3, 1, 2)
+    x = (2.0 / 255.0) * x - 1.0
+    r1 = o.conv2d_same(x, 'xception_65/entry_flow/conv1_1', 2)
+    r2 = o.conv2d_same(r1, 'xception_65/entry_flow/conv1_2', 1)
+    from epos_b200.model import EposNet, _bn_fold
+    def fold(scope):
+        k = np.asarray(w[scope + '/weights'], np.float64)
+        s, sh = _bn_fold(w, scope, 1e-3)
+        return (torch.from_numpy((k * s).astype(np.float32)).to(dev), torch.from_numpy(sh.astype(np.float32)).to(dev))
+    k1, b1 = fold('xception_65/entry_flow/conv1_1')
+    k2, b2 = fold('xception_65/entry_flow/conv1_2')
+    xd = torch.from_numpy(img).to(dev)
+    c1 = torch.empty((2, 32, 48, 32), device=dev)
+    c2 = torch.empty((2, 32, 48, 64), device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.epos_conv3x3_rgb_s2(xd.data_ptr(), k1.data_ptr(), b1.data_ptr(), c1.data_ptr(), 2, 64, 96, 32, s), 'c1')
+    _lib.check(lib.epos_conv3x3_dense(c1.data_ptr(), k2.data_ptr(), b2.data_ptr(), c2.data_ptr(), 2, 32, 48, 32, 64, s), 'c2')
+    torch.cuda.synchronize()
+    assert rel_err(c1.cpu().numpy(), r1.permute(0, 2, 3, 1).numpy()) < 1e-5
+    assert rel_err(c2.cpu().numpy(), r2.permute(0, 2, 3, 1).numpy()) < 1e-5
+
+
+def test_resize_mean_softmax(env):
+    from epos_b200 import _lib
+    import torch.nn.functional as F
+    lib, dev = env
+    s = torch.cuda.current_stream().cuda_stream
+    x = torch.randn(2, 15, 20, 256, device=dev)
+    y = torch.zeros(2, 30, 40, 304, device=dev)
+    _lib.check(lib.epos_resize_bilinear(x.data_ptr(), y.data_ptr(), 304, 2, 15, 20, 30, 40, 256, s), 'rs')
+    ref = F.interpolate(x.permute(0, 3, 1, 2), size=(30, 40), mode='bilinear', align_corners=True).permute(0, 2, 3, 1)
+    assert rel_err(y[..., :256].cpu().numpy(), ref.cpu().numpy()) < 1e-5
+    assert float(y[..., 256:].abs().max()) == 0
+    m = torch.empty(2, 256, device=dev)
+    _lib.check(lib.epos_global_mean(x.data_ptr(), m.data_ptr(), 2, 300, 256, s), 'mean')
+    assert rel_err(m.cpu().numpy(), x.view(2, 300, 256).mean(1).cpu().numpy()) < 1e-5
+    for n in (2, 22, 64, 256):
+        z = torch.randn(1000, n, device=dev) * 3
+        ref = torch.softmax(z, -1)
+        lab = torch.empty(1000, dtype=torch.int64, device=dev)
+        _lib.check(lib.epos_softmax_rows(z.data_ptr(), lab.data_ptr(), 1000, n, s), 'sm')
+        assert rel_err(z.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+        assert (lab == ref.argmax(-1)).float().mean() > 0.999
+
+
+def _net_parity(B, H, W, O, F, seed, check_simt=False):
+    from epos_b200 import model, weights as Wt
+    from oracle import cnn
+    dev = torch.device('cuda:0')
+    w = Wt.random_init(O, F, seed=seed, bn='random', logits_std=0.5)
+    img = Wt.synthetic_images(B, seed=seed, height=H, width=W)
+    net = model.EposNet(w, O, F, dev, keep_f32=True)
+    out = net.predict(torch.from_numpy(img).to(dev))
+    torch.cuda.synchronize()
+    ref = cnn.predict(w, img, O, F, return_features=True)
+    errs = {}
+    for name, key in (('backbone', '_backbone'), ('aspp', '_aspp'), ('decoder', '_decoder')):
+        t, h, w_, c = net.end_points[name]
+        errs[name] = rel_err(t.cpu().numpy().reshape(ref[key].shape), ref[key])
+    for k in (model.PRED_OBJ_CONF, model.PRED_FRAG_CONF, model.PRED_FRAG_LOC):
+        assert out[k].shape == ref[k].shape and out[k].dtype == torch.float32
+        errs[k] = rel_err(out[k].cpu().numpy(), ref[k])
+    lab = out[model.PRED_OBJ_LABEL]
+    assert lab.dtype == torch.int64 and lab.shape == ref['pred_obj_label'].shape
+    errs['label_agree'] = float((lab.cpu().numpy() == ref['pred_obj_label']).mean())
+    print(errs)
+    for k, v in errs.items():
+        if k == 'label_agree':
+            assert v > 0.999
+        else:
+            assert v < 1e-3, (k, v)
+    if check_simt:
+        net.impl = 'simt'
+        out2 = net.predict(torch.from_numpy(img).to(dev))
+        for k in (model.PRED_FRAG_LOC, model.PRED_OBJ_CONF):
+            assert rel_err(out2[k].cpu().numpy(), ref[k]) < 1e-3
+
+
+def test_network_small():
+    _net_parity(2, 96, 128, 3, 8, seed=11, check_simt=True)
+
+
+def test_network_odd_size():
+    _net_parity(1, 81, 113, 1, 4, seed=12)
+
+
+def test_network_full_size_c1():
+    """BASELINE config 1: single 640x480 image, 1 object / 64 fragments."""
+    _net_parity(1, 480, 640, 1, 64, seed=13)
+
+
+def test_network_full_size_ycbv_heads():
+    """21 objects x 64 fragments (YCB-V-shaped heads), batch 2."""
+    _net_parity(2, 480, 640, 21, 64, seed=14)
