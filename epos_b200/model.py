@@ -88,6 +88,7 @@ class EposNet:
         self.keep_f32 = keep_f32
         self.impl = 'tcgen05'            # 'simt' = fp32 validation path (needs keep_f32=True)
         self.end_points = {}
+        self.gemm_events = None          # bench.py: list collecting (start, stop, M, N, K) per tcgen05 GEMM launch
         self._prepare(weights)
 
     # -- weight preparation ---------------------------------------------------------------------------
@@ -191,11 +192,18 @@ class EposNet:
                 torch.as_strided(d_split, (M, N), (ldd_split, 1), d_split.storage_offset() + plane).copy_(
                     (src - hi.float()).to(torch.bfloat16))
             return d_f32, d_split
+        ev = None
+        if self.gemm_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         _lib.check(self.lib.epos_pwconv_gemm(
             a_split.data_ptr(), lda, a_split.stride(0), g.w_split.data_ptr(), _lib.ptr(bias_t), bias_group_rows,
             _lib.ptr(residual), 0 if residual is None else residual.shape[-1],
             _lib.ptr(d_f32), ldd or 0, _lib.ptr(d_split), ldd_split or 0, plane, M, N, K, int(relu), self._s()),
             'epos_pwconv_gemm')
+        if ev is not None:
+            ev[1].record()
+            self.gemm_events.append((ev[0], ev[1], M, N, K))
         return d_f32, d_split
 
     def small_fc(self, a, w_f32, bias, relu):
