@@ -37,8 +37,9 @@ _SIGS = {
     'epos_resize_bilinear': (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
     'epos_softmax_rows': (i32, [vp, vp, sz, i32, vp]),
     'epos_corresp': (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, f64, f32, f32, i32, i32,
-                           vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
-    'epos_corresp_workspace_bytes': (sz, [i32, i32, i32]),
+                           vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    'epos_corresp_workspace_bytes': (sz, [i32, i32, i32, i32]),
+    'epos_fit_max_points': (i32, []),
     'epos_fit_params_default': (None, [C.POINTER(FitParams)]),
     'epos_fit_poses': (i32, [vp, vp, vp, vp, i32, vp, vp, C.POINTER(FitParams), vp, vp, vp, sz, vp]),
     'epos_fit_workspace_bytes': (sz, [i32, i32, C.POINTER(FitParams)]),

@@ -1,0 +1,290 @@
+// 2D-3D correspondence extraction on sm_100a: establish_many_to_many (/root/reference/epos_lib/corresp.py:9-101)
+// plus the confidence top-K of scripts/infer.py:425-440, for every (image, object slot) segment of a batch.
+//
+// One CTA per segment.  HBM-bound: the segment's obj_conf column and, for masked pixels only, the F-float frag_conf row
+// (one coalesced 256-byte read per warp at F = 64) and 12 bytes of frag_loc per emitted row.
+//   phase 1  warp per pixel: obj_conf > tau_a, row max, frag_conf > tau_b * max  -> per-pixel counts -> block scan
+//            (row-major pixel, then fragment: the emission order of the reference)
+//   phase 2  (only if the segment has more than max_corr rows) radix select of the max_corr largest 64-bit keys
+//            (conf bits << 32 | emission index), i.e. np.argsort(conf)[::-1][:K] with ties by descending index,
+//            then a shared-memory bitonic sort of the K survivors
+//   phase 3  rows: coord_2d = (x + 0.5, y + 0.5) / output_scale (misc.py:14-26), coord_3d = centre[f] +
+//            f32(loc * size[f]) (corresp.py:70-78), conf = obj_conf * frag_conf
+#include "common.cuh"
+
+namespace epos {
+
+constexpr int CT = 1024;            // threads per CTA
+constexpr int CW = CT / 32;
+constexpr int MAXF = 512;           // fragments per object supported (registers: MAXF / 32 per lane)
+constexpr int SORT_MAX = 4096;      // max_corr supported by the in-kernel sort
+
+struct CorrArgs {
+  const float* obj_conf; const float* frag_conf; const float* frag_loc;
+  int B, h, w, O, F;
+  const int* obj_ids; int J;
+  const double* centers; const double* sizes;
+  double inv_scale; float min_obj_conf, min_rel;
+  int cap, max_corr;
+  double* c2d; double* c3d; float* conf; float* conf_obj; float* conf_frag; int* px; int* frag; int* counts; int* totals;
+  unsigned int* off;               // workspace [B*J][HW+1]
+};
+
+__device__ inline int block_scan_excl(int v, int* sh, int* total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) sh[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    int s = lane < CW ? sh[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += y;
+    }
+    if (lane < CW) sh[lane] = s;
+  }
+  __syncthreads();
+  const int base = w > 0 ? sh[w - 1] : 0;
+  *total = sh[CW - 1];
+  __syncthreads();
+  return base + x - v;
+}
+
+// Visits every candidate row of the segment in parallel (warp per masked pixel).  fn(p, f, e, vobj, vfrag, lane-local)
+// is called by the lane that owns fragment f with e = emission index.  If COUNT, per-pixel counts are written to off[].
+template <bool COUNT, class Fn>
+__device__ inline void for_each_candidate(const CorrArgs& a, int b, int obj_id, unsigned int* off, Fn fn) {
+  const int HW = a.h * a.w, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* oc = a.obj_conf + (size_t)b * HW * (a.O + 1) + obj_id;
+  const float* fcb = a.frag_conf + ((size_t)b * HW * a.O + (obj_id - 1)) * a.F;
+  const int nf = (a.F + 31) >> 5;
+  for (int p0 = warp * 32; p0 < HW; p0 += CW * 32) {
+    const int pl = p0 + lane;
+    float v = 0.f;
+    bool m = false;
+    if (pl < HW) {
+      v = __ldg(oc + (size_t)pl * (a.O + 1));
+      m = v > a.min_obj_conf;                                   // corresp.py:46-47
+      if (!COUNT) m = m && (off[pl + 1] > off[pl]);
+    }
+    unsigned int mask = __ballot_sync(0xffffffffu, m);
+    if (COUNT && pl < HW && !m) off[pl] = 0u;
+    while (mask) {
+      const int l = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int p = p0 + l;
+      const float vobj = __shfl_sync(0xffffffffu, v, l);
+      const float* row = fcb + (size_t)p * a.O * a.F;
+      float r[MAXF / 32];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < MAXF / 32; ++k)
+        if (k < nf) {
+          const int f = k * 32 + lane;
+          r[k] = f < a.F ? __ldg(row + f) : -INFINITY;
+          mx = fmaxf(mx, r[k]);
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float thr = __fmul_rn(mx, a.min_rel);                // corresp.py:62-64 (float32 product)
+      int run = 0;
+      const unsigned int base = COUNT ? 0u : off[p];
+#pragma unroll
+      for (int k = 0; k < MAXF / 32; ++k)
+        if (k < nf) {
+          const int f = k * 32 + lane;
+          const bool sel = f < a.F && r[k] > thr;
+          const unsigned int bm = __ballot_sync(0xffffffffu, sel);
+          if (!COUNT && sel) fn(p, f, base + run + __popc(bm & ((1u << lane) - 1u)), vobj, r[k]);
+          run += __popc(bm);
+        }
+      if (COUNT && lane == 0) off[p] = (unsigned int)run;
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned long long make_key(float vobj, float vfrag, unsigned int e) {
+  const float c = __fmul_rn(vobj, vfrag);                        // corresp.py:95 conf = conf_obj * conf_frag (f32)
+  return ((unsigned long long)__float_as_uint(c) << 32) | (unsigned long long)e;
+}
+
+__device__ inline void write_row(const CorrArgs& a, int b, int obj_id, size_t dst, int p, int f, float vobj, float vfrag) {
+  const int x = p % a.w, y = p / a.w;
+  a.c2d[2 * dst] = a.inv_scale * ((double)x + 0.5);
+  a.c2d[2 * dst + 1] = a.inv_scale * ((double)y + 0.5);
+  const int HW = a.h * a.w;
+  const float* loc = a.frag_loc + ((((size_t)b * HW + p) * a.O + (obj_id - 1)) * a.F + f) * 3;
+  const double* cen = a.centers + ((size_t)(obj_id - 1) * a.F + f) * 3;
+  const double sz = a.sizes[(size_t)(obj_id - 1) * a.F + f];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float l32 = (float)((double)__ldg(loc + k) * sz);      // numpy: f32 array *= f64 array -> computed in f64, cast to f32
+    a.c3d[3 * dst + k] = cen[k] + (double)l32;
+  }
+  a.conf[dst] = __fmul_rn(vobj, vfrag);
+  a.conf_obj[dst] = vobj;
+  a.conf_frag[dst] = vfrag;
+  a.px[dst] = p;
+  a.frag[dst] = f;
+}
+
+__global__ void __launch_bounds__(CT, 1) corresp_kernel(CorrArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ int scan_sh[CW + 1];
+  __shared__ unsigned long long s_prefix, s_maskbits;
+  __shared__ int s_need, s_count;
+  const int seg = blockIdx.x, b = seg / a.J, j = seg % a.J, tid = threadIdx.x;
+  const int obj_id = a.obj_ids[j];
+  const int HW = a.h * a.w;
+  unsigned int* off = a.off + (size_t)seg * (HW + 1);
+  const size_t seg_base = (size_t)seg * a.cap;
+  if (obj_id < 1 || obj_id > a.O) {
+    if (tid == 0) { a.counts[seg] = 0; if (a.totals) a.totals[seg] = 0; }
+    return;
+  }
+  // ---- phase 1: counts + exclusive scan ----
+  for_each_candidate<true>(a, b, obj_id, off, [](int, int, unsigned int, float, float) {});
+  __syncthreads();
+  int total;
+  {
+    const int per = (HW + CT - 1) / CT;
+    const int lo = tid * per, hi = min(lo + per, HW);
+    int s = 0;
+    for (int i = lo; i < hi; ++i) s += (int)off[i];
+    int base = block_scan_excl(s, scan_sh, &total);
+    for (int i = lo; i < hi; ++i) { const int c = (int)off[i]; off[i] = (unsigned int)base; base += c; }
+    if (tid == 0) off[HW] = (unsigned int)total;
+    __syncthreads();
+  }
+  if (tid == 0 && a.totals) a.totals[seg] = total;
+  const bool topk = a.max_corr > 0 && total > a.max_corr;
+  if (!topk) {
+    const int n = total < a.cap ? total : a.cap;
+    if (tid == 0) a.counts[seg] = n;
+    for_each_candidate<false>(a, b, obj_id, off, [&](int p, int f, unsigned int e, float vo, float vf) {
+      if ((int)e < a.cap) write_row(a, b, obj_id, seg_base + e, p, f, vo, vf);
+    });
+    return;
+  }
+  // ---- phase 2: radix select of the K largest 64-bit keys ----
+  const int K = a.max_corr;
+  unsigned int* hist = reinterpret_cast<unsigned int*>(smem_raw);            // 2048 bins
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + 2048 * 4);   // SORT_MAX
+  unsigned int* payload = reinterpret_cast<unsigned int*>(smem_raw + 2048 * 4 + SORT_MAX * 8);
+  if (tid == 0) { s_prefix = 0ULL; s_maskbits = 0ULL; s_need = K; }
+  __syncthreads();
+  // digits from the top: conf bits 31..21, 20..10, 9..0, then emission index bits 31..21 (always 0 for < 2^21 rows
+  // but kept general), 20..10, 9..0
+  const int shifts[6] = {53, 42, 32, 21, 10, 0};
+  const int widths[6] = {11, 11, 10, 11, 11, 10};
+  for (int d = 0; d < 6; ++d) {
+    const int sh_ = shifts[d], wd = widths[d];
+    for (int i = tid; i < 2048; i += CT) hist[i] = 0u;
+    __syncthreads();
+    const unsigned long long pre = s_prefix, mk = s_maskbits;
+    for_each_candidate<false>(a, b, obj_id, off, [&](int, int, unsigned int e, float vo, float vf) {
+      const unsigned long long key = make_key(vo, vf, e);
+      if ((key & mk) == pre) atomicAdd(&hist[(unsigned int)(key >> sh_) & ((1u << wd) - 1u)], 1u);
+    });
+    __syncthreads();
+    // suffix scan from the top bin: thread t owns bins 2047-2t and 2046-2t
+    const int b0 = 2047 - 2 * tid, b1 = 2046 - 2 * tid;
+    const int c0 = (int)hist[b0], c1 = (int)hist[b1];
+    int tot2;
+    const int above = block_scan_excl(c0 + c1, scan_sh, &tot2);     // rows in bins strictly above b0
+    const int need = s_need;
+    __syncthreads();
+    if (above < need && need <= above + c0) { s_prefix = pre | ((unsigned long long)b0 << sh_); s_need = need - above; }
+    else if (above + c0 < need && need <= above + c0 + c1) { s_prefix = pre | ((unsigned long long)b1 << sh_); s_need = need - above - c0; }
+    if (tid == 0) s_maskbits = mk | (((1ULL << wd) - 1ULL) << sh_);
+    __syncthreads();
+  }
+  // s_prefix is now the K-th largest key; keys are unique (emission index), so exactly K keys are >= it
+  const unsigned long long kth = s_prefix;
+  if (tid == 0) s_count = 0;
+  for (int i = tid; i < SORT_MAX; i += CT) { keys[i] = 0ULL; payload[i] = 0u; }
+  __syncthreads();
+  for_each_candidate<false>(a, b, obj_id, off, [&](int p, int f, unsigned int e, float vo, float vf) {
+    const unsigned long long key = make_key(vo, vf, e);
+    if (key >= kth) {
+      const int slot = atomicAdd(&s_count, 1);
+      if (slot < SORT_MAX) { keys[slot] = key; payload[slot] = ((unsigned int)p << 9) | (unsigned int)f; }
+    }
+  });
+  __syncthreads();
+  // bitonic sort, descending, SORT_MAX elements (padding keys are 0 = smallest)
+  for (int k = 2; k <= SORT_MAX; k <<= 1)
+    for (int jj = k >> 1; jj > 0; jj >>= 1) {
+      for (int i = tid; i < SORT_MAX; i += CT) {
+        const int l = i ^ jj;
+        if (l > i) {
+          const bool desc = (i & k) == 0;
+          const unsigned long long ki = keys[i], kl = keys[l];
+          if (desc ? (ki < kl) : (ki > kl)) {
+            keys[i] = kl; keys[l] = ki;
+            const unsigned int t = payload[i]; payload[i] = payload[l]; payload[l] = t;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  const int n = K < a.cap ? K : a.cap;
+  if (tid == 0) a.counts[seg] = n;
+  for (int i = tid; i < n; i += CT) {
+    const unsigned int pl = payload[i];
+    const int p = (int)(pl >> 9), f = (int)(pl & 511u);
+    const float vo = __ldg(a.obj_conf + ((size_t)b * HW + p) * (a.O + 1) + obj_id);
+    const float vf = __ldg(a.frag_conf + (((size_t)b * HW + p) * a.O + (obj_id - 1)) * a.F + f);
+    write_row(a, b, obj_id, seg_base + i, p, f, vo, vf);
+  }
+}
+
+}  // namespace epos
+
+using namespace epos;
+
+extern "C" {
+
+size_t epos_corresp_workspace_bytes(int B, int J, int h, int w) {
+  if (B <= 0 || J <= 0 || h <= 0 || w <= 0) return 0;
+  return (size_t)B * J * ((size_t)h * w + 1) * 4 + 256;
+}
+
+int epos_corresp(const float* obj_conf, const float* frag_conf, const float* frag_loc, int B, int h, int w, int num_objs,
+                 int num_frags, const int32_t* obj_ids, int J, const double* frag_centers, const double* frag_sizes,
+                 double output_scale, float min_obj_conf, float min_frag_rel_conf, int cap, int max_corr, double* coord_2d,
+                 double* coord_3d, float* conf, float* conf_obj, float* conf_frag, int32_t* px, int32_t* frag,
+                 int32_t* counts, int32_t* totals, void* workspace, size_t workspace_bytes, void* stream) {
+  EPOS_CHECK_ARG(obj_conf && frag_conf && frag_loc && obj_ids && frag_centers && frag_sizes);
+  EPOS_CHECK_ARG(coord_2d && coord_3d && conf && conf_obj && conf_frag && px && frag && counts && workspace);
+  EPOS_CHECK_ARG(B > 0 && h > 0 && w > 0 && num_objs > 0 && num_frags > 0 && J > 0 && cap > 0 && output_scale > 0);
+  EPOS_CHECK_ARG((size_t)h * w < (1u << 23));
+  if (num_frags > MAXF) { set_error("epos_corresp: num_frags=%d > %d unsupported", num_frags, MAXF); return EPOS_ERR_UNSUPPORTED; }
+  if (max_corr > SORT_MAX) { set_error("epos_corresp: max_corr=%d > %d unsupported", max_corr, SORT_MAX); return EPOS_ERR_UNSUPPORTED; }
+  if (workspace_bytes < epos_corresp_workspace_bytes(B, J, h, w)) { set_error("epos_corresp: workspace too small"); return EPOS_ERR_INVALID_ARG; }
+  CorrArgs a;
+  a.obj_conf = obj_conf; a.frag_conf = frag_conf; a.frag_loc = frag_loc;
+  a.B = B; a.h = h; a.w = w; a.O = num_objs; a.F = num_frags; a.obj_ids = obj_ids; a.J = J;
+  a.centers = frag_centers; a.sizes = frag_sizes; a.inv_scale = 1.0 / output_scale;
+  a.min_obj_conf = min_obj_conf; a.min_rel = min_frag_rel_conf; a.cap = cap; a.max_corr = max_corr;
+  a.c2d = coord_2d; a.c3d = coord_3d; a.conf = conf; a.conf_obj = conf_obj; a.conf_frag = conf_frag; a.px = px; a.frag = frag;
+  a.counts = counts; a.totals = totals;
+  a.off = reinterpret_cast<unsigned int*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  const size_t smem = 2048 * 4 + (size_t)SORT_MAX * 12;
+  static bool attr = false;
+  if (!attr) {
+    EPOS_CUDA(cudaFuncSetAttribute(corresp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  corresp_kernel<<<B * J, CT, smem, (cudaStream_t)stream>>>(a);
+  EPOS_LAUNCH_CHECK();
+  return EPOS_OK;
+}
+
+}  // extern "C"

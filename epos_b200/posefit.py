@@ -1,0 +1,148 @@
+"""Pose fitting on the GPU: drop-in for pyprogressivex.find6DPoses
+(/root/reference/external/progressive-x/src/pyprogressivex/src/bindings.cpp:9-155), single-instance branch, and the
+batched fitter the engine uses after model.predict.  All arithmetic is in csrc/posefit.cu behind epos_fit_poses();
+there is no CPU fallback."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import corresp as _corresp
+
+
+def default_params(**kw):
+    p = _lib.FitParams()
+    _lib.lib().epos_fit_params_default(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise KeyError(k)
+        setattr(p, k, v)
+    return p
+
+
+class PoseFitter:
+    """P independent single-instance problems per call (one CTA each)."""
+
+    def __init__(self, device, max_problems, params=None):
+        self.lib = _lib.lib()
+        self.dev = torch.device(device)
+        self.params = params or default_params()
+        self.P = max_problems
+        nbytes = self.lib.epos_fit_workspace_bytes(max_problems, self.lib.epos_fit_max_points(), C.byref(self.params))
+        self.workspace = torch.empty((nbytes + 256,), dtype=torch.uint8, device=self.dev)
+        self._ws_ptr = (self.workspace.data_ptr() + 255) // 256 * 256
+
+    def fit(self, coord_2d, coord_3d, offsets, counts, K, seeds, poses=None, labeling=None):
+        """coord_2d [R,2] f64, coord_3d [R,3] f64, offsets/counts [P] i32, K [P,3,3] f64, seeds [P] i64 (device).
+        Returns (poses [P,16] f64, labeling [R] i32)."""
+        P = offsets.numel()
+        assert P <= self.P
+        if poses is None:
+            poses = torch.empty((P, 16), dtype=torch.float64, device=self.dev)
+        if labeling is None:
+            labeling = torch.empty((coord_2d.shape[0],), dtype=torch.int32, device=self.dev)
+        _lib.check(self.lib.epos_fit_poses(coord_2d.data_ptr(), coord_3d.data_ptr(), offsets.data_ptr(), counts.data_ptr(),
+                                           P, K.data_ptr(), seeds.data_ptr(), C.byref(self.params), poses.data_ptr(),
+                                           labeling.data_ptr(), self._ws_ptr, self.workspace.numel() - 256,
+                                           _lib.stream_ptr()), 'epos_fit_poses')
+        return poses, labeling
+
+
+class BatchFitter:
+    """model.predict outputs -> correspondences -> poses for a whole batch: [B, J, 16] pose records on the device
+    (record layout: include/epos_b200.h EPOS_POSE_RECORD_DOUBLES)."""
+
+    def __init__(self, device, num_objs, num_frags, model_store, K, params=None, max_correspondences=4096, seed=0,
+                 obj_ids=None, output_scale=0.25, min_obj_conf=0.1, min_frag_rel_conf=0.5):
+        self.dev = torch.device(device)
+        self.params = params or default_params()
+        nmax = _lib.lib().epos_fit_max_points()
+        if max_correspondences is None or max_correspondences > nmax:
+            raise ValueError('this build keeps the point set in shared memory: max_correspondences must be <= %d '
+                             '(the reference default is None = unbounded, infer.py:112-114)' % nmax)
+        self.extract = _corresp.CorrespExtractor(self.dev, num_objs, num_frags, model_store, obj_ids=obj_ids,
+                                                 output_scale=output_scale, min_obj_conf=min_obj_conf,
+                                                 min_frag_rel_conf=min_frag_rel_conf, cap=max_correspondences,
+                                                 max_correspondences=max_correspondences)
+        self.J = len(self.extract.obj_ids_list)
+        self.K = np.asarray(K, np.float64)
+        self.seed = int(seed)
+        self._fitter = None
+        self._Kdev = None
+        self._seeds = None
+        self.batch_index = 0
+
+    def _prepare(self, B):
+        P = B * self.J
+        if self._fitter is None or self._fitter.P < P:
+            self._fitter = PoseFitter(self.dev, P, self.params)
+        if self._Kdev is None or self._Kdev.shape[0] != P:
+            K = self.K if self.K.ndim == 3 else np.broadcast_to(self.K, (B, 3, 3))
+            self._Kdev = torch.from_numpy(np.ascontiguousarray(np.repeat(K, self.J, axis=0))).to(self.dev)
+            self._poses = torch.empty((P, 16), dtype=torch.float64, device=self.dev)
+            self._labeling = torch.empty((P * self.extract.cap,), dtype=torch.int32, device=self.dev)
+            self._base = torch.arange(P, dtype=torch.int64, device=self.dev)
+
+    def seeds_for(self, B):
+        """Stream key of problem (image b, slot j) in batch n: seed * 2^32 + n * P + b * J + j."""
+        return self._base + (self.seed << 32) + self.batch_index * (B * self.J)
+
+    def fit_maps(self, obj_conf, frag_conf, frag_loc):
+        B = obj_conf.shape[0]
+        self._prepare(B)
+        bc = self.extract(obj_conf, frag_conf, frag_loc)
+        self.corr = bc
+        seeds = self.seeds_for(B)
+        self.batch_index += 1
+        poses, lab = self._fitter.fit(bc.coord_2d.view(-1, 2), bc.coord_3d.view(-1, 3), bc.offsets, bc.counts,
+                                      self._Kdev, seeds, self._poses, self._labeling)
+        return poses.view(B, self.J, 16)
+
+    def fit(self, predictions):
+        from . import model
+        return self.fit_maps(predictions[model.PRED_OBJ_CONF], predictions[model.PRED_FRAG_CONF],
+                             predictions[model.PRED_FRAG_LOC])
+
+
+def find6DPoses(x1y1, x2y2z2, K, threshold=4.0, max_model_number=-1, conf=0.5, proposal_engine_conf=1.0,
+                spatial_coherence_weight=0.1, neighborhood_ball_radius=20.0, max_tanimoto_similarity=0.9,
+                scaling_from_millimeters=0.1, min_triangle_area=100.0, min_coverage=0.5, max_iters=400,
+                min_point_number=6, use_prosac=False, max_model_number_for_optimization=3,
+                apply_numerical_optimization=True, log=False, seed=0, device='cuda:0', max_neighbors=5):
+    """Same name / keyword arguments / return triple as pyprogressivex.find6DPoses (bindings.cpp:9-28,117,133-152):
+    (poses [3M,4] f64, labeling [N] i32, scores [M] f64) as numpy arrays.  Errors: ValueError for malformed shapes
+    (bindings.cpp:30-58).  Only max_model_number == 1 (plain GC-RANSAC) is built; `seed` selects the RANSAC stream
+    (the reference seeds from std::random_device)."""
+    x1y1 = np.ascontiguousarray(x1y1, np.float64)
+    x2y2z2 = np.ascontiguousarray(x2y2z2, np.float64)
+    K = np.ascontiguousarray(K, np.float64)
+    if x1y1.ndim != 2 or x1y1.shape[1] != 2:
+        raise ValueError('x1y1 should be an array with dims [n,2], n>=3')
+    n = x1y1.shape[0]
+    if x2y2z2.ndim != 2 or x2y2z2.shape[1] != 3 or x2y2z2.shape[0] != n or n < 3:
+        raise ValueError('x2y2z2 should be an array with dims [n,3], n>=3, same n as x1y1')
+    if K.shape != (3, 3):
+        raise ValueError('K should be an array with dims [3,3]')
+    if max_model_number != 1:
+        raise NotImplementedError('multi-instance Progressive-X is not built yet (SURVEY.md 8f rank 2)')
+    if proposal_engine_conf != 1.0:
+        raise NotImplementedError('proposal_engine_conf must be 1.0 (scripts/infer.py:90)')
+    dev = torch.device(device)
+    p = default_params(threshold=threshold, spatial_coherence_weight=spatial_coherence_weight,
+                       neighborhood_ball_radius=neighborhood_ball_radius,
+                       scaling_from_millimeters=scaling_from_millimeters, min_triangle_area=min_triangle_area,
+                       min_coverage=min_coverage, max_iters=max_iters, max_neighbors=max_neighbors,
+                       apply_numerical_optimization=int(apply_numerical_optimization))
+    if n > _lib.lib().epos_fit_max_points():
+        raise ValueError('more than %d correspondences' % _lib.lib().epos_fit_max_points())
+    f = PoseFitter(dev, 1, p)
+    poses, lab = f.fit(torch.from_numpy(x1y1).to(dev), torch.from_numpy(x2y2z2).to(dev),
+                       torch.zeros(1, dtype=torch.int32, device=dev), torch.tensor([n], dtype=torch.int32, device=dev),
+                       torch.from_numpy(K.reshape(1, 3, 3)).to(dev), torch.tensor([seed], dtype=torch.int64, device=dev))
+    rec = poses.cpu().numpy()[0]
+    labeling = lab.cpu().numpy().astype(np.int32)
+    find6DPoses.last_record = rec
+    if rec[14] != 1.0:
+        return np.zeros((0, 4)), labeling, np.zeros((0,))
+    return rec[:12].reshape(3, 4).copy(), labeling, np.zeros((1,))

@@ -102,13 +102,16 @@ int epos_softmax_rows(float* x, int64_t* labels, size_t rows, int n, void* strea
  * top-K selection of scripts/infer.py:425-440 ------------------------------------------------------ */
 
 /* For every (image b, object slot j): pixels with obj_conf[b,p,obj_ids[j]] > min_obj_conf, fragments with
- * frag_conf > min_frag_rel_conf * max_f; emits rows in row-major pixel then fragment order.
- * Outputs per (b,j) segment of capacity `cap`: coord_2d [cap][2] f64, coord_3d [cap][3] f64, conf [cap] f32,
- * conf_obj, conf_frag f32, px [cap] i32 (linear output pixel), frag [cap] i32; counts[b*J+j] = N (untruncated
- * count; rows beyond cap are dropped and must be treated as an error by the caller unless top-K is used).
- * If max_corr > 0 the segment is reduced to the max_corr most confident rows in descending confidence
- * (ties: descending emission index), as np.argsort(conf)[::-1][:max_corr].
- * frag_centers [num_objs][F][3] f64, frag_sizes [num_objs][F] f64 indexed by obj_id-1. */
+ * frag_conf > min_frag_rel_conf * max_f; emits rows in row-major pixel then fragment order (the reference's order).
+ * Inputs are model.predict's maps: obj_conf [B,h,w,O+1], frag_conf [B,h,w,O,F], frag_loc [B,h,w,O,F,3] (f32).
+ * Outputs per (b,j) segment of capacity `cap` (segment s = b*J+j starts at row s*cap): coord_2d [cap][2] f64,
+ * coord_3d [cap][3] f64, conf / conf_obj / conf_frag [cap] f32, px [cap] i32 (linear output pixel y*w+x),
+ * frag [cap] i32; counts[s] = rows written, totals[s] (may be NULL) = rows the reference would emit.
+ * If max_corr > 0 and totals[s] > max_corr the segment holds the max_corr most confident rows in descending
+ * confidence (ties: descending emission index) = np.argsort(conf)[::-1][:max_corr] (infer.py:431-440);
+ * max_corr <= 4096.  Without top-K, rows beyond cap are dropped (counts[s] = cap < totals[s]).
+ * frag_centers [num_objs][F][3] f64, frag_sizes [num_objs][F] f64, indexed by obj_id-1 (datagen.py:93-124).
+ * obj_ids outside [1, num_objs] give an empty segment. */
 int epos_corresp(const float* obj_conf, const float* frag_conf, const float* frag_loc,
                  int B, int h, int w, int num_objs, int num_frags,
                  const int32_t* obj_ids, int J,
@@ -116,9 +119,9 @@ int epos_corresp(const float* obj_conf, const float* frag_conf, const float* fra
                  double output_scale, float min_obj_conf, float min_frag_rel_conf,
                  int cap, int max_corr,
                  double* coord_2d, double* coord_3d, float* conf, float* conf_obj, float* conf_frag,
-                 int32_t* px, int32_t* frag, int32_t* counts,
+                 int32_t* px, int32_t* frag, int32_t* counts, int32_t* totals,
                  void* workspace, size_t workspace_bytes, void* stream);
-size_t epos_corresp_workspace_bytes(int B, int J, int cap);
+size_t epos_corresp_workspace_bytes(int B, int J, int h, int w);
 
 /* ---- pose fitting: replaces pyprogressivex.find6DPoses
  * (external/progressive-x/src/pyprogressivex/src/bindings.cpp:9-118, progressivex_python.cpp:36-336),
@@ -137,25 +140,31 @@ typedef struct {
   int32_t max_graph_cuts;            /* 10  (settings.h:78) */
   int32_t max_lsq_iters;             /* 10  (settings.h:79) */
   int32_t max_unsuccessful;          /* 100 (settings.h:85) */
-  int32_t max_neighbors;             /* 5: deterministic stand-in for FLANN checks=6 */
+  int32_t max_neighbors;             /* 5 (<= 8): deterministic stand-in for FLANN checks=6 */
   int32_t apply_numerical_optimization; /* 1 */
   int32_t reserved;
 } epos_fit_params;
 
 void epos_fit_params_default(epos_fit_params* p);
 
-/* One record per problem: pose[12] row-major [R|t], then n_inliers, iterations, valid, graph_cuts. */
+/* One record per problem: pose[12] row-major [R|t], then n_inliers, iterations, valid (1 = pose found,
+ * 0 = no pose: fewer than 6 correspondences or no model with > 3 inliers, -1 = more than epos_fit_max_points()
+ * correspondences), graph_cuts.  The reference returns an uninitialised matrix when nothing is found
+ * (model.h:84-89, progressivex_python.cpp:326-335); this library reports valid = 0 instead. */
 #define EPOS_POSE_RECORD_DOUBLES 16
 
 /* P problems; problem i owns rows [offsets[i], offsets[i]+counts[i]) of coord_2d [*,2] / coord_3d [*,3]
  * (f64, device).  K [P][9] f64 row-major.  seeds [P] u64: RANSAC stream key (counter-based generator).
- * Outputs: poses [P][16] f64, labeling [total rows] i32 (1 = inlier). */
+ * Outputs: poses [P][16] f64, labeling i32 (1 = inlier) at the same row positions as the inputs.
+ * proposal_engine_conf is fixed at 1.0 (scripts/infer.py:90 default), i.e. the iteration bound is max_iters. */
 int epos_fit_poses(const double* coord_2d, const double* coord_3d,
                    const int32_t* offsets, const int32_t* counts, int P,
                    const double* K, const uint64_t* seeds, const epos_fit_params* params,
                    double* poses, int32_t* labeling,
                    void* workspace, size_t workspace_bytes, void* stream);
 size_t epos_fit_workspace_bytes(int P, int max_points, const epos_fit_params* params);
+/* Largest number of correspondences per problem (shared-memory resident point set): 4096. */
+int epos_fit_max_points(void);
 
 #ifdef __cplusplus
 }

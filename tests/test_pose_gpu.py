@@ -1,0 +1,212 @@
+"""GPU parity tests of correspondence extraction and pose fitting against the oracle, through the C ABI.
+
+Bars (north_star / SURVEY.md 8d): correspondences bit-exact (indices, f64 coordinates, f32 confidences, order);
+poses: identical inlier sets, identical iteration / graph-cut counts, (R, t) within 1e-4 (relative for t) of the
+oracle under a shared seed and shared (deterministic) neighbour graph."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+DEV = 'cuda:0'
+
+
+def _softmax(x, axis=-1):
+    e = np.exp(x - x.max(axis=axis, keepdims=True))
+    return (e / e.sum(axis=axis, keepdims=True)).astype(np.float32)
+
+
+def _random_maps(rng, B, h, w, O, F, sharp=2.0):
+    oc = _softmax(rng.standard_normal((B, h, w, O + 1)) * sharp)
+    fc = _softmax(rng.standard_normal((B, h, w, O, F)) * sharp)
+    fl = rng.standard_normal((B, h, w, O, F, 3)).astype(np.float32)
+    return oc, fc, fl
+
+
+def _check_corresp(oc, fc, fl, store, O, F, max_corr, min_obj_conf=0.1, min_rel=0.5):
+    from epos_b200 import corresp
+    from oracle import corresp as ocorr
+    B, h, w = oc.shape[:3]
+    cap = h * w * F if not max_corr else max_corr
+    ex = corresp.CorrespExtractor(DEV, O, F, store, cap=cap, max_correspondences=max_corr, min_obj_conf=min_obj_conf,
+                                  min_frag_rel_conf=min_rel)
+    bc = ex(torch.from_numpy(oc).to(DEV), torch.from_numpy(fc).to(DEV), torch.from_numpy(fl).to(DEV))
+    torch.cuda.synchronize()
+    counts, totals = bc.counts.cpu().numpy(), bc.totals.cpu().numpy()
+    ids = store.dp_model['obj_ids']
+    J = len(ids)
+    nrows = 0
+    for b in range(B):
+        ref = ocorr.establish_many_to_many(oc[b], fc[b], fl[b], ids, ids, store.frag_centers, store.frag_sizes, 0.25,
+                                           min_obj_conf, min_rel, only_annotated_objs=False)
+        for j, oid in enumerate(ids):
+            s = b * J + j
+            r = ref.get(oid)
+            if r is None:
+                assert counts[s] == 0 and totals[s] == 0
+                continue
+            assert totals[s] == r['coord_2d'].shape[0]
+            r = ocorr.select_top_k(r, max_corr if max_corr else None)
+            n = r['coord_2d'].shape[0]
+            assert counts[s] == n, (b, oid, counts[s], n)
+            nrows += n
+            assert np.array_equal(bc.px[s, :n].cpu().numpy(), r['pixel'])
+            assert np.array_equal(bc.frag[s, :n].cpu().numpy(), r['frag_id'])
+            assert np.array_equal(bc.coord_2d[s, :n].cpu().numpy(), r['coord_2d'])
+            assert np.array_equal(bc.coord_3d[s, :n].cpu().numpy(), r['coord_3d'])
+            assert np.array_equal(bc.conf[s, :n].cpu().numpy(), r['conf'])
+            assert np.array_equal(bc.conf_obj[s, :n].cpu().numpy(), r['conf_obj'])
+            assert np.array_equal(bc.conf_frag[s, :n].cpu().numpy(), r['conf_frag'])
+    return nrows
+
+
+@pytest.mark.parametrize('O,F,h,w,max_corr', [(3, 64, 120, 160, 0), (3, 64, 120, 160, 700), (2, 8, 33, 47, 0),
+                                              (5, 256, 30, 40, 512), (1, 64, 60, 80, 4096), (4, 40, 31, 37, 100)])
+def test_corresp_random_maps(O, F, h, w, max_corr):
+    from epos_b200 import synthetic
+    rng = np.random.default_rng(O * 100 + F)
+    store = synthetic.model_store(O, F)
+    oc, fc, fl = _random_maps(rng, 2, h, w, O, F)
+    n = _check_corresp(oc, fc, fl, store, O, F, max_corr, min_obj_conf=0.3 if O < 3 else 0.1)
+    assert n > 0
+
+
+def test_corresp_planted_maps_with_ties_and_empty_objects():
+    """Constant confidences: every row ties, so top-K is decided by the descending-index rule alone."""
+    from epos_b200 import synthetic
+    O, F = 4, 64
+    store = synthetic.model_store(O, F)
+    oc, fc, fl, gt = synthetic.planted_maps(2, O, F, store, synthetic.default_K(), seed=5, objs_per_image=2)
+    assert _check_corresp(oc, fc, fl, store, O, F, 0) > 0
+    assert _check_corresp(oc, fc, fl, store, O, F, 300) > 0
+    assert _check_corresp(oc, fc, fl, store, O, F, 4096) > 0
+
+
+def test_establish_many_to_many_dropin():
+    from epos_b200 import corresp, synthetic
+    from oracle import corresp as ocorr
+    rng = np.random.default_rng(3)
+    O, F = 3, 16
+    store = synthetic.model_store(O, F)
+    oc, fc, fl = _random_maps(rng, 1, 24, 32, O, F)
+    got = corresp.establish_many_to_many(torch.from_numpy(oc[0]).to(DEV), torch.from_numpy(fc[0]).to(DEV),
+                                         torch.from_numpy(fl[0]).to(DEV), [1, 3], store, 0.25, 0.1, 0.5,
+                                         only_annotated_objs=True)
+    ref = ocorr.establish_many_to_many(oc[0], fc[0], fl[0], [1, 3], store.dp_model['obj_ids'], store.frag_centers,
+                                       store.frag_sizes, 0.25, 0.1, 0.5, only_annotated_objs=True)
+    assert sorted(got) == sorted(ref)
+    for oid in ref:
+        for k in ('px_id', 'frag_id', 'coord_2d', 'coord_3d', 'conf', 'conf_obj', 'conf_frag'):
+            assert np.array_equal(got[oid][k].cpu().numpy(), ref[oid][k]), (oid, k)
+
+
+# ---------------------------------------------------------------------------------------------------
+def _fit_both(x2d, x3d, K, seed, **kw):
+    from epos_b200 import posefit
+    from oracle import posefit as opf
+    gp, gl, gs = posefit.find6DPoses(x2d, x3d, K, max_model_number=1, seed=seed, **kw)
+    rec = posefit.find6DPoses.last_record.copy()
+    op, ol, os_, st = opf.find6DPoses(x2d, x3d, K, max_model_number=1, seed=seed, return_stats=True, **kw)
+    return gp, gl, rec, op, ol, st
+
+
+def _assert_same_fit(gp, gl, rec, op, ol, st, tol=1e-4):
+    assert gp.shape == op.shape, (gp.shape, op.shape, rec, st)
+    assert int(rec[13]) == st['iterations'], (rec[13], st)
+    assert int(rec[15]) == st['graph_cuts'], (rec[15], st)
+    assert np.array_equal(gl, ol), int((gl != ol).sum())
+    if op.shape[0] == 3:
+        assert np.abs(gp[:, :3] - op[:, :3]).max() < tol
+        assert np.linalg.norm(gp[:, 3] - op[:, 3]) < tol * max(1.0, np.linalg.norm(op[:, 3]))
+
+
+def test_fit_golden_fixtures_match_oracle():
+    for name, seeds in (('pnp16.json', (0, 1, 2)), ('pose6dscene.json', (0, 1)), ('tless.json', (0, 1, 2, 3))):
+        g = json.load(open(os.path.join(GOLDEN, name)))
+        c, K = np.array(g['corrs']), np.array(g['K'])
+        for seed in seeds:
+            out = _fit_both(c[:, :2], c[:, 2:], K, seed, threshold=4.0, min_triangle_area=0.0)
+            _assert_same_fit(*out)
+        if name == 'pnp16.json':
+            np.testing.assert_allclose(out[0][:, :3], np.array(g['R_gcransac']), atol=1e-5)
+            np.testing.assert_allclose(out[0][:, 3], np.array(g['t_gcransac']), atol=1e-3)
+
+
+def test_fit_planted_scene_matches_oracle_and_ground_truth():
+    from epos_b200 import synthetic
+    from oracle import corresp as ocorr
+    O, F = 3, 64
+    store = synthetic.model_store(O, F)
+    K = synthetic.default_K()
+    oc, fc, fl, gt = synthetic.planted_maps(2, O, F, store, K, seed=7)
+    ids = store.dp_model['obj_ids']
+    checked = 0
+    for b in range(2):
+        ref = ocorr.establish_many_to_many(oc[b], fc[b], fl[b], ids, ids, store.frag_centers, store.frag_sizes, 0.25,
+                                           0.1, 0.5, only_annotated_objs=False)
+        for oid, d in ref.items():
+            d = ocorr.select_top_k(d, 4096)
+            out = _fit_both(d['coord_2d'], d['coord_3d'], K, seed=100 * b + oid, threshold=4.0, min_triangle_area=0.0)
+            _assert_same_fit(*out)
+            R, t = gt[b][oid]
+            assert np.abs(out[0][:, :3] - R).max() < 2e-2 and np.linalg.norm(out[0][:, 3] - t) < 5.0
+            checked += 1
+    assert checked >= 4
+
+
+def test_fit_without_consensus_runs_all_iterations():
+    rng = np.random.default_rng(11)
+    K = np.array([[1066.778, 0, 312.9869], [0, 1067.487, 241.3109], [0, 0, 1]])
+    for n, seed in ((200, 1), (900, 2), (64, 3)):
+        x2d = 4.0 * (rng.integers(0, 160, (n, 2)) + 0.5)
+        x3d = rng.uniform(-100, 100, (n, 3))
+        out = _fit_both(x2d, x3d, K, seed, threshold=4.0, min_triangle_area=0.0)
+        assert out[5]['iterations'] >= 400
+        _assert_same_fit(*out)
+
+
+def test_fit_small_and_degenerate_inputs():
+    from epos_b200 import posefit
+    K = np.array([[1066.778, 0, 312.9869], [0, 1067.487, 241.3109], [0, 0, 1]])
+    rng = np.random.default_rng(2)
+    # fewer than 6 correspondences: no pose (scripts/infer.py:417-422)
+    p, lab, s = posefit.find6DPoses(rng.uniform(0, 600, (5, 2)), rng.uniform(-50, 50, (5, 3)), K, max_model_number=1)
+    assert p.shape == (0, 4) and lab.sum() == 0 and s.shape == (0,)
+    # all points identical: every sample is degenerate, nothing is found
+    x2d = np.tile([[100.0, 100.0]], (50, 1))
+    x3d = np.tile([[1.0, 2.0, 3.0]], (50, 1))
+    out = _fit_both(x2d, x3d, K, 0, threshold=4.0, min_triangle_area=0.0)
+    assert out[0].shape == (0, 4) and out[3].shape == (0, 4)
+
+
+def test_batch_fitter_matches_oracle_pipeline():
+    """BASELINE configs[2]-shaped post-processing: maps -> correspondences -> poses for a batch, against the oracle."""
+    from epos_b200 import posefit, synthetic
+    from oracle import pipeline
+    O, F, B = 4, 64, 3
+    store = synthetic.model_store(O, F)
+    K = synthetic.default_K()
+    oc, fc, fl, gt = synthetic.planted_maps(B, O, F, store, K, seed=21, objs_per_image=3)
+    bf = posefit.BatchFitter(DEV, O, F, store, K, max_correspondences=2048, seed=9)
+    recs = bf.fit_maps(torch.from_numpy(oc).to(DEV), torch.from_numpy(fc).to(DEV), torch.from_numpy(fl).to(DEV))
+    torch.cuda.synchronize()
+    recs = recs.cpu().numpy()
+    pp = pipeline.PostProcess(O, F, seed=9, model_store=store, K=K, max_correspondences=2048)
+    found = 0
+    for b in range(B):
+        corr = pp.corresp({'pred_obj_conf': oc, 'pred_frag_conf': fc, 'pred_frag_loc': fl}, b)
+        ref = pp.fit(corr, image_index=b, images_per_batch=B, batch_index=0)
+        for j, oid in enumerate(store.dp_model['obj_ids']):
+            g, r = recs[b, j], ref[oid]
+            assert g[14] == r[14] and g[12] == r[12] and g[13] == r[13] and g[15] == r[15], (b, oid, g[12:], r[12:])
+            if r[14] == 1.0:
+                found += 1
+                assert np.abs(g[:12] - r[:12]).max() < 1e-4 * max(1.0, np.abs(r[:12]).max())
+                if oid in gt[b]:
+                    R, t = gt[b][oid]
+                    assert np.abs(g[:12].reshape(3, 4)[:, :3] - R).max() < 2e-2
+    assert found >= 6
