@@ -30,6 +30,12 @@ if ROOT not in sys.path:
 
 H, W = 480, 640
 TRUNK_FLOP = 401.97e9          # Xception-65 trunk + ASPP + decoder, per image
+# Random-init logit weights (reference: truncated_normal(0.01), model.py:437) give uniform heads -> obj_conf = 1/22 < tau_a
+# -> ZERO correspondences.  The full workload therefore scales the logit initialiser so that the
+# random features produce a varied, mostly no-consensus correspondence load (0 .. >30k rows per object, top-K 4096):
+# every object runs all 400 RANSAC iterations and its graph-cut budget, i.e. the expensive case for pose fitting.
+HEAD_STD_FULL = 300.0
+MAX_CORR = 4096
 
 
 def head_flop(O, F):
@@ -130,12 +136,12 @@ def cpu_reference_run(kind, O, F, n_images, threads, seed=0):
     from epos_b200 import weights as Wt
     from oracle import cnn as ocnn
     torch.set_num_threads(threads)
-    w = Wt.random_init(O, F, seed=seed)
+    w = Wt.random_init(O, F, seed=seed, logits_std=HEAD_STD_FULL if kind == 'full' else None)
     net = ocnn.Oracle(w)
     fit = None
     if kind == 'full':
         from oracle import pipeline as opipe
-        fit = opipe.PostProcess(O, F, seed=seed)
+        fit = opipe.PostProcess(O, F, seed=seed, max_correspondences=MAX_CORR)
     stages = {'prediction': 0.0, 'establish_corr': 0.0, 'fitting': 0.0}
     timed = 0
     for i in range(n_images + 1):
@@ -207,14 +213,15 @@ def run_ours(args, kind):
 
     # weights: generated on rank 0 and broadcast once over NCCL
     from epos_b200 import dist as edist
-    w = edist.broadcast_weights(Wt.random_init(O, F, seed=0) if rank == 0 else None, O, F, dev, world, rank)
+    w = edist.broadcast_weights(Wt.random_init(O, F, seed=0, logits_std=HEAD_STD_FULL if kind == 'full' else None)
+                                if rank == 0 else None, O, F, dev, world, rank)
     store = K = None
     if kind == 'full':
         from epos_b200 import synthetic
         store = synthetic.model_store(O, F)
         K = synthetic.default_K()
     eng = engine.Engine(w, O, F, dev, stages=engine.STAGES_FULL if kind == 'full' else engine.STAGES_CNN,
-                        model_store=store, K=K, seed=1234 + rank)
+                        model_store=store, K=K, seed=1234 + rank, max_correspondences=MAX_CORR)
 
     # inputs: NROT distinct batches (> L2 in total) rotated between steps, both pinned-host and device copies
     NROT = 5
@@ -322,6 +329,8 @@ def run_ours(args, kind):
                        'l2': 'inputs rotate over %d distinct batches (%.0f MB) and per-layer activations (>=112 MB at B=8) '
                              'exceed the 126 MB L2' % (NROT, NROT * host_batches[0].numel() * 4 / 1e6),
                        'algorithmic_gflop_per_image': flop_img / 1e9,
+                       'heads': 'random-init; logit initialiser stddev %s' % (HEAD_STD_FULL if kind == 'full' else 0.01),
+                       'max_correspondences': MAX_CORR if kind == 'full' else None,
                        'parallelism': 'image-sharded dp%d' % world},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu,
             'model_tflops_algorithmic': value * flop_img / 1e12 / world,

@@ -15,7 +15,7 @@ STAGES_FULL = 'cnn+corresp+fit'
 
 class Engine:
     def __init__(self, weights, num_objs, num_frags, device, stages=STAGES_CNN, model_store=None, K=None,
-                 fit_params=None, max_correspondences=4096, seed=0):
+                 fit_params=None, max_correspondences=4096, seed=0, min_obj_conf=0.1, min_frag_rel_conf=0.5):
         self.dev = torch.device(device)
         self.net = model.EposNet(weights, num_objs, num_frags, self.dev)
         self.O, self.F = num_objs, num_frags
@@ -29,7 +29,8 @@ class Engine:
         if stages == STAGES_FULL:
             from . import posefit
             self._fitter = posefit.BatchFitter(self.dev, num_objs, num_frags, model_store, K, fit_params,
-                                               max_correspondences, seed)
+                                               max_correspondences, seed, min_obj_conf=min_obj_conf,
+                                               min_frag_rel_conf=min_frag_rel_conf)
 
     def run_device(self, images_dev):
         """images_dev [B,H,W,3] f32 CUDA.  Returns a dict of CUDA tensors: model.predict's outputs for 'cnn',

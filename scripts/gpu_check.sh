@@ -7,10 +7,12 @@ python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/pytest_$TAG.log
 cat gpurun_out/pytest_$TAG.log
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 tail -3 gpurun_out/bench_$TAG.err; cat gpurun_out/bench_$TAG.json
-ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 600 --csv --log-file gpurun_out/launches_$TAG.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 420 -c 700 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench_stdout_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:pw_gemm -s 60 -c 3 -f -o gpurun_out/prof_gemm_$TAG \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:dwconv -s 40 -c 2 -f -o gpurun_out/prof_dw_$TAG \
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:main_kernel -c 2 -f -o gpurun_out/prof_ransac_$TAG \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
 ls -la gpurun_out

@@ -210,3 +210,35 @@ def test_batch_fitter_matches_oracle_pipeline():
                     R, t = gt[b][oid]
                     assert np.abs(g[:12].reshape(3, 4)[:, :3] - R).max() < 2e-2
     assert found >= 6
+
+
+def test_engine_full_path_postprocessing_matches_oracle_on_its_own_maps():
+    """Engine = model.predict -> corresp -> fit on the device; the oracle post-processes the SAME maps (copied to the
+    host), so the comparison is exact although the CNN itself only matches the f32 oracle to 1e-3."""
+    from epos_b200 import engine, model, synthetic, weights as W
+    from oracle import pipeline
+    O, F, B = 3, 16, 2
+    w = W.random_init(O, F, seed=2, bn='random', logits_std=0.5)
+    store = synthetic.model_store(O, F)
+    K = synthetic.default_K()
+    eng = engine.Engine(w, O, F, DEV, stages=engine.STAGES_FULL, model_store=store, K=K, max_correspondences=1024, seed=4)
+    img = torch.from_numpy(W.synthetic_images(B, seed=6, height=160, width=224)).to(DEV)
+    out = eng.run_device(img)
+    torch.cuda.synchronize()
+    recs = out['poses'].cpu().numpy()
+    assert recs.shape == (B, O, 16)
+    maps = {k: out[k].cpu().numpy() for k in (model.PRED_OBJ_CONF, model.PRED_FRAG_CONF, model.PRED_FRAG_LOC)}
+    pp = pipeline.PostProcess(O, F, seed=4, model_store=store, K=K, max_correspondences=1024)
+    nprob = 0
+    for b in range(B):
+        ref = pp.fit(pp.corresp(maps, b), image_index=b, images_per_batch=B, batch_index=0)
+        for j, oid in enumerate(store.dp_model['obj_ids']):
+            g, r = recs[b, j], ref[oid]
+            assert g[13] == r[13] and g[14] == r[14] and g[12] == r[12] and g[15] == r[15], (b, oid, g[12:], r[12:])
+            nprob += r[13] > 0
+            if r[14] == 1.0:
+                assert np.abs(g[:12] - r[:12]).max() < 1e-4 * max(1.0, np.abs(r[:12]).max())
+    assert nprob >= 2
+    # second batch uses the next stream keys
+    out2 = eng.run_device(img)
+    assert eng._fitter.batch_index == 2
