@@ -40,6 +40,7 @@ _SIGS = {
                            vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     'epos_corresp_workspace_bytes': (sz, [i32, i32, i32, i32]),
     'epos_fit_max_points': (i32, []),
+    'epos_fit_debug_state': (i32, [vp, i32, vp]),
     'epos_fit_params_default': (None, [C.POINTER(FitParams)]),
     'epos_fit_poses': (i32, [vp, vp, vp, vp, i32, vp, vp, C.POINTER(FitParams), vp, vp, vp, sz, vp]),
     'epos_fit_workspace_bytes': (sz, [i32, i32, C.POINTER(FitParams)]),

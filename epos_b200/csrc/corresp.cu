@@ -14,9 +14,9 @@
 
 namespace epos {
 
-constexpr int CT = 1024;            // threads per CTA
+constexpr int CT = 512;             // threads per CTA
 constexpr int CW = CT / 32;
-constexpr int MAXF = 512;           // fragments per object supported (registers: MAXF / 32 per lane)
+constexpr int MAXF = 512;           // fragments per object supported
 constexpr int SORT_MAX = 4096;      // max_corr supported by the in-kernel sort
 
 struct CorrArgs {
@@ -27,7 +27,7 @@ struct CorrArgs {
   double inv_scale; float min_obj_conf, min_rel;
   int cap, max_corr;
   double* c2d; double* c3d; float* conf; float* conf_obj; float* conf_frag; int* px; int* frag; int* counts; int* totals;
-  unsigned int* off;               // workspace [B*J][HW+1]
+  unsigned int* ws;                // workspace [B*J][4][HW+1]: masked-pixel list, obj_conf, row max, emission offsets
 };
 
 __device__ inline int block_scan_excl(int v, int* sh, int* total) {
@@ -56,55 +56,43 @@ __device__ inline int block_scan_excl(int v, int* sh, int* total) {
   return base + x - v;
 }
 
-// Visits every candidate row of the segment in parallel (warp per masked pixel).  fn(p, f, e, vobj, vfrag, lane-local)
-// is called by the lane that owns fragment f with e = emission index.  If COUNT, per-pixel counts are written to off[].
-template <bool COUNT, class Fn>
-__device__ inline void for_each_candidate(const CorrArgs& a, int b, int obj_id, unsigned int* off, Fn fn) {
-  const int HW = a.h * a.w, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float* oc = a.obj_conf + (size_t)b * HW * (a.O + 1) + obj_id;
+// Per-segment view of the masked pixels (ordered by pixel index).
+struct SegLists {
+  const unsigned int* mpix;   // [nm]   pixel index
+  const float* vobj;          // [nm]   obj_conf of the pixel
+  const float* rmax;          // [nm]   max_f frag_conf
+  const unsigned int* off;    // [nm+1] emission offset of the pixel's first row
+  int nm;
+};
+
+// Visits every candidate row of the segment, ONE THREAD PER MASKED PIXEL (many rows in flight per SM; the F-float row is
+// read with 16-byte loads).  fn(p, f, e, vobj, vfrag) with e = emission index (row-major pixel, then fragment).
+template <class Fn>
+__device__ inline void for_each_candidate(const CorrArgs& a, int b, int obj_id, const SegLists& L, Fn fn) {
+  const int HW = a.h * a.w;
   const float* fcb = a.frag_conf + ((size_t)b * HW * a.O + (obj_id - 1)) * a.F;
-  const int nf = (a.F + 31) >> 5;
-  for (int p0 = warp * 32; p0 < HW; p0 += CW * 32) {
-    const int pl = p0 + lane;
-    float v = 0.f;
-    bool m = false;
-    if (pl < HW) {
-      v = __ldg(oc + (size_t)pl * (a.O + 1));
-      m = v > a.min_obj_conf;                                   // corresp.py:46-47
-      if (!COUNT) m = m && (off[pl + 1] > off[pl]);
-    }
-    unsigned int mask = __ballot_sync(0xffffffffu, m);
-    if (COUNT && pl < HW && !m) off[pl] = 0u;
-    while (mask) {
-      const int l = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const int p = p0 + l;
-      const float vobj = __shfl_sync(0xffffffffu, v, l);
-      const float* row = fcb + (size_t)p * a.O * a.F;
-      float r[MAXF / 32];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int k = 0; k < MAXF / 32; ++k)
-        if (k < nf) {
-          const int f = k * 32 + lane;
-          r[k] = f < a.F ? __ldg(row + f) : -INFINITY;
-          mx = fmaxf(mx, r[k]);
-        }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      const float thr = __fmul_rn(mx, a.min_rel);                // corresp.py:62-64 (float32 product)
-      int run = 0;
-      const unsigned int base = COUNT ? 0u : off[p];
-#pragma unroll
-      for (int k = 0; k < MAXF / 32; ++k)
-        if (k < nf) {
-          const int f = k * 32 + lane;
-          const bool sel = f < a.F && r[k] > thr;
-          const unsigned int bm = __ballot_sync(0xffffffffu, sel);
-          if (!COUNT && sel) fn(p, f, base + run + __popc(bm & ((1u << lane) - 1u)), vobj, r[k]);
-          run += __popc(bm);
-        }
-      if (COUNT && lane == 0) off[p] = (unsigned int)run;
+  const bool vec = (a.F % 4 == 0);
+  for (int m = threadIdx.x; m < L.nm; m += CT) {
+    const unsigned int e0 = L.off[m];
+    if (L.off[m + 1] == e0) continue;
+    const int p = (int)L.mpix[m];
+    const float vobj = L.vobj[m];
+    const float thr = __fmul_rn(L.rmax[m], a.min_rel);              // corresp.py:62-64 (float32 product)
+    const float* row = fcb + (size_t)p * a.O * a.F;
+    unsigned int e = e0;
+    if (vec) {
+      for (int f = 0; f < a.F; f += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(row + f));
+        if (v.x > thr) fn(p, f, e++, vobj, v.x);
+        if (v.y > thr) fn(p, f + 1, e++, vobj, v.y);
+        if (v.z > thr) fn(p, f + 2, e++, vobj, v.z);
+        if (v.w > thr) fn(p, f + 3, e++, vobj, v.w);
+      }
+    } else {
+      for (int f = 0; f < a.F; ++f) {
+        const float v = __ldg(row + f);
+        if (v > thr) fn(p, f, e++, vobj, v);
+      }
     }
   }
 }
@@ -142,32 +130,79 @@ __global__ void __launch_bounds__(CT, 1) corresp_kernel(CorrArgs a) {
   const int seg = blockIdx.x, b = seg / a.J, j = seg % a.J, tid = threadIdx.x;
   const int obj_id = a.obj_ids[j];
   const int HW = a.h * a.w;
-  unsigned int* off = a.off + (size_t)seg * (HW + 1);
+  unsigned int* mpix = a.ws + (size_t)seg * 4 * (HW + 1);
+  float* vobj_l = reinterpret_cast<float*>(mpix + (HW + 1));
+  float* rmax_l = reinterpret_cast<float*>(mpix + 2 * (HW + 1));
+  unsigned int* off = mpix + 3 * (HW + 1);
   const size_t seg_base = (size_t)seg * a.cap;
   if (obj_id < 1 || obj_id > a.O) {
     if (tid == 0) { a.counts[seg] = 0; if (a.totals) a.totals[seg] = 0; }
     return;
   }
-  // ---- phase 1: counts + exclusive scan ----
-  for_each_candidate<true>(a, b, obj_id, off, [](int, int, unsigned int, float, float) {});
+  // ---- phase 0: ordered list of masked pixels (obj_conf > tau_a, corresp.py:46-47); contiguous range per thread ----
+  const float* oc = a.obj_conf + (size_t)b * HW * (a.O + 1) + obj_id;
+  const int per = (HW + CT - 1) / CT;
+  const int lo = min(tid * per, HW), hi = min(lo + per, HW);
+  int nmask = 0;
+  for (int i = lo; i < hi; ++i) nmask += (__ldg(oc + (size_t)i * (a.O + 1)) > a.min_obj_conf);
+  int nm;
+  {
+    int base = block_scan_excl(nmask, scan_sh, &nm);
+    for (int i = lo; i < hi; ++i) {
+      const float v = __ldg(oc + (size_t)i * (a.O + 1));
+      if (v > a.min_obj_conf) { mpix[base] = (unsigned int)i; vobj_l[base] = v; ++base; }
+    }
+  }
+  __syncthreads();
+  // ---- phase 1: row max and number of selected fragments per masked pixel, then exclusive scan ----
+  {
+    const float* fcb = a.frag_conf + ((size_t)b * HW * a.O + (obj_id - 1)) * a.F;
+    const bool vec = (a.F % 4 == 0);
+    for (int m = tid; m < nm; m += CT) {
+      const float* row = fcb + (size_t)mpix[m] * a.O * a.F;
+      float mx = -INFINITY;
+      if (vec) {
+        for (int f = 0; f < a.F; f += 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(row + f));
+          mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+        }
+      } else {
+        for (int f = 0; f < a.F; ++f) mx = fmaxf(mx, __ldg(row + f));
+      }
+      const float thr = __fmul_rn(mx, a.min_rel);
+      int c = 0;
+      if (vec) {
+        for (int f = 0; f < a.F; f += 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(row + f));
+          c += (v.x > thr) + (v.y > thr) + (v.z > thr) + (v.w > thr);
+        }
+      } else {
+        for (int f = 0; f < a.F; ++f) c += (__ldg(row + f) > thr);
+      }
+      rmax_l[m] = mx;
+      off[m] = (unsigned int)c;
+    }
+  }
   __syncthreads();
   int total;
   {
-    const int per = (HW + CT - 1) / CT;
-    const int lo = tid * per, hi = min(lo + per, HW);
-    int s = 0;
-    for (int i = lo; i < hi; ++i) s += (int)off[i];
-    int base = block_scan_excl(s, scan_sh, &total);
-    for (int i = lo; i < hi; ++i) { const int c = (int)off[i]; off[i] = (unsigned int)base; base += c; }
-    if (tid == 0) off[HW] = (unsigned int)total;
+    const int per2 = (nm + CT - 1) / CT;
+    const int l2 = min(tid * per2, nm), h2 = min(l2 + per2, nm);
+    int sc = 0;
+    for (int i = l2; i < h2; ++i) sc += (int)off[i];
+    int base = block_scan_excl(sc, scan_sh, &total);
+    for (int i = l2; i < h2; ++i) { const int c = (int)off[i]; off[i] = (unsigned int)base; base += c; }
+    if (tid == 0) off[nm] = (unsigned int)total;
     __syncthreads();
   }
+  SegLists L;
+  L.mpix = mpix; L.vobj = vobj_l; L.rmax = rmax_l; L.off = off; L.nm = nm;
   if (tid == 0 && a.totals) a.totals[seg] = total;
   const bool topk = a.max_corr > 0 && total > a.max_corr;
   if (!topk) {
     const int n = total < a.cap ? total : a.cap;
     if (tid == 0) a.counts[seg] = n;
-    for_each_candidate<false>(a, b, obj_id, off, [&](int p, int f, unsigned int e, float vo, float vf) {
+    for_each_candidate(a, b, obj_id, L, [&](int p, int f, unsigned int e, float vo, float vf) {
       if ((int)e < a.cap) write_row(a, b, obj_id, seg_base + e, p, f, vo, vf);
     });
     return;
@@ -185,32 +220,46 @@ __global__ void __launch_bounds__(CT, 1) corresp_kernel(CorrArgs a) {
   const int widths[6] = {11, 11, 10, 11, 11, 10};
   for (int d = 0; d < 6; ++d) {
     const int sh_ = shifts[d], wd = widths[d];
+    if (d == 3 && s_need == s_count) break;     // all rows tied with the K-th confidence are kept: no index digits needed
     for (int i = tid; i < 2048; i += CT) hist[i] = 0u;
     __syncthreads();
     const unsigned long long pre = s_prefix, mk = s_maskbits;
-    for_each_candidate<false>(a, b, obj_id, off, [&](int, int, unsigned int e, float vo, float vf) {
+    for_each_candidate(a, b, obj_id, L, [&](int, int, unsigned int e, float vo, float vf) {
       const unsigned long long key = make_key(vo, vf, e);
       if ((key & mk) == pre) atomicAdd(&hist[(unsigned int)(key >> sh_) & ((1u << wd) - 1u)], 1u);
     });
     __syncthreads();
-    // suffix scan from the top bin: thread t owns bins 2047-2t and 2046-2t
-    const int b0 = 2047 - 2 * tid, b1 = 2046 - 2 * tid;
-    const int c0 = (int)hist[b0], c1 = (int)hist[b1];
+    // suffix scan from the top bin: thread t owns bins 2047-4t .. 2044-4t
+    int cb[4];
+    int csum = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { cb[q] = (int)hist[2047 - 4 * tid - q]; csum += cb[q]; }
     int tot2;
-    const int above = block_scan_excl(c0 + c1, scan_sh, &tot2);     // rows in bins strictly above b0
+    int above = block_scan_excl(csum, scan_sh, &tot2);            // rows in bins strictly above this thread's first bin
     const int need = s_need;
     __syncthreads();
-    if (above < need && need <= above + c0) { s_prefix = pre | ((unsigned long long)b0 << sh_); s_need = need - above; }
-    else if (above + c0 < need && need <= above + c0 + c1) { s_prefix = pre | ((unsigned long long)b1 << sh_); s_need = need - above - c0; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (above < need && need <= above + cb[q]) {
+        s_prefix = pre | ((unsigned long long)(2047 - 4 * tid - q) << sh_);
+        s_need = need - above;
+      }
+      above += cb[q];
+    }
     if (tid == 0) s_maskbits = mk | (((1ULL << wd) - 1ULL) << sh_);
     __syncthreads();
+    if (d == 2) {                               // number of rows whose confidence equals the K-th one
+      const unsigned int b3 = (unsigned int)(s_prefix >> sh_) & ((1u << wd) - 1u);
+      if (tid == 0) s_count = (int)hist[b3];
+      __syncthreads();
+    }
   }
   // s_prefix is now the K-th largest key; keys are unique (emission index), so exactly K keys are >= it
   const unsigned long long kth = s_prefix;
   if (tid == 0) s_count = 0;
   for (int i = tid; i < SORT_MAX; i += CT) { keys[i] = 0ULL; payload[i] = 0u; }
   __syncthreads();
-  for_each_candidate<false>(a, b, obj_id, off, [&](int p, int f, unsigned int e, float vo, float vf) {
+  for_each_candidate(a, b, obj_id, L, [&](int p, int f, unsigned int e, float vo, float vf) {
     const unsigned long long key = make_key(vo, vf, e);
     if (key >= kth) {
       const int slot = atomicAdd(&s_count, 1);
@@ -253,7 +302,7 @@ extern "C" {
 
 size_t epos_corresp_workspace_bytes(int B, int J, int h, int w) {
   if (B <= 0 || J <= 0 || h <= 0 || w <= 0) return 0;
-  return (size_t)B * J * ((size_t)h * w + 1) * 4 + 256;
+  return (size_t)B * J * ((size_t)h * w + 1) * 16 + 256;
 }
 
 int epos_corresp(const float* obj_conf, const float* frag_conf, const float* frag_loc, int B, int h, int w, int num_objs,
@@ -275,7 +324,7 @@ int epos_corresp(const float* obj_conf, const float* frag_conf, const float* fra
   a.min_obj_conf = min_obj_conf; a.min_rel = min_frag_rel_conf; a.cap = cap; a.max_corr = max_corr;
   a.c2d = coord_2d; a.c3d = coord_3d; a.conf = conf; a.conf_obj = conf_obj; a.conf_frag = conf_frag; a.px = px; a.frag = frag;
   a.counts = counts; a.totals = totals;
-  a.off = reinterpret_cast<unsigned int*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  a.ws = reinterpret_cast<unsigned int*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
   const size_t smem = 2048 * 4 + (size_t)SORT_MAX * 12;
   static bool attr = false;
   if (!attr) {

@@ -10,7 +10,8 @@
 namespace epos {
 namespace pose {
 
-constexpr int FIT_SCRATCH_DOUBLES = 12 * 12 * 2 + 12 + 48;   // A, V, w, reduction output
+constexpr int FIT_SCRATCH_DOUBLES = 12 * 12 * 2 + 12 + 28;   // A, V, w, reduction output
+constexpr int WARP_FIT_MAX = 21;                             // points a warp-level fit handles (one per lane, 14 doubles each)
 constexpr int FIT_NRED = 28;
 
 struct WarpGroup {
@@ -322,6 +323,73 @@ __device__ inline void lm_eval(const G& g, const PointView& pv, const double* pa
     }
   }
   g.reduce(acc, nacc, red);
+}
+
+// Warp-level evaluation for n <= WARP_FIT_MAX points (one point per lane): every lane stores its 14 per-point
+// quantities (j0[6], j1[6], ex, ey) in the warp's scratch (the Jacobi A/V/w area, idle during LM), then lanes 0..27 each
+// form one of the 28 sums.
+template <>
+__device__ inline void lm_eval<WarpGroup>(const WarpGroup& g, const PointView& pv, const double* param, bool with_jac,
+                                          double* red) {
+  double R[9], dR[27];
+  rodrigues_to_matrix(param, R, with_jac ? dR : nullptr);
+  double* rows = g.sh;                         // [n][14] <= 294 doubles (A + V + w = 300)
+  const int n = pv.n, lane = g.rank;
+  double e2 = 0.0;
+  if (lane < n) {
+    double p[3], uv[2];
+    pv.get(lane, p, uv);
+    const double Y0 = R[0] * p[0] + R[1] * p[1] + R[2] * p[2] + param[3];
+    const double Y1 = R[3] * p[0] + R[4] * p[1] + R[5] * p[2] + param[4];
+    const double Y2 = R[6] * p[0] + R[7] * p[1] + R[8] * p[2] + param[5];
+    const double iz = Y2 != 0.0 ? 1.0 / Y2 : 1.0;
+    const double x = Y0 * iz, y = Y1 * iz;
+    const double ex = x - uv[0], ey = y - uv[1];
+    e2 = ex * ex + ey * ey;
+    if (with_jac) {
+      double* r = rows + lane * 14;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double* d = dR + 9 * k;
+        const double dY0 = d[0] * p[0] + d[1] * p[1] + d[2] * p[2];
+        const double dY1 = d[3] * p[0] + d[4] * p[1] + d[5] * p[2];
+        const double dY2 = d[6] * p[0] + d[7] * p[1] + d[8] * p[2];
+        r[k] = iz * (dY0 - x * dY2);
+        r[6 + k] = iz * (dY1 - y * dY2);
+      }
+      r[3] = iz; r[4] = 0.0; r[5] = -x * iz;
+      r[9] = 0.0; r[10] = iz; r[11] = -y * iz;
+      r[12] = ex; r[13] = ey;
+    }
+  }
+  if (!with_jac) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+    if (lane == 0) red[0] = e2;
+    __syncwarp();
+    return;
+  }
+  __syncwarp();
+  if (lane < FIT_NRED) {
+    // sum_i r[ia0] r[ib0] + r[ia1] r[ib1]: JtJ(a,b) -> (a, b | 6+a, 6+b); JtErr(a) -> (a, 12 | 6+a, 13); err^2 -> (12,12|13,13)
+    int ia0, ib0, ia1, ib1;
+    if (lane < 21) {
+      int k = lane, a = 0, b = 0;
+      for (a = 0; a < 6; ++a) { const int len = 6 - a; if (k < len) { b = a + k; break; } k -= len; }
+      ia0 = a; ib0 = b; ia1 = 6 + a; ib1 = 6 + b;
+    } else if (lane < 27) {
+      ia0 = lane - 21; ib0 = 12; ia1 = 6 + lane - 21; ib1 = 13;
+    } else {
+      ia0 = 12; ib0 = 12; ia1 = 13; ib1 = 13;
+    }
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double* r = rows + i * 14;
+      s += r[ia0] * r[ib0] + r[ia1] * r[ib1];
+    }
+    red[lane] = s;
+  }
+  __syncwarp();
 }
 
 __device__ inline bool lm_step(const double* red, const double* prev, int lambdaLg10, double* param) {

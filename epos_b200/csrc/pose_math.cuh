@@ -82,9 +82,29 @@ __device__ inline bool polar_rotation(const double* M, double* R) {
   return true;
 }
 
-// serial cyclic Jacobi for tiny symmetric matrices (n = 3); V columns = eigenvectors
+// Jacobi eigen-solvers in the round-robin parallel ordering (each step of a sweep rotates n/2 disjoint index pairs at
+// once: A <- J^T A J, all angles taken from A before the step).  Stand in for the SVDs of OpenCV's
+// cvFindExtrinsicCameraParams2 / cvFindHomography (solver_epnp_lm.h:139-146 call path).
+__device__ __forceinline__ void jacobi_pair(int m, int step, int k, int* p, int* q) {
+  const int a = k == 0 ? m - 1 : (step + k) % (m - 1);
+  const int b = k == 0 ? step : (step - k + (m - 1)) % (m - 1);
+  *p = a < b ? a : b;
+  *q = a < b ? b : a;
+}
+__device__ __forceinline__ void jacobi_angle(const double* A, int n, int p, int q, double* c, double* s) {
+  const double apq = A[p * n + q];
+  *c = 1.0; *s = 0.0;
+  if (apq != 0.0) {
+    const double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
+    const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+    *c = 1.0 / sqrt(t * t + 1.0);
+    *s = t * (*c);
+  }
+}
+
+// serial version for n = 3 (every thread computes it redundantly on private copies); V columns = eigenvectors
 __device__ inline void jacobi_eig3(double* A, double* V, double* w) {
-  const int n = 3;
+  const int n = 3, m = 4;
   for (int i = 0; i < 9; ++i) V[i] = (i % 4 == 0) ? 1.0 : 0.0;
   for (int sweep = 0; sweep < 60; ++sweep) {
     double off = 0.0, diag = 0.0;
@@ -93,39 +113,38 @@ __device__ inline void jacobi_eig3(double* A, double* V, double* w) {
         const double v = A[i * n + j] * A[i * n + j];
         if (i == j) diag += v; else off += v;
       }
-    if (off <= 1e-300 || off < 1e-32 * diag) break;
-    for (int p = 0; p < n - 1; ++p)
-      for (int q = p + 1; q < n; ++q) {
-        const double apq = A[p * n + q];
-        if (apq == 0.0) continue;
-        const double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
-        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-        for (int k = 0; k < n; ++k) {
-          const double akp = A[k * n + p], akq = A[k * n + q];
-          A[k * n + p] = c * akp - s * akq;
-          A[k * n + q] = s * akp + c * akq;
+    if (off <= 1e-300 || off < 1e-28 * diag) break;
+    for (int step = 0; step < m - 1; ++step)
+      for (int k = 0; k < m / 2; ++k) {                  // at most one real pair per step for n = 3
+        int p, q;
+        jacobi_pair(m, step, k, &p, &q);
+        if (q >= n) continue;
+        double c, s;
+        jacobi_angle(A, n, p, q, &c, &s);
+        for (int r = 0; r < n; ++r) {
+          const double akp = A[r * n + p], akq = A[r * n + q];
+          A[r * n + p] = c * akp - s * akq;
+          A[r * n + q] = s * akp + c * akq;
+          const double vkp = V[r * n + p], vkq = V[r * n + q];
+          V[r * n + p] = c * vkp - s * vkq;
+          V[r * n + q] = s * vkp + c * vkq;
         }
-        for (int k = 0; k < n; ++k) {
-          const double apk = A[p * n + k], aqk = A[q * n + k];
-          A[p * n + k] = c * apk - s * aqk;
-          A[q * n + k] = s * apk + c * aqk;
-        }
-        for (int k = 0; k < n; ++k) {
-          const double vkp = V[k * n + p], vkq = V[k * n + q];
-          V[k * n + p] = c * vkp - s * vkq;
-          V[k * n + q] = s * vkp + c * vkq;
+        for (int r = 0; r < n; ++r) {
+          const double apk = A[p * n + r], aqk = A[q * n + r];
+          A[p * n + r] = c * apk - s * aqk;
+          A[q * n + r] = s * apk + c * aqk;
         }
       }
   }
   for (int i = 0; i < n; ++i) w[i] = A[i * n + i];
 }
 
-// Warp-cooperative cyclic Jacobi on a symmetric n x n matrix (n <= 12) held in shared memory.
-// All 32 lanes must call.  A is destroyed; V (n x n) receives eigenvectors in columns, w the eigenvalues.
+// Warp-cooperative version on a symmetric n x n matrix (n <= 12) held in shared memory.  All 32 lanes must call.
+// A is destroyed; V (n x n) receives eigenvectors in columns, w the eigenvalues.  Lane j < n/2 owns pair j of a step.
 __device__ inline void jacobi_eig_warp(int n, double* A, double* V, double* w, int lane) {
   for (int i = lane; i < n * n; i += 32) V[i] = (i / n == i % n) ? 1.0 : 0.0;
   __syncwarp();
+  const int m = (n + 1) & ~1, half = m / 2;
   for (int sweep = 0; sweep < 60; ++sweep) {
     double off = 0.0, diag = 0.0;
     for (int i = lane; i < n * n; i += 32) {
@@ -137,61 +156,91 @@ __device__ inline void jacobi_eig_warp(int n, double* A, double* V, double* w, i
       off += __shfl_xor_sync(0xffffffffu, off, o);
       diag += __shfl_xor_sync(0xffffffffu, diag, o);
     }
-    if (off <= 1e-300 || off < 1e-32 * diag) break;
-    for (int p = 0; p < n - 1; ++p)
-      for (int q = p + 1; q < n; ++q) {
-        const double apq = A[p * n + q];
-        if (apq == 0.0) continue;                      // uniform across the warp (shared-memory broadcast)
-        const double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
-        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-        __syncwarp();
-        if (lane < n) {
-          const int k = lane;
-          const double akp = A[k * n + p], akq = A[k * n + q];
-          A[k * n + p] = c * akp - s * akq;
-          A[k * n + q] = s * akp + c * akq;
-          const double vkp = V[k * n + p], vkq = V[k * n + q];
-          V[k * n + p] = c * vkp - s * vkq;
-          V[k * n + q] = s * vkp + c * vkq;
-        }
-        __syncwarp();
-        if (lane < n) {
-          const int k = lane;
-          const double apk = A[p * n + k], aqk = A[q * n + k];
-          A[p * n + k] = c * apk - s * aqk;
-          A[q * n + k] = s * apk + c * aqk;
-        }
-        __syncwarp();
+    if (off <= 1e-300 || off < 1e-28 * diag) break;
+    for (int step = 0; step < m - 1; ++step) {
+      int p = 0, q = n;                                  // q >= n marks "no rotation" for this lane
+      double c = 1.0, s = 0.0;
+      if (lane < half) {
+        jacobi_pair(m, step, lane, &p, &q);
+        if (q < n) jacobi_angle(A, n, p, q, &c, &s);
       }
+      __syncwarp();
+      const int items = half * n;
+      for (int it = lane; it < ((items + 31) & ~31); it += 32) {        // A <- A J, V <- V J
+        const int j = it < items ? it / n : 0, k = it < items ? it % n : 0;
+        const int pj = __shfl_sync(0xffffffffu, p, j), qj = __shfl_sync(0xffffffffu, q, j);
+        const double cj = __shfl_sync(0xffffffffu, c, j), sj = __shfl_sync(0xffffffffu, s, j);
+        if (it < items && qj < n) {
+          const double akp = A[k * n + pj], akq = A[k * n + qj];
+          A[k * n + pj] = cj * akp - sj * akq;
+          A[k * n + qj] = sj * akp + cj * akq;
+          const double vkp = V[k * n + pj], vkq = V[k * n + qj];
+          V[k * n + pj] = cj * vkp - sj * vkq;
+          V[k * n + qj] = sj * vkp + cj * vkq;
+        }
+      }
+      __syncwarp();
+      for (int it = lane; it < ((items + 31) & ~31); it += 32) {        // A <- J^T A
+        const int j = it < items ? it / n : 0, k = it < items ? it % n : 0;
+        const int pj = __shfl_sync(0xffffffffu, p, j), qj = __shfl_sync(0xffffffffu, q, j);
+        const double cj = __shfl_sync(0xffffffffu, c, j), sj = __shfl_sync(0xffffffffu, s, j);
+        if (it < items && qj < n) {
+          const double apk = A[pj * n + k], aqk = A[qj * n + k];
+          A[pj * n + k] = cj * apk - sj * aqk;
+          A[qj * n + k] = sj * apk + cj * aqk;
+        }
+      }
+      __syncwarp();
+    }
   }
   __syncwarp();
   if (lane < n) w[lane] = A[lane * n + lane];
   __syncwarp();
 }
 
-// 6x6 (or smaller) Gaussian elimination with partial pivoting
-__device__ inline bool solve_linear6(double* A, double* b, double* x) {
-  const int n = 6;
-  for (int c = 0; c < n; ++c) {
+// 6x6 Gaussian elimination with partial pivoting, fully unrolled so that the matrix lives in registers
+// (same operation order as a textbook row-major elimination: the oracle's solve_linear).
+__device__ __forceinline__ bool solve_linear6(double* A_, double* b_, double* x) {
+  double A[6][6], b[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    b[r] = b_[r];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) A[r][c] = A_[r * 6 + c];
+  }
+  bool ok = true;
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
     int piv = c;
-    for (int r = c + 1; r < n; ++r)
-      if (fabs(A[r * n + c]) > fabs(A[piv * n + c])) piv = r;
-    if (A[piv * n + c] == 0.0) return false;
-    if (piv != c) {
-      for (int k = 0; k < n; ++k) { const double t = A[c * n + k]; A[c * n + k] = A[piv * n + k]; A[piv * n + k] = t; }
-      const double t = b[c]; b[c] = b[piv]; b[piv] = t;
+    double best = fabs(A[c][c]);
+#pragma unroll
+    for (int r = c + 1; r < 6; ++r) {
+      const double v = fabs(A[r][c]);
+      if (v > best) { best = v; piv = r; }
     }
-    for (int r = c + 1; r < n; ++r) {
-      const double f = A[r * n + c] / A[c * n + c];
-      for (int k = c; k < n; ++k) A[r * n + k] -= f * A[c * n + k];
+    if (best == 0.0) ok = false;
+#pragma unroll
+    for (int r = c + 1; r < 6; ++r)
+      if (piv == r) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { const double t = A[c][k]; A[c][k] = A[r][k]; A[r][k] = t; }
+        const double t = b[c]; b[c] = b[r]; b[r] = t;
+      }
+#pragma unroll
+    for (int r = c + 1; r < 6; ++r) {
+      const double f = A[r][c] / A[c][c];
+#pragma unroll
+      for (int k = c; k < 6; ++k) A[r][k] -= f * A[c][k];
       b[r] -= f * b[c];
     }
   }
-  for (int r = n - 1; r >= 0; --r) {
+  if (!ok) return false;
+#pragma unroll
+  for (int r = 5; r >= 0; --r) {
     double s = b[r];
-    for (int k = r + 1; k < n; ++k) s -= A[r * n + k] * x[k];
-    x[r] = s / A[r * n + r];
+#pragma unroll
+    for (int k = r + 1; k < 6; ++k) s -= A[r][k] * x[k];
+    x[r] = s / A[r][r];
   }
   return true;
 }

@@ -27,11 +27,14 @@ namespace pose {
 
 constexpr int NMAX = 4096;          // max correspondences per problem (shared-memory resident point set)
 constexpr int MAXNB = 8;            // storage stride of neighbour lists
-constexpr int THREADS = 512;
+constexpr int MAX_TRIALS = 20;
+constexpr int THREADS = MAX_TRIALS * 32;      // fit kernel: 20 warps = one warp per LO trial
 constexpr int WARPS = THREADS / 32;
-constexpr int MAX_TRIALS = 32;
-constexpr unsigned short DIST_INF = 0xFFFF;
-constexpr size_t SMEM_CUT_DYN = 201 * 1024;
+constexpr int PT = 512;                       // prep kernel threads
+constexpr int TRIAL_THREADS = THREADS;
+constexpr int PER_THREAD = (NMAX + THREADS - 1) / THREADS;   // contiguous points per thread in ordered compactions
+constexpr int DIST_INF = 0x7fffffff;
+constexpr size_t SMEM_CUT_DYN = 222 * 1024;
 
 enum Phase { PH_MAIN = 0, PH_LO = 1, PH_FINAL = 2, PH_DONE = 3 };
 
@@ -46,7 +49,12 @@ struct ProbState {
   int best_value, best_inl, lo_value, lo_inl;
   int lo_runs, gc_count, lo_final, lo_stage;
   int ni, found, err, pad;
+  int chunk_base, chunk_n;
+  long long t_sample, t_score, t_replay, t_total;   // main_kernel clock64() accumulators (profiling aid)
+  long long t_cut, t_trials, t_final, t_fit;        // other kernels; t_fit = non-minimal fits inside trials (warp 0)
 };
+
+struct PassRecord;
 
 struct Workspace {
   ProbState* st;
@@ -61,7 +69,10 @@ struct Workspace {
   double* capf;             // [P][NMAX*MAXNB]
   double* exc;              // [P][NMAX]
   double* dd;               // [P][NMAX]
-  unsigned short* dist;     // [P][NMAX]
+  int* dist;                // [P][NMAX]
+  int* lstart;              // [P][NMAX+2]  BFS level boundaries
+  unsigned short* order;    // [P][NMAX]    BFS queue
+  PassRecord* recs;         // [P][CHUNK]   hypotheses of the current chunk of RANSAC passes
 };
 
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
@@ -82,7 +93,10 @@ static size_t workspace_layout(int P, void* base, Workspace* w) {
   p = take((size_t)P * NMAX * MAXNB * 8); if (w) w->capf = (double*)p;
   p = take((size_t)P * NMAX * 8); if (w) w->exc = (double*)p;
   p = take((size_t)P * NMAX * 8); if (w) w->dd = (double*)p;
-  p = take((size_t)P * NMAX * 2); if (w) w->dist = (unsigned short*)p;
+  p = take((size_t)P * NMAX * 4); if (w) w->dist = (int*)p;
+  p = take((size_t)P * (NMAX + 2) * 4); if (w) w->lstart = (int*)p;
+  p = take((size_t)P * NMAX * 2); if (w) w->order = (unsigned short*)p;
+  p = take((size_t)P * 80 * 432); if (w) w->recs = (PassRecord*)p;
   return off;
 }
 
@@ -96,7 +110,8 @@ __device__ inline unsigned long long iteration_bound(double confidence, int inl,
 }
 
 // block-wide exclusive scan of one int per thread (THREADS threads); returns exclusive prefix, total via *total
-__device__ inline int block_excl_scan(int v, int* sh /* WARPS+1 ints */, int* total) {
+template <int NW>
+__device__ inline int block_excl_scan(int v, int* sh /* NW+1 ints */, int* total) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int x = v;
 #pragma unroll
@@ -107,17 +122,17 @@ __device__ inline int block_excl_scan(int v, int* sh /* WARPS+1 ints */, int* to
   if (lane == 31) sh[w] = x;
   __syncthreads();
   if (w == 0) {
-    int s = lane < WARPS ? sh[lane] : 0;
+    int s = lane < NW ? sh[lane] : 0;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int y = __shfl_up_sync(0xffffffffu, s, o);
       if (lane >= o) s += y;
     }
-    if (lane < WARPS) sh[lane] = s;      // inclusive over warps
+    if (lane < NW) sh[lane] = s;      // inclusive over warps
   }
   __syncthreads();
   const int base = w > 0 ? sh[w - 1] : 0;
-  *total = sh[WARPS - 1];
+  *total = sh[NW - 1];
   __syncthreads();
   return base + x - v;
 }
@@ -125,7 +140,7 @@ __device__ inline int block_excl_scan(int v, int* sh /* WARPS+1 ints */, int* to
 // =====================================================================================================
 // prep
 // =====================================================================================================
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(PT, 1)
 prep_kernel(Workspace ws, const double* __restrict__ c2d, const double* __restrict__ c3d, const int* __restrict__ offsets,
             const int* __restrict__ counts, const double* __restrict__ Kmat, const unsigned long long* __restrict__ seeds,
             epos_fit_params prm, int* __restrict__ labeling, double* __restrict__ poses) {
@@ -136,14 +151,16 @@ prep_kernel(Workspace ws, const double* __restrict__ c2d, const double* __restri
   const int off = offsets[p];
   double* rec = poses + (size_t)p * EPOS_POSE_RECORD_DOUBLES;
   if (tid < EPOS_POSE_RECORD_DOUBLES) rec[tid] = 0.0;
-  for (int i = tid; i < N; i += THREADS) labeling[off + i] = 0;
+  for (int i = tid; i < N; i += PT) labeling[off + i] = 0;
   const bool ok = N >= 6 && N <= NMAX;          // scripts/infer.py:417-422 skips objects with < 6 correspondences
   if (tid == 0) {
     st->N = N; st->valid = ok ? 1 : 0; st->err = N > NMAX ? 1 : 0;
     st->phase = ok ? PH_MAIN : PH_DONE;
     st->iter = 0; st->pass = 0; st->best_value = 0; st->best_inl = 0; st->coverage = 0.0;
     st->lo_runs = 0; st->gc_count = 0; st->lo_final = 0; st->lo_stage = 0; st->ni = 0; st->found = 0;
-    st->lo_value = 0; st->lo_inl = 0; st->used_pixels = 0;
+    st->lo_value = 0; st->lo_inl = 0; st->used_pixels = 0; st->chunk_base = 0; st->chunk_n = 0;
+    st->t_sample = st->t_score = st->t_replay = st->t_total = 0;
+    st->t_cut = st->t_trials = st->t_final = st->t_fit = 0;
     st->seed = seeds[p];
     st->max_iteration = iteration_bound(1.0 /* set below */, 1, N > 0 ? N : 1);
     for (int i = 0; i < 12; ++i) { st->best_model[i] = 0.0; st->lo_model[i] = 0.0; }
@@ -164,9 +181,9 @@ prep_kernel(Workspace ws, const double* __restrict__ c2d, const double* __restri
   unsigned long long* table = reinterpret_cast<unsigned long long*>(smem_raw + 5 * NMAX * 4);   // 8192 hash slots
   int* scan_sh = reinterpret_cast<int*>(smem_raw + 5 * NMAX * 4 + 8192 * 8);
   const float sc = (float)0;  (void)sc;
-  for (int i = tid; i < 8192; i += THREADS) table[i] = ~0ULL;
+  for (int i = tid; i < 8192; i += PT) table[i] = ~0ULL;
   __syncthreads();
-  for (int i = tid; i < N; i += THREADS) {
+  for (int i = tid; i < N; i += PT) {
     const double u = c2d[2 * (size_t)(off + i)], v = c2d[2 * (size_t)(off + i) + 1];
     const double x = c3d[3 * (size_t)(off + i)], y = c3d[3 * (size_t)(off + i) + 1], z = c3d[3 * (size_t)(off + i) + 2];
     P5[i] = st->Kinv[0] * u + st->Kinv[1] * v + st->Kinv[2];
@@ -190,10 +207,10 @@ prep_kernel(Workspace ws, const double* __restrict__ c2d, const double* __restri
   // dense ids of the occupied slots
   {
     int cnt = 0;
-    const int per = 8192 / THREADS;
+    const int per = 8192 / PT;
     for (int k = 0; k < per; ++k) cnt += table[tid * per + k] != ~0ULL;
     int total;
-    int base = block_excl_scan(cnt, scan_sh, &total);
+    int base = block_excl_scan<PT / 32>(cnt, scan_sh, &total);
     // the key's high bits are overwritten by the dense id: slot -> (id << 40 | low 40 bits kept for matching is not
     // possible), so ids go to a parallel array placed over the neighbourhood scratch that follows
     unsigned short* slot_id = reinterpret_cast<unsigned short*>(scan_sh + 64);
@@ -202,7 +219,7 @@ prep_kernel(Workspace ws, const double* __restrict__ c2d, const double* __restri
     if (tid == 0) st->used_pixels = total;
     __syncthreads();
     unsigned short* pixg = ws.pix + (size_t)p * NMAX;
-    for (int i = tid; i < N; i += THREADS) {
+    for (int i = tid; i < N; i += PT) {
       const double u = c2d[2 * (size_t)(off + i)], v = c2d[2 * (size_t)(off + i) + 1];
       const unsigned long long key = ((unsigned long long)(unsigned int)(int)u << 32) | (unsigned long long)(unsigned int)(int)v;
       unsigned int h = (unsigned int)(mix64(key) & 8191ULL);
@@ -216,7 +233,7 @@ prep_kernel(Workspace ws, const double* __restrict__ c2d, const double* __restri
   const int KN = prm.max_neighbors < MAXNB ? prm.max_neighbors : MAXNB;
   const float r2 = (float)prm.neighborhood_ball_radius * (float)prm.neighborhood_ball_radius;
   short* nbr = ws.nbr + (size_t)p * NMAX * MAXNB;
-  for (int i = tid; i < N; i += THREADS) {
+  for (int i = tid; i < N; i += PT) {
     float bd[MAXNB];
     int bj[MAXNB];
 #pragma unroll
@@ -254,9 +271,9 @@ prep_kernel(Workspace ws, const double* __restrict__ c2d, const double* __restri
   int* rev_off = ws.rev_off + (size_t)p * (NMAX + 1);
   int* rev_idx = ws.rev_idx + (size_t)p * NMAX * MAXNB;
   int* indeg = reinterpret_cast<int*>(smem_raw);                         // q is dead now
-  for (int i = tid; i <= N; i += THREADS) indeg[i] = 0;
+  for (int i = tid; i <= N; i += PT) indeg[i] = 0;
   __syncthreads();
-  for (int i = tid; i < N; i += THREADS)
+  for (int i = tid; i < N; i += PT)
     for (int k = 0; k < MAXNB; ++k) {
       const int j = nbr[(size_t)i * MAXNB + k];
       unsigned char own = 0;
@@ -271,26 +288,26 @@ prep_kernel(Workspace ws, const double* __restrict__ c2d, const double* __restri
   __syncthreads();
   {
     // exclusive scan of indeg over N nodes (N <= 4096 = 8 per thread)
-    const int per = NMAX / THREADS;
+    const int per = NMAX / PT;
     int loc[per];
     int s = 0;
     for (int k = 0; k < per; ++k) { const int i = tid * per + k; loc[k] = i < N ? indeg[i] : 0; s += loc[k]; }
     int* scan2 = indeg + NMAX + 8;
     int total;
-    int base = block_excl_scan(s, scan2, &total);
+    int base = block_excl_scan<PT / 32>(s, scan2, &total);
     for (int k = 0; k < per; ++k) { const int i = tid * per + k; if (i < N) rev_off[i] = base; base += loc[k]; }
     if (tid == 0) rev_off[N] = total;
     __syncthreads();
-    for (int i = tid; i < N; i += THREADS) indeg[i] = rev_off[i];          // fill cursors
+    for (int i = tid; i < N; i += PT) indeg[i] = rev_off[i];          // fill cursors
     __syncthreads();
-    for (int i = tid; i < N; i += THREADS)
+    for (int i = tid; i < N; i += PT)
       for (int k = 0; k < MAXNB; ++k)
         if (owned[(size_t)i * MAXNB + k]) {
           const int j = nbr[(size_t)i * MAXNB + k];
           rev_idx[atomicAdd(&indeg[j], 1)] = i * MAXNB + k;
         }
     __syncthreads();
-    for (int i = tid; i < N; i += THREADS) {                                // sort each short list (reproducibility)
+    for (int i = tid; i < N; i += PT) {                                // sort each short list (reproducibility)
       const int b = rev_off[i], e = rev_off[i + 1];
       for (int a = b + 1; a < e; ++a) {
         const int v = rev_idx[a];
@@ -310,10 +327,13 @@ struct SmemPoints {
   unsigned short* pix;
 };
 
-__device__ inline unsigned char* load_points(unsigned char* smem, const Workspace& ws, int p, int N, SmemPoints* sp) {
+__device__ inline unsigned char* load_points(unsigned char* smem, const Workspace& ws, int p, int N, SmemPoints* sp,
+                                            bool& loaded) {
   double* d = reinterpret_cast<double*>(smem);
   sp->un = d; sp->vn = d + NMAX; sp->x = d + 2 * NMAX; sp->y = d + 3 * NMAX; sp->z = d + 4 * NMAX;
   sp->pix = reinterpret_cast<unsigned short*>(d + 5 * NMAX);
+  if (loaded) return smem + 5 * NMAX * 8 + NMAX * 2;
+  loaded = true;
   const double* P5 = ws.pts + (size_t)p * 7 * NMAX;
   const unsigned short* pg = ws.pix + (size_t)p * NMAX;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
@@ -324,25 +344,44 @@ __device__ inline unsigned char* load_points(unsigned char* smem, const Workspac
   return smem + 5 * NMAX * 8 + NMAX * 2;
 }
 
+// Inlier test of EPOSScoringFunction::getScore (scoring_function.h:236-242): r^2 < T with
+// r^2 = (px/pz - un)^2 + (py/pz - vn)^2.  Evaluated without the divisions as
+// (px - un pz)^2 + (py - vn pz)^2 < T pz^2, which is the same predicate for every finite pz != 0 (pz = 0 or a NaN
+// gives "outlier" in both forms).
+__device__ __forceinline__ bool is_inlier(double un, double vn, double x, double y, double z, const double* m, double T) {
+  const double px = fma(m[0], x, fma(m[1], y, fma(m[2], z, m[3])));
+  const double py = fma(m[4], x, fma(m[5], y, fma(m[6], z, m[7])));
+  const double pz = fma(m[8], x, fma(m[9], y, fma(m[10], z, m[11])));
+  const double a = fma(-un, pz, px), b = fma(-vn, pz, py);
+  return fma(a, a, b * b) < T * (pz * pz);
+}
+
 // EPOSScoringFunction::getScore (scoring_function.h:220-267) by one warp: inlier count by ballot, distinct pixels
-// through a per-warp bitset.  bits: NMAX/32 words owned by this warp.
+// through a per-warp bitset.  bits: NMAX/32 words owned by this warp.  Four points per lane are in flight.
 __device__ inline void score_warp(const SmemPoints& sp, int N, const double* model, double sq_trunc, unsigned int* bits,
                                   int lane, int* inl_out, int* pix_out) {
+  double m[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) m[k] = model[k];
   for (int k = lane; k < NMAX / 32; k += 32) bits[k] = 0u;
   __syncwarp();
   int inl = 0;
-  for (int base = 0; base < N; base += 32) {
-    const int i = base + lane;
-    bool in = false;
-    if (i < N) {
-      const double r2 = sq_residual(sp.un[i], sp.vn[i], sp.x[i], sp.y[i], sp.z[i], model);
-      in = r2 < sq_trunc;
-      if (in) {
-        const unsigned int pid = sp.pix[i];
+  for (int base = 0; base < N; base += 128) {
+    bool in[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * 32 + lane;
+      in[u] = false;
+      if (i < N) in[u] = is_inlier(sp.un[i], sp.vn[i], sp.x[i], sp.y[i], sp.z[i], m, sq_trunc);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (in[u]) {
+        const unsigned int pid = sp.pix[base + u * 32 + lane];
         atomicOr(&bits[pid >> 5], 1u << (pid & 31));
       }
+      inl += __popc(__ballot_sync(0xffffffffu, in[u]));
     }
-    inl += __popc(__ballot_sync(0xffffffffu, in));
   }
   __syncwarp();
   int px = 0;
@@ -379,21 +418,23 @@ struct PassRecord {
   int inl[4], pix[4];
 };
 
-__global__ void __launch_bounds__(THREADS, 1) main_kernel(Workspace ws, epos_fit_params prm) {
-  extern __shared__ unsigned char smem_raw[];
-  const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+constexpr int CHUNK = 80;            // RANSAC passes evaluated per chunk (a multiple of the 20 warps) (records survive LO rounds in the workspace)
+
+__device__ __noinline__ void phase_main(const Workspace& ws, const epos_fit_params& prm, int p, unsigned char* smem_raw,
+                                        bool& pts_loaded) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   ProbState* st = ws.st + p;
-  if (st->phase != PH_MAIN) return;
   const int N = st->N;
   SmemPoints sp;
-  unsigned char* rest = load_points(smem_raw, ws, p, N, &sp);
+  unsigned char* rest = load_points(smem_raw, ws, p, N, &sp, pts_loaded);
   unsigned int* bits = reinterpret_cast<unsigned int*>(rest) + warp * (NMAX / 32);
-  PassRecord* recs = reinterpret_cast<PassRecord*>(rest + WARPS * (NMAX / 32) * 4);
-  double* best_model = reinterpret_cast<double*>(recs + WARPS);
+  double* best_model = reinterpret_cast<double*>(rest + WARPS * (NMAX / 32) * 4);
+  PassRecord* recs = ws.recs + (size_t)p * CHUNK;                  // global (L2): hypotheses do not depend on the state
   // state (identical in every thread)
   unsigned long long iter = st->iter, max_iteration = st->max_iteration;
   const unsigned long long seed = st->seed;
   int pass = st->pass, best_value = st->best_value, best_inl = st->best_inl, lo_runs = st->lo_runs, gc_count = st->gc_count;
+  int chunk_base = st->chunk_base, chunk_n = st->chunk_n;
   double coverage = st->coverage;
   const int used_pixels = st->used_pixels;
   const double sq_trunc = st->sq_trunc;
@@ -401,39 +442,54 @@ __global__ void __launch_bounds__(THREADS, 1) main_kernel(Workspace ws, epos_fit
   if (tid < 12) best_model[tid] = st->best_model[tid];
   __syncthreads();
   bool ended = false, to_lo = false;
+  long long t_sample = 0, t_score = 0, t_replay = 0;
+  const long long t_begin = clock64();
   while (true) {
-    // ---- evaluate WARPS passes, one per warp ----
-    {
-      PassRecord* rc = recs + warp;
-      const int my_pass = pass + warp;
-      int fails = -1, nm = 0;
-      const double* PU = ws.pts + (size_t)p * 7 * NMAX + 5 * NMAX;       // original pixel coordinates (u row, v row)
-      while (++fails < prm.max_unsuccessful) {
-        int s[3];
-        if (!unique_set(seed, 0, (u64)my_pass, (u64)fails, N, 3, s)) continue;
-        // isValidSample (perspective_n_point_estimator.h:172-198): pixel-space triangle area > min_triangle_area
-        const double u0 = PU[s[0]], v0 = PU[NMAX + s[0]];
-        const double area = 0.5 * fabs((PU[s[1]] - u0) * (PU[NMAX + s[2]] - v0) - (PU[s[2]] - u0) * (PU[NMAX + s[1]] - v0));
-        if (!(area > prm.min_triangle_area)) continue;
-        double un[3], vn[3], X[3][3];
-        for (int k = 0; k < 3; ++k) {
-          un[k] = sp.un[s[k]]; vn[k] = sp.vn[s[k]];
-          X[k][0] = sp.x[s[k]]; X[k][1] = sp.y[s[k]]; X[k][2] = sp.z[s[k]];
+    long long t0 = clock64();
+    if (pass >= chunk_base + chunk_n) {
+      // ---- phase A: one THREAD per pass: sample until a valid sample gives >= 1 admissible P3P pose ----
+      chunk_base = pass; chunk_n = CHUNK;
+      if (tid < CHUNK) {
+        PassRecord* rc = recs + tid;
+        const int my_pass = chunk_base + tid;
+        int fails = -1, nm = 0;
+        const double* PU = ws.pts + (size_t)p * 7 * NMAX + 5 * NMAX;   // original pixel coordinates (u row, v row)
+        double models[48];
+        while (++fails < prm.max_unsuccessful) {
+          int s[3];
+          if (!unique_set(seed, 0, (u64)my_pass, (u64)fails, N, 3, s)) continue;
+          // isValidSample (perspective_n_point_estimator.h:172-198): pixel-space triangle area > min_triangle_area
+          const double u0 = PU[s[0]], v0 = PU[NMAX + s[0]];
+          const double area = 0.5 * fabs((PU[s[1]] - u0) * (PU[NMAX + s[2]] - v0) - (PU[s[2]] - u0) * (PU[NMAX + s[1]] - v0));
+          if (!(area > prm.min_triangle_area)) continue;
+          double un[3], vn[3], X[3][3];
+          for (int k = 0; k < 3; ++k) {
+            un[k] = sp.un[s[k]]; vn[k] = sp.vn[s[k]];
+            X[k][0] = sp.x[s[k]]; X[k][1] = sp.y[s[k]]; X[k][2] = sp.z[s[k]];
+          }
+          nm = p3p_kneip(un, vn, X, models);
+          if (nm > 0) break;
         }
-        nm = p3p_kneip(un, vn, X, rc->models);       // every lane writes the same values
-        if (nm > 0) break;
+        rc->nm = nm; rc->fails = fails;
+        for (int k = 0; k < 12 * nm; ++k) rc->models[k] = models[k];
       }
-      __syncwarp();
-      if (lane == 0) { rc->nm = nm; rc->fails = fails; }
-      for (int m = 0; m < nm; ++m) {
-        int inl, px;
-        score_warp(sp, N, rc->models + 12 * m, sq_trunc, bits, lane, &inl, &px);
-        if (lane == 0) { rc->inl[m] = inl; rc->pix[m] = px; }
+      __syncthreads();
+      t_sample += clock64() - t0; t0 = clock64();
+      // ---- phase B: one WARP per pass (round-robin): score every solution over all N points ----
+      for (int k = warp; k < CHUNK; k += WARPS) {
+        PassRecord* rc = recs + k;
+        const int nm = rc->nm;
+        for (int m = 0; m < nm; ++m) {
+          int inl, px;
+          score_warp(sp, N, rc->models + 12 * m, sq_trunc, bits, lane, &inl, &px);
+          if (lane == 0) { rc->inl[m] = inl; rc->pix[m] = px; }
+        }
       }
+      __syncthreads();
+      t_score += clock64() - t0; t0 = clock64();
     }
-    __syncthreads();
-    // ---- in-order replay (every thread runs the same scalar code on the shared records) ----
-    for (int k = 0; k < WARPS; ++k) {
+    // ---- in-order replay (every thread runs the same scalar code on the same records) ----
+    for (int k = pass - chunk_base; k < chunk_n; ++k) {
       const unsigned long long lim = max_iteration < max_iters ? max_iteration : max_iters;
       if (!(min_iters > iter || iter < lim)) { ended = true; break; }
       if (min_iters < iter) {
@@ -443,7 +499,8 @@ __global__ void __launch_bounds__(THREADS, 1) main_kernel(Workspace ws, epos_fit
       ++iter;
       const PassRecord* rc = recs + k;
       iter += (unsigned long long)rc->fails;
-      for (int m = 0; m < rc->nm; ++m) {
+      const int nm = rc->nm;
+      for (int m = 0; m < nm; ++m) {
         int s_inl = rc->inl[m], s_val = rc->pix[m];
         if (s_inl + 1 < best_inl) { s_inl = 0; s_val = 0; }       // early-out of getScore, scoring_function.h:257-259
         if (best_value < s_val) {
@@ -464,11 +521,13 @@ __global__ void __launch_bounds__(THREADS, 1) main_kernel(Workspace ws, epos_fit
       }
     }
     __syncthreads();
+    t_replay += clock64() - t0;
     if (ended || to_lo) break;
   }
   if (tid == 0) {
+    st->t_sample += t_sample; st->t_score += t_score; st->t_replay += t_replay; st->t_total += clock64() - t_begin;
     st->iter = iter; st->max_iteration = max_iteration; st->pass = pass; st->best_value = best_value;
-    st->best_inl = best_inl; st->coverage = coverage;
+    st->best_inl = best_inl; st->coverage = coverage; st->chunk_base = chunk_base; st->chunk_n = chunk_n;
     for (int i = 0; i < 12; ++i) st->best_model[i] = best_model[i];
     bool start_lo = to_lo;
     if (ended) {
@@ -495,19 +554,18 @@ __global__ void __launch_bounds__(THREADS, 1) main_kernel(Workspace ws, epos_fit
 // =====================================================================================================
 // cut: graph-cut labeling of lo_model
 // =====================================================================================================
-__global__ void __launch_bounds__(THREADS, 1) cut_kernel(Workspace ws, epos_fit_params prm) {
-  extern __shared__ unsigned char smem_raw[];
-  __shared__ int s_flag, s_any;
+__device__ __noinline__ void phase_cut(const Workspace& ws, const epos_fit_params& prm, int p, unsigned char* smem_raw) {
+  __shared__ int s_qn, s_any;
   __shared__ int scan_sh[WARPS + 1];
-  const int p = blockIdx.x, tid = threadIdx.x;
+  const int tid = threadIdx.x;
   ProbState* st = ws.st + p;
-  if (st->phase != PH_LO || st->lo_stage != 0) return;
   const int gc0 = st->gc_count;
   __syncthreads();
-  if (gc0 + 1 >= prm.max_graph_cuts) {                   // while (++graph_cut_number < max) fails
+  if (gc0 + 1 >= prm.max_graph_cuts) {                             // while (++graph_cut_number < max) fails
     if (tid == 0) { ++st->gc_count; finalize_lo(st, prm); }
     return;
   }
+  const long long t_begin = clock64();
   const int N = st->N;
   const double* P5 = ws.pts + (size_t)p * 7 * NMAX;
   const short* nbr = ws.nbr + (size_t)p * NMAX * MAXNB;
@@ -515,6 +573,7 @@ __global__ void __launch_bounds__(THREADS, 1) cut_kernel(Workspace ws, epos_fit_
   const int* rev_off = ws.rev_off + (size_t)p * (NMAX + 1);
   const int* rev_idx = ws.rev_idx + (size_t)p * NMAX * MAXNB;
   double* capf = ws.capf + (size_t)p * NMAX * MAXNB;
+  int* lstart = ws.lstart + (size_t)p * (NMAX + 2);
   const int KN = prm.max_neighbors < MAXNB ? prm.max_neighbors : MAXNB;   // per-node stride of flow / capf
   // shared-memory carve-up by access frequency; what does not fit stays in the (L2-resident) workspace
   size_t used = 0;
@@ -523,14 +582,15 @@ __global__ void __launch_bounds__(THREADS, 1) cut_kernel(Workspace ws, epos_fit_
     if (used + bytes <= SMEM_CUT_DYN) { void* r = smem_raw + used; used += bytes; return r; }
     return fallback;
   };
-  unsigned short* dist = (unsigned short*)carve((size_t)N * 2, ws.dist + (size_t)p * NMAX);
+  int* dist = (int*)carve((size_t)N * 4, ws.dist + (size_t)p * NMAX);
+  unsigned short* order = (unsigned short*)carve((size_t)N * 2, ws.order + (size_t)p * NMAX);
   double* exc = (double*)carve((size_t)N * 8, ws.exc + (size_t)p * NMAX);
   double* flow = (double*)carve((size_t)N * KN * 8, ws.flow + (size_t)p * NMAX * MAXNB);
   double* dd = (double*)carve((size_t)N * 8, ws.dd + (size_t)p * NMAX);
   const double lambda = prm.spatial_coherence_weight, oml = 1.0 - lambda, T = st->sq_trunc;
   double model[12];
   for (int i = 0; i < 12; ++i) model[i] = st->lo_model[i];
-  // ---- unary terms ----
+  // ---- unary terms (GCRANSAC.h:843-860) ----
   for (int i = tid; i < N; i += THREADS) {
     const double r2 = sq_residual(P5[i], P5[NMAX + i], P5[2 * NMAX + i], P5[3 * NMAX + i], P5[4 * NMAX + i], model);
     const double qd = r2 / T;
@@ -558,48 +618,62 @@ __global__ void __launch_bounds__(THREADS, 1) cut_kernel(Workspace ws, epos_fit_
     exc[i] = tr;
   }
   __syncthreads();
-  // ---- preflow-push in waves ----
-  for (int round = 0; round < 1024; ++round) {
-    for (int i = tid; i < N; i += THREADS) dist[i] = exc[i] < 0.0 ? (unsigned short)0 : DIST_INF;
+  // ---- preflow-push in waves.  Each round: reverse BFS from the nodes that still have sink capacity (exc < 0)
+  // over residual arcs (frontier queue, work ~ reached set), then one push wave from the farthest level down. ----
+  // The BFS depth is capped (iterative deepening): excess far from every sink can only matter after the arcs next to
+  // the sinks have carried flow, so shallow rounds come first; a round proves termination only if its BFS ran dry.
+  int depth_cap = 2;
+  for (int round = 0; round < 4096; ++round) {
+    if (tid == 0) { s_qn = 0; s_any = 0; }
     __syncthreads();
-    int level = 0;
-    for (;;) {
-      if (tid == 0) s_flag = 0;
-      __syncthreads();
-      bool changed = false;
-      for (int i = tid; i < N; i += THREADS) {
-        if (dist[i] != DIST_INF) continue;
-        bool hit = false;
-        for (int k = 0; k < KN && !hit; ++k)                     // own arcs i -> j: residual capf - flow
-          if (owned[(size_t)i * MAXNB + k]) {
-            const int j = nbr[(size_t)i * MAXNB + k];
-            if (dist[j] == level && capf[(size_t)i * KN + k] - flow[(size_t)i * KN + k] > 0.0) hit = true;
-          }
-        for (int a = rev_off[i]; a < rev_off[i + 1] && !hit; ++a) {  // reverse arcs i -> x of edges owned by x
-          const int e = rev_idx[a];
-          const int x = e / MAXNB;
-          if (dist[x] == level && lambda + flow[(size_t)x * KN + (e % MAXNB)] > 0.0) hit = true;
-        }
-        if (hit) { dist[i] = (unsigned short)(level + 1); changed = true; }
-      }
-      if (changed) s_flag = 1;
-      __syncthreads();
-      const int f = s_flag;
-      __syncthreads();
-      ++level;
-      if (!f || level >= 0xFFF0) break;
+    for (int i = tid; i < N; i += THREADS) {
+      const bool root = exc[i] < 0.0;
+      dist[i] = root ? 0 : DIST_INF;
+      if (root) order[atomicAdd(&s_qn, 1)] = (unsigned short)i;
     }
-    const int maxlevel = level;
-    if (tid == 0) s_any = 0;
     __syncthreads();
-    bool any = false;
-    for (int i = tid; i < N; i += THREADS) any |= (exc[i] > 0.0 && dist[i] != DIST_INF && dist[i] > 0);
-    if (any) s_any = 1;
+    int level = 0, begin = 0, end = s_qn;
+    if (tid == 0) lstart[0] = 0;
+    while (begin < end && level < depth_cap) {
+      for (int q = begin + tid; q < end; q += THREADS) {
+        const int v = order[q];
+        for (int k = 0; k < KN; ++k)                                 // edges owned by v: arc u -> v has residual lambda + flow
+          if (owned[(size_t)v * MAXNB + k]) {
+            const int u = nbr[(size_t)v * MAXNB + k];
+            if (dist[u] == DIST_INF && lambda + flow[(size_t)v * KN + k] > 0.0 &&
+                atomicCAS(&dist[u], DIST_INF, level + 1) == DIST_INF) {
+              order[atomicAdd(&s_qn, 1)] = (unsigned short)u;
+              if (exc[u] > 0.0) s_any = 1;
+            }
+          }
+        for (int a = rev_off[v]; a < rev_off[v + 1]; ++a) {           // edges owned by u that end in v: arc u -> v forward
+          const int e0 = rev_idx[a];
+          const int u = e0 / MAXNB;
+          const size_t e = (size_t)u * KN + (e0 % MAXNB);
+          if (dist[u] == DIST_INF && capf[e] - flow[e] > 0.0 && atomicCAS(&dist[u], DIST_INF, level + 1) == DIST_INF) {
+            order[atomicAdd(&s_qn, 1)] = (unsigned short)u;
+            if (exc[u] > 0.0) s_any = 1;
+          }
+        }
+      }
+      __syncthreads();
+      begin = end; end = s_qn; ++level;
+      if (tid == 0) lstart[level] = begin;
+      __syncthreads();
+    }
+    const bool exhausted = begin >= end;                              // the BFS ran dry: dist is exact for every node
+    const int maxlevel = exhausted ? level - 1 : level;              // deepest labelled level
+    if (!exhausted && tid == 0) lstart[level + 1] = end;
     __syncthreads();
-    if (!s_any) break;
+    if (!s_any) {
+      if (exhausted) break;
+      depth_cap *= 4;                                                 // nothing to push within the cap: look deeper
+      continue;
+    }
     for (int d = maxlevel; d >= 1; --d) {
-      for (int i = tid; i < N; i += THREADS) {
-        if (dist[i] != d) continue;
+      const int qb = lstart[d], qe = lstart[d + 1];
+      for (int q = qb + tid; q < qe; q += THREADS) {
+        const int i = order[q];
         double ex = exc[i];
         if (!(ex > 0.0)) continue;
         for (int k = 0; k < KN && ex > 0.0; ++k)
@@ -630,13 +704,13 @@ __global__ void __launch_bounds__(THREADS, 1) cut_kernel(Workspace ws, epos_fit_
   // ---- inliers = SINK segment = nodes with a residual path to a node that still has sink capacity ----
   unsigned short* inl = ws.inl + (size_t)p * NMAX;
   {
-    const int per = NMAX / THREADS;
+    const int per = PER_THREAD;
     int cnt = 0;
     for (int k = 0; k < per; ++k) { const int i = tid * per + k; cnt += (i < N && dist[i] != DIST_INF); }
     int total;
-    int base = block_excl_scan(cnt, scan_sh, &total);
+    int base = block_excl_scan<WARPS>(cnt, scan_sh, &total);
     for (int k = 0; k < per; ++k) { const int i = tid * per + k; if (i < N && dist[i] != DIST_INF) inl[base++] = (unsigned short)i; }
-    if (tid == 0) { st->ni = total; ++st->gc_count; st->lo_stage = 1; }
+    if (tid == 0) { st->ni = total; ++st->gc_count; st->lo_stage = 1; st->t_cut += clock64() - t_begin; }
   }
 }
 
@@ -645,34 +719,35 @@ __global__ void __launch_bounds__(THREADS, 1) cut_kernel(Workspace ws, epos_fit_
 // =====================================================================================================
 struct TrialRecord { double model[12]; int ok, inl, pix, pad; };
 
-__global__ void __launch_bounds__(THREADS, 1) trials_kernel(Workspace ws, epos_fit_params prm) {
-  extern __shared__ unsigned char smem_raw[];
-  const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+__device__ __noinline__ void phase_trials(const Workspace& ws, const epos_fit_params& prm, int p, unsigned char* smem_raw,
+                                          bool& pts_loaded) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int TW = TRIAL_THREADS / 32;
   ProbState* st = ws.st + p;
-  if (st->phase != PH_LO || st->lo_stage != 1) return;
+  const long long t_begin = clock64();
+  long long t_fit = 0;
   const int N = st->N, ni = st->ni;
   SmemPoints sp;
-  unsigned char* rest = load_points(smem_raw, ws, p, N, &sp);
-  unsigned int* bits = reinterpret_cast<unsigned int*>(rest) + warp * (NMAX / 32);
-  rest += WARPS * (NMAX / 32) * 4;
+  unsigned char* rest = load_points(smem_raw, ws, p, N, &sp, pts_loaded);
   TrialRecord* recs = reinterpret_cast<TrialRecord*>(rest);
   rest += MAX_TRIALS * sizeof(TrialRecord);
   double* fit_sh = reinterpret_cast<double*>(rest) + warp * FIT_SCRATCH_DOUBLES;
-  rest += WARPS * FIT_SCRATCH_DOUBLES * 8;
+  unsigned int* bits = reinterpret_cast<unsigned int*>(fit_sh);        // the fit scratch is idle while scoring
+  rest += TW * FIT_SCRATCH_DOUBLES * 8;
   unsigned short* sample = reinterpret_cast<unsigned short*>(rest) + warp * 32;
   const unsigned short* inl = ws.inl + (size_t)p * NMAX;
   const int trials = prm.max_lo_trials < MAX_TRIALS ? prm.max_lo_trials : MAX_TRIALS;
   const int sample_size = ni < 21 ? ni : 21;
   const double sq_trunc = st->sq_trunc;
   const int gc = st->gc_count;
-  for (int t = tid; t < MAX_TRIALS; t += THREADS) recs[t].ok = 0;
+  for (int t = tid; t < MAX_TRIALS; t += TRIAL_THREADS) recs[t].ok = 0;
   __syncthreads();
   WarpGroup g;
   g.rank = lane; g.size = 32; g.sh = fit_sh;
   int n_eval = 0;                      // trials actually evaluated (the all-inlier case repeats one model)
   if (sample_size < ni) n_eval = trials;
   else if (3 < ni) n_eval = 1;
-  for (int t = warp; t < n_eval; t += WARPS) {
+  for (int t = warp; t < n_eval; t += TW) {
     if (sample_size < ni) {
       int sel[21];
       unique_set(st->seed, 1, (u64)gc, (u64)t, ni, sample_size, sel);
@@ -684,8 +759,10 @@ __global__ void __launch_bounds__(THREADS, 1) trials_kernel(Workspace ws, epos_f
     PointView pv;
     pv.un = sp.un; pv.vn = sp.vn; pv.x = sp.x; pv.y = sp.y; pv.z = sp.z; pv.idx = sample; pv.n = sample_size;
     double model[12];
+    const long long tf0 = clock64();
     const bool ok = fit_nonminimal_group(g, pv, model);
     __syncwarp();
+    t_fit += clock64() - tf0;
     if (ok) {
       TrialRecord* rc = recs + t;
       if (lane < 12) rc->model[lane] = model[lane];
@@ -698,6 +775,7 @@ __global__ void __launch_bounds__(THREADS, 1) trials_kernel(Workspace ws, epos_f
   }
   __syncthreads();
   if (tid == 0) {
+    st->t_fit += t_fit;
     bool updated = false;
     int mv = st->lo_value, mi = st->lo_inl;
     if (sample_size < ni) {
@@ -719,6 +797,7 @@ __global__ void __launch_bounds__(THREADS, 1) trials_kernel(Workspace ws, epos_f
     st->lo_value = mv; st->lo_inl = mi;
     if (updated) st->lo_stage = 0;                                  // another labeling round (GCRANSAC.h:794-796)
     else finalize_lo(st, prm);
+    st->t_trials += clock64() - t_begin;
   }
 }
 
@@ -731,14 +810,13 @@ __device__ inline void score_cta(const SmemPoints& sp, int N, const double* mode
   const int tid = threadIdx.x;
   for (int k = tid; k < NMAX / 32; k += THREADS) bits[k] = 0u;
   __syncthreads();
-  const int per = NMAX / THREADS;
+  const int per = PER_THREAD;
   unsigned int mask = 0;
   int cnt = 0;
   for (int k = 0; k < per; ++k) {
     const int i = tid * per + k;
     if (i < N) {
-      const double r2 = sq_residual(sp.un[i], sp.vn[i], sp.x[i], sp.y[i], sp.z[i], model);
-      if (r2 < sq_trunc) {
+      if (is_inlier(sp.un[i], sp.vn[i], sp.x[i], sp.y[i], sp.z[i], model, sq_trunc)) {
         mask |= 1u << k; ++cnt;
         const unsigned int pid = sp.pix[i];
         atomicOr(&bits[pid >> 5], 1u << (pid & 31));
@@ -746,7 +824,7 @@ __device__ inline void score_cta(const SmemPoints& sp, int N, const double* mode
     }
   }
   int total;
-  int base = block_excl_scan(cnt, scan_sh, &total);
+  int base = block_excl_scan<WARPS>(cnt, scan_sh, &total);
   if (out)
     for (int k = 0; k < per; ++k)
       if (mask & (1u << k)) out[base++] = (unsigned short)(tid * per + k);
@@ -763,13 +841,12 @@ __device__ inline void score_cta(const SmemPoints& sp, int N, const double* mode
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
-final_kernel(Workspace ws, epos_fit_params prm, const int* __restrict__ offsets, double* __restrict__ poses,
-             int* __restrict__ labeling) {
-  extern __shared__ unsigned char smem_raw[];
+__device__ __noinline__ void phase_final(const Workspace& ws, const epos_fit_params& prm, int p, unsigned char* smem_raw,
+                                         bool& pts_loaded, const int* __restrict__ offsets, double* __restrict__ poses,
+                                         int* __restrict__ labeling) {
   __shared__ int scan_sh[WARPS + 1];
   __shared__ int red_sh;
-  const int p = blockIdx.x, tid = threadIdx.x;
+  const int tid = threadIdx.x;
   ProbState* st = ws.st + p;
   double* rec = poses + (size_t)p * EPOS_POSE_RECORD_DOUBLES;
   if (st->phase != PH_FINAL) {
@@ -777,18 +854,40 @@ final_kernel(Workspace ws, epos_fit_params prm, const int* __restrict__ offsets,
     if (tid == 0 && st->err) rec[14] = -1.0;                      // more than NMAX correspondences
     return;
   }
+  const long long t_begin = clock64();
   const int N = st->N;
   SmemPoints sp;
-  unsigned char* rest = load_points(smem_raw, ws, p, N, &sp);
+  unsigned char* rest = load_points(smem_raw, ws, p, N, &sp, pts_loaded);
   unsigned int* bits = reinterpret_cast<unsigned int*>(rest); rest += (NMAX / 32) * 4;
   unsigned short* listA = reinterpret_cast<unsigned short*>(rest); rest += NMAX * 2;
   unsigned short* listB = reinterpret_cast<unsigned short*>(rest); rest += NMAX * 2;
   unsigned short* listC = reinterpret_cast<unsigned short*>(rest); rest += NMAX * 2;
   double* fit_sh = reinterpret_cast<double*>(rest); rest += FIT_SCRATCH_DOUBLES * 8;
-  double* part = reinterpret_cast<double*>(rest);
+  double* part = reinterpret_cast<double*>(rest); rest += WARPS * FIT_NRED * 8;
+  double* bcast = reinterpret_cast<double*>(rest);                   // 16 doubles: result of a warp-level fit
   __syncthreads();
   CtaGroup g;
   g.rank = tid; g.size = THREADS; g.sh = fit_sh; g.part = part;
+  WarpGroup wg;
+  wg.rank = tid & 31; wg.size = 32; wg.sh = fit_sh;
+  // Non-minimal fit on an index list: small lists (the no-consensus case) are fitted by warp 0 alone, which avoids a
+  // block barrier per reduction; large lists use the whole CTA.
+  auto fit_list = [&](const unsigned short* list, int n, double* m2) -> bool {
+    PointView v;
+    v.un = sp.un; v.vn = sp.vn; v.x = sp.x; v.y = sp.y; v.z = sp.z; v.idx = list; v.n = n;
+    if (n > WARP_FIT_MAX) return fit_nonminimal_group(g, v, m2);
+    __syncthreads();
+    if (tid < 32) {
+      double mm[12];
+      const bool ok = fit_nonminimal_group(wg, v, mm);
+      if (tid == 0) { bcast[12] = ok ? 1.0 : 0.0; for (int i = 0; i < 12; ++i) bcast[i] = ok ? mm[i] : 0.0; }
+    }
+    __syncthreads();
+    for (int i = 0; i < 12; ++i) m2[i] = bcast[i];
+    const bool ok = bcast[12] != 0.0;
+    __syncthreads();
+    return ok;
+  };
   const double sq_trunc = st->sq_trunc;
   double best_model[12];
   for (int i = 0; i < 12; ++i) best_model[i] = st->best_model[i];
@@ -806,8 +905,7 @@ final_kernel(Workspace ws, epos_fit_params prm, const int* __restrict__ offsets,
     int nB = nA, iterations = 0;
     while (++iterations < prm.max_lsq_iters) {
       double m2[12];
-      pv.idx = listB; pv.n = nB;
-      if (!fit_nonminimal_group(g, pv, m2)) break;
+      if (!fit_list(listB, nB, m2)) break;
       int nC, pxC;
       score_cta(sp, N, m2, sq_trunc, bits, scan_sh, listC, &nC, &pxC, &red_sh);
       if (nC < 3) break;
@@ -831,8 +929,7 @@ final_kernel(Workspace ws, epos_fit_params prm, const int* __restrict__ offsets,
   }
   if (!refit_applied) {                                                                  // GCRANSAC.h:510-521
     double m2[12];
-    pv.idx = listA; pv.n = nA;
-    if (fit_nonminimal_group(g, pv, m2))
+    if (fit_list(listA, nA, m2))
       for (int i = 0; i < 12; ++i) best_model[i] = m2[i];
   }
   if (prm.apply_numerical_optimization && nA >= 6) {                                     // progressivex_python.cpp:257-312
@@ -842,7 +939,18 @@ final_kernel(Workspace ws, epos_fit_params prm, const int* __restrict__ offsets,
     matrix_to_rodrigues(R, param);
     param[3] = best_model[3]; param[4] = best_model[7]; param[5] = best_model[11];
     pv.idx = listA; pv.n = nA;
-    lm_refine_group(g, pv, param);
+    if (nA > WARP_FIT_MAX) {
+      lm_refine_group(g, pv, param);
+    } else {
+      __syncthreads();
+      if (tid < 32) {
+        lm_refine_group(wg, pv, param);
+        if (tid == 0) for (int i = 0; i < 6; ++i) bcast[i] = param[i];
+      }
+      __syncthreads();
+      for (int i = 0; i < 6; ++i) param[i] = bcast[i];
+      __syncthreads();
+    }
     bool fin = true;
     for (int i = 0; i < 6; ++i) fin &= isfinite(param[i]);
     if (fin) {
@@ -858,19 +966,50 @@ final_kernel(Workspace ws, epos_fit_params prm, const int* __restrict__ offsets,
   if (tid < 12) rec[tid] = best_model[tid];
   if (tid == 0) {
     rec[12] = (double)nA; rec[13] = (double)st->iter; rec[14] = 1.0; rec[15] = (double)st->gc_count;
-    st->found = 1; st->phase = PH_DONE;
+    st->found = 1; st->phase = PH_DONE; st->t_final += clock64() - t_begin;
   }
   const int off = offsets[p];
   for (int i = tid; i < nA; i += THREADS) labeling[off + listA[i]] = 1;
 }
 
+// One persistent CTA per problem runs the whole state machine; phases re-carve the dynamic shared memory
+// (the cut overwrites the point set, which is reloaded from the L2-resident workspace afterwards).
+__global__ void __launch_bounds__(THREADS, 1)
+fit_kernel(Workspace ws, epos_fit_params prm, const int* __restrict__ offsets, double* __restrict__ poses,
+           int* __restrict__ labeling) {
+  extern __shared__ unsigned char smem_raw[];
+  const int p = blockIdx.x;
+  ProbState* st = ws.st + p;
+  bool pts_loaded = false;
+  for (int guard = 0; guard < 1 << 14; ++guard) {
+    __syncthreads();
+    const int phase = st->phase, stage = st->lo_stage;
+    __syncthreads();
+    if (phase == PH_MAIN) {
+      phase_main(ws, prm, p, smem_raw, pts_loaded);
+    } else if (phase == PH_LO) {
+      if (stage == 0) { phase_cut(ws, prm, p, smem_raw); pts_loaded = false; }
+      else phase_trials(ws, prm, p, smem_raw, pts_loaded);
+    } else {
+      break;
+    }
+  }
+  __syncthreads();
+  phase_final(ws, prm, p, smem_raw, pts_loaded, offsets, poses, labeling);
+}
+
 constexpr size_t SMEM_POINTS = 5 * NMAX * 8 + NMAX * 2;
 constexpr size_t SMEM_PREP = 5 * NMAX * 4 + 8192 * 8 + 64 * 4 + 8192 * 2 + 64;
-constexpr size_t SMEM_MAIN = SMEM_POINTS + WARPS * (NMAX / 32) * 4 + WARPS * sizeof(PassRecord) + 12 * 8 + 64;
+static_assert(sizeof(PassRecord) <= 432 && CHUNK == 80, "workspace_layout reserves 80 x 432 bytes of pass records");
+constexpr size_t SMEM_MAIN = SMEM_POINTS + WARPS * (NMAX / 32) * 4 + 12 * 8 + 64;
 constexpr size_t SMEM_CUT = SMEM_CUT_DYN;
-constexpr size_t SMEM_TRIALS = SMEM_POINTS + WARPS * (NMAX / 32) * 4 + MAX_TRIALS * sizeof(TrialRecord) +
-                               WARPS * FIT_SCRATCH_DOUBLES * 8 + WARPS * 32 * 2 + 64;
-constexpr size_t SMEM_FINAL = SMEM_POINTS + (NMAX / 32) * 4 + 3 * NMAX * 2 + FIT_SCRATCH_DOUBLES * 8 + WARPS * FIT_NRED * 8 + 64;
+static_assert(FIT_SCRATCH_DOUBLES * 8 >= (NMAX / 32) * 4, "bitset must fit in the fit scratch");
+constexpr size_t SMEM_TRIALS = SMEM_POINTS + MAX_TRIALS * sizeof(TrialRecord) +
+                               (TRIAL_THREADS / 32) * FIT_SCRATCH_DOUBLES * 8 + (TRIAL_THREADS / 32) * 32 * 2 + 64;
+constexpr size_t SMEM_FINAL = SMEM_POINTS + (NMAX / 32) * 4 + 3 * NMAX * 2 + FIT_SCRATCH_DOUBLES * 8 + WARPS * FIT_NRED * 8 + 16 * 8 + 64;
+constexpr size_t cmax(size_t a, size_t b) { return a > b ? a : b; }
+constexpr size_t SMEM_FIT = cmax(cmax(SMEM_MAIN, SMEM_CUT), cmax(SMEM_TRIALS, SMEM_FINAL));
+static_assert(SMEM_FIT + 1024 <= 227 * 1024, "fit kernel shared memory");
 
 }  // namespace pose
 }  // namespace epos
@@ -891,6 +1030,28 @@ void epos_fit_params_default(epos_fit_params* p) {
 
 int epos_fit_max_points(void) { return NMAX; }
 
+// Profiling / debugging aid: copies per-problem counters out of a workspace after epos_fit_poses (synchronises).
+// out [P][16] i64: N, used_pixels, iterations, passes, graph_cuts, lo_runs, phase, best_inliers,
+//                  main-kernel clocks: sample+P3P, scoring, replay, total.
+int epos_fit_debug_state(const void* workspace, int P, long long* out) {
+  EPOS_CHECK_ARG(workspace && out && P > 0);
+  Workspace ws;
+  workspace_layout(P, const_cast<void*>(workspace), &ws);
+  ProbState* h = (ProbState*)malloc((size_t)P * sizeof(ProbState));
+  if (!h) return EPOS_ERR_CUDA;
+  cudaError_t e = cudaMemcpy(h, ws.st, (size_t)P * sizeof(ProbState), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { free(h); set_error("epos_fit_debug_state: %s", cudaGetErrorString(e)); return EPOS_ERR_CUDA; }
+  for (int i = 0; i < P; ++i) {
+    long long* o = out + (size_t)i * 16;
+    o[0] = h[i].N; o[1] = h[i].used_pixels; o[2] = (long long)h[i].iter; o[3] = h[i].pass; o[4] = h[i].gc_count;
+    o[5] = h[i].lo_runs; o[6] = h[i].phase; o[7] = h[i].best_inl; o[8] = h[i].t_sample; o[9] = h[i].t_score;
+    o[10] = h[i].t_replay; o[11] = h[i].t_total; o[12] = h[i].t_cut; o[13] = h[i].t_trials; o[14] = h[i].t_final;
+    o[15] = h[i].t_fit;
+  }
+  free(h);
+  return EPOS_OK;
+}
+
 size_t epos_fit_workspace_bytes(int P, int max_points, const epos_fit_params* params) {
   (void)max_points; (void)params;
   if (P <= 0) return 0;
@@ -901,10 +1062,7 @@ static int set_smem_attrs() {
   static bool done = false;
   if (done) return EPOS_OK;
   EPOS_CUDA(cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PREP));
-  EPOS_CUDA(cudaFuncSetAttribute(main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAIN));
-  EPOS_CUDA(cudaFuncSetAttribute(cut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CUT));
-  EPOS_CUDA(cudaFuncSetAttribute(trials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TRIALS));
-  EPOS_CUDA(cudaFuncSetAttribute(final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FINAL));
+  EPOS_CUDA(cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FIT));
   done = true;
   return EPOS_OK;
 }
@@ -927,20 +1085,10 @@ int epos_fit_poses(const double* coord_2d, const double* coord_3d, const int32_t
   Workspace ws;
   workspace_layout(P, workspace, &ws);
   cudaStream_t s = (cudaStream_t)stream;
-  prep_kernel<<<P, THREADS, SMEM_PREP, s>>>(ws, coord_2d, coord_3d, offsets, counts, K,
+  prep_kernel<<<P, PT, SMEM_PREP, s>>>(ws, coord_2d, coord_3d, offsets, counts, K,
                                             reinterpret_cast<const unsigned long long*>(seeds), *params, labeling, poses);
   EPOS_LAUNCH_CHECK();
-  // every LO round consumes one of the (max_graph_cuts - 1) cuts; one extra slot lets the main loop finish
-  const int rounds = params->max_graph_cuts + 1;
-  for (int r = 0; r < rounds; ++r) {
-    main_kernel<<<P, THREADS, SMEM_MAIN, s>>>(ws, *params);
-    EPOS_LAUNCH_CHECK();
-    cut_kernel<<<P, THREADS, SMEM_CUT, s>>>(ws, *params);
-    EPOS_LAUNCH_CHECK();
-    trials_kernel<<<P, THREADS, SMEM_TRIALS, s>>>(ws, *params);
-    EPOS_LAUNCH_CHECK();
-  }
-  final_kernel<<<P, THREADS, SMEM_FINAL, s>>>(ws, *params, offsets, poses, labeling);
+  fit_kernel<<<P, THREADS, SMEM_FIT, s>>>(ws, *params, offsets, poses, labeling);
   EPOS_LAUNCH_CHECK();
   return EPOS_OK;
 }

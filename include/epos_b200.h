@@ -165,6 +165,10 @@ int epos_fit_poses(const double* coord_2d, const double* coord_3d,
 size_t epos_fit_workspace_bytes(int P, int max_points, const epos_fit_params* params);
 /* Largest number of correspondences per problem (shared-memory resident point set): 4096. */
 int epos_fit_max_points(void);
+/* Profiling aid (synchronous): per-problem counters of the last epos_fit_poses on `workspace`.
+ * out [P][16] i64 (host): N, used_pixels, iterations, passes, graph_cuts, lo_runs, phase, best_inliers, then clock64()
+ * totals: main kernel sampling+P3P, scoring, replay, whole; cut, trials, final kernels; fits inside trials (warp 0). */
+int epos_fit_debug_state(const void* workspace, int P, long long* out);
 
 #ifdef __cplusplus
 }

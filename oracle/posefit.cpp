@@ -114,38 +114,53 @@ static bool inv3(const double* m, double* o) {
   return true;
 }
 
-// Cyclic Jacobi eigen-decomposition of a symmetric n x n matrix (row-major A, destroyed); V columns = eigenvectors.
+// Jacobi eigen-decomposition of a symmetric n x n matrix (row-major A, destroyed); V columns = eigenvectors.
+// Rotations are applied in the round-robin ("tournament") parallel ordering: each of the m-1 steps of a sweep
+// (m = n rounded up to even) rotates n/2 disjoint index pairs at once, A <- J^T A J with J the product of the step's
+// rotations, all angles taken from A before the step.  (Stands in for the SVDs inside cvFindExtrinsicCameraParams2 /
+// cvFindHomography; the CUDA kernels use the same ordering so that both sides take the same path.)
 static void jacobi_eig(int n, double* A, double* V, double* w) {
   for (int i = 0; i < n; ++i)
     for (int j = 0; j < n; ++j) V[i * n + j] = (i == j) ? 1.0 : 0.0;
+  const int m = (n + 1) & ~1;
   for (int sweep = 0; sweep < 60; ++sweep) {
     double off = 0.0, diag = 0.0;
     for (int i = 0; i < n; ++i)
       for (int j = 0; j < n; ++j) (i == j ? diag : off) += A[i * n + j] * A[i * n + j];
-    if (off <= 1e-300 || off < 1e-32 * diag) break;
-    for (int p = 0; p < n - 1; ++p)
-      for (int q = p + 1; q < n; ++q) {
-        double apq = A[p * n + q];
-        if (apq == 0.0) continue;
-        double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
-        double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
-        double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
-        for (int k = 0; k < n; ++k) {
-          double akp = A[k * n + p], akq = A[k * n + q];
-          A[k * n + p] = c * akp - s * akq;
-          A[k * n + q] = s * akp + c * akq;
+    if (off <= 1e-300 || off < 1e-28 * diag) break;
+    for (int step = 0; step < m - 1; ++step) {
+      int P[8], Q[8], np = 0;
+      double C[8], S[8];
+      for (int k = 0; k < m / 2; ++k) {
+        int a = k == 0 ? m - 1 : (step + k) % (m - 1);
+        int b = k == 0 ? step : (step - k + (m - 1)) % (m - 1);
+        int p = a < b ? a : b, q = a < b ? b : a;
+        if (q >= n) continue;
+        double apq = A[p * n + q], c = 1.0, s_ = 0.0;
+        if (apq != 0.0) {
+          double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
+          double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+          c = 1.0 / std::sqrt(t * t + 1.0);
+          s_ = t * c;
         }
-        for (int k = 0; k < n; ++k) {
-          double apk = A[p * n + k], aqk = A[q * n + k];
-          A[p * n + k] = c * apk - s * aqk;
-          A[q * n + k] = s * apk + c * aqk;
-        }
-        for (int k = 0; k < n; ++k) {
-          double vkp = V[k * n + p], vkq = V[k * n + q];
-          V[k * n + p] = c * vkp - s * vkq;
-          V[k * n + q] = s * vkp + c * vkq;
-        }
+        P[np] = p; Q[np] = q; C[np] = c; S[np] = s_; ++np;
       }
+      for (int j = 0; j < np; ++j)                                  // A <- A J, V <- V J
+        for (int k = 0; k < n; ++k) {
+          double akp = A[k * n + P[j]], akq = A[k * n + Q[j]];
+          A[k * n + P[j]] = C[j] * akp - S[j] * akq;
+          A[k * n + Q[j]] = S[j] * akp + C[j] * akq;
+          double vkp = V[k * n + P[j]], vkq = V[k * n + Q[j]];
+          V[k * n + P[j]] = C[j] * vkp - S[j] * vkq;
+          V[k * n + Q[j]] = S[j] * vkp + C[j] * vkq;
+        }
+      for (int j = 0; j < np; ++j)                                  // A <- J^T A
+        for (int k = 0; k < n; ++k) {
+          double apk = A[P[j] * n + k], aqk = A[Q[j] * n + k];
+          A[P[j] * n + k] = C[j] * apk - S[j] * aqk;
+          A[Q[j] * n + k] = S[j] * apk + C[j] * aqk;
+        }
+    }
   }
   for (int i = 0; i < n; ++i) w[i] = A[i * n + i];
 }
