@@ -3,6 +3,7 @@
 // softmax/argmax, plus an fp32 SIMT GEMM used for validation and for tiny (M = batch) GEMMs.
 // Reference call sites are cited in include/epos_b200.h next to each entry point.
 #include <stdarg.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace epos {
@@ -126,10 +127,106 @@ __global__ void __launch_bounds__(256) conv3x3_dense_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// Depthwise 3x3: one thread = one output pixel x 4 channels; consecutive threads walk the channel
-// axis (coalesced float4 loads, 9 taps served by L1/L2), output as f32 and/or split-bf16.
+// Depthwise 3x3.  A warp owns a strip of DW_PX consecutive output pixels of one row and 32 channel groups
+// (lane = 4 channels): every tap is one coalesced 512-byte row segment, the 9 filter taps of the lane's channels
+// live in registers, bounds tests are warp-uniform, DW_PX independent accumulators give the loads ILP.
+// Output as f32 and/or split-bf16.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dwconv3x3_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w,
+constexpr int DW_PX = 4;
+
+template <bool INTERIOR>
+__device__ __forceinline__ void dw_strip(const float4* __restrict__ x0, int ld4, int W, int H, int iy0, int ix0, int stride,
+                                         int rate, int npx, bool relu_in, const float4 (&wk)[9], float4 (&acc)[DW_PX]) {
+  // x0 points at (row iy0, column ix0) of this image for the lane's channel group; taps are addressed with 32-bit
+  // element offsets relative to it.
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    if (!INTERIOR) {
+      const int iy = iy0 + ky * rate;
+      if (iy < 0 || iy >= H) continue;
+    }
+    const int rowoff = ky * rate * W * ld4;
+#pragma unroll
+    for (int p = 0; p < DW_PX; ++p) {
+      if (!INTERIOR && p >= npx) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int dx = p * stride + kx * rate;
+        if (!INTERIOR) {
+          const int ix = ix0 + dx;
+          if (ix < 0 || ix >= W) continue;
+        }
+        float4 v = __ldg(x0 + (rowoff + dx * ld4));
+        if (relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        const float4 ww = wk[ky * 3 + kx];
+        acc[p].x = fmaf(v.x, ww.x, acc[p].x); acc[p].y = fmaf(v.y, ww.y, acc[p].y);
+        acc[p].z = fmaf(v.z, ww.z, acc[p].z); acc[p].w = fmaf(v.w, ww.w, acc[p].w);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 3) dwconv3x3_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, float* __restrict__ y_f32,
+                                                           uint16_t* __restrict__ y_split, long long plane_stride,
+                                                           int B, int H, int W, int C, int Ho, int Wo, int stride, int rate,
+                                                           int relu_in, int relu_out) {
+  const int G = C >> 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = blockIdx.y * 32 + lane;
+  // a block = 8 consecutive output ROWS of one strip column: the rows a warp reads are re-read by its neighbours in the
+  // same block (from L1) when rate <= 3
+  // (measured: pays for rate <= 2); for larger rates a block = 8 consecutive strips of one row
+  const int strips_per_row = (Wo + DW_PX - 1) / DW_PX;
+  int sx, oy, b;
+  if (rate <= 2) {
+    const int row_blocks = (Ho + 7) >> 3;
+    sx = blockIdx.x % strips_per_row;
+    const int q = blockIdx.x / strips_per_row;
+    oy = (q % row_blocks) * 8 + warp; b = q / row_blocks;
+  } else {
+    const int col_blocks = (strips_per_row + 7) >> 3;
+    sx = (blockIdx.x % col_blocks) * 8 + warp;
+    const int q = blockIdx.x / col_blocks;
+    oy = q % Ho; b = q / Ho;
+  }
+  if (oy >= Ho || sx >= strips_per_row || g >= G) return;
+  const int ox0 = sx * DW_PX;
+  const int npx = min(DW_PX, Wo - ox0);
+  float4 wk[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) wk[t] = __ldg(reinterpret_cast<const float4*>(w + (size_t)t * C) + g);
+  const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + g);
+  float4 acc[DW_PX];
+#pragma unroll
+  for (int p = 0; p < DW_PX; ++p) acc[p] = bb;
+  const int ld4 = ldx >> 2;
+  const int iy0 = oy * stride - rate, ix0 = ox0 * stride - rate;
+  const float4* x0 = reinterpret_cast<const float4*>(x) + (((long long)b * H + iy0) * W + ix0) * ld4 + g;
+  const bool interior = iy0 >= 0 && iy0 + 2 * rate < H && ix0 >= 0 && ix0 + (DW_PX - 1) * stride + 2 * rate < W &&
+                        npx == DW_PX;
+  if (interior) dw_strip<true>(x0, ld4, W, H, iy0, ix0, stride, rate, npx, relu_in != 0, wk, acc);
+  else dw_strip<false>(x0, ld4, W, H, iy0, ix0, stride, rate, npx, relu_in != 0, wk, acc);
+  const long long pix0 = ((long long)b * Ho + oy) * Wo + ox0;
+#pragma unroll
+  for (int p = 0; p < DW_PX; ++p) {
+    if (p >= npx) break;
+    float4 a = acc[p];
+    if (relu_out) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+    const long long pix = pix0 + p;
+    if (y_f32) *(reinterpret_cast<float4*>(y_f32 + pix * C) + g) = a;
+    if (y_split) {
+      uint2 hi, lo;
+      split_bf16x2(a.x, a.y, hi.x, lo.x);
+      split_bf16x2(a.z, a.w, hi.y, lo.y);
+      *(reinterpret_cast<uint2*>(y_split + pix * C) + g) = hi;
+      *(reinterpret_cast<uint2*>(y_split + plane_stride + pix * C) + g) = lo;
+    }
+  }
+}
+
+// Variant A (flat): one thread = one output pixel x 4 channels, grid-stride; consecutive threads walk the channel axis.
+__global__ void __launch_bounds__(256) dwconv3x3_flat_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w,
                                                         const float* __restrict__ bias, float* __restrict__ y_f32,
                                                         uint16_t* __restrict__ y_split, long long plane_stride,
                                                         int B, int H, int W, int C, int Ho, int Wo, int stride, int rate,
@@ -172,6 +269,7 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const float* __restrict_
     }
   }
 }
+
 
 __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, int ldx, uint16_t* __restrict__ y,
                                                          int ldy, long long plane_stride, int B, int H, int W, int C,
@@ -382,10 +480,22 @@ int epos_dwconv3x3(const float* x, int ldx, const float* w, const float* bias, f
   EPOS_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && (C % 4) == 0 && (ldx % 4) == 0 && ldx >= C);
   EPOS_CHECK_ARG((stride == 1 || stride == 2) && rate >= 1);
   const int Ho = stride == 1 ? H : (H - 1) / 2 + 1, Wo = stride == 1 ? W : (W - 1) / 2 + 1;
-  const long long total = (long long)B * Ho * Wo * (C / 4);
-  dwconv3x3_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, ldx, w, bias, y_f32, y_split,
-                                                                      (long long)B * Ho * Wo * C, B, H, W, C, Ho, Wo,
-                                                                      stride, rate, relu_in, relu_out);
+  const int spr = (Wo + DW_PX - 1) / DW_PX;
+  const long long blocks = rate <= 2 ? (long long)B * ((Ho + 7) / 8) * spr : (long long)B * Ho * ((spr + 7) / 8);
+  EPOS_CHECK_ARG(blocks < (1LL << 31) && ceil_div(C / 4, 32) <= 65535 && (long long)H * W * (ldx / 4) < (1LL << 30));
+  dim3 grid((unsigned)blocks, (unsigned)ceil_div(C / 4, 32));
+  static int variant = -1;
+  if (variant < 0) { const char* e = getenv("EPOS_DW_VARIANT"); variant = e ? atoi(e) : 1; }
+  if (variant == 1) {
+    dwconv3x3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, w, bias, y_f32, y_split,
+                                                             (long long)B * Ho * Wo * C, B, H, W, C, Ho, Wo,
+                                                             stride, rate, relu_in, relu_out);
+  } else {
+    const long long total = (long long)B * Ho * Wo * (C / 4);
+    dwconv3x3_flat_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, ldx, w, bias, y_f32, y_split,
+                                                                             (long long)B * Ho * Wo * C, B, H, W, C, Ho, Wo,
+                                                                             stride, rate, relu_in, relu_out);
+  }
   EPOS_LAUNCH_CHECK();
   return EPOS_OK;
 }

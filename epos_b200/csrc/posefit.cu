@@ -230,34 +230,105 @@ prep_kernel(Workspace ws, const double* __restrict__ c2d, const double* __restri
   __syncthreads();
 
   // ---- neighbourhood graph: the max_neighbors nearest points within the radius (f32, 5-D, ties by index) ----
+  // A uniform grid over (u, v) with cells at least one radius wide bounds the search to 3 x 3 cells.
   const int KN = prm.max_neighbors < MAXNB ? prm.max_neighbors : MAXNB;
-  const float r2 = (float)prm.neighborhood_ball_radius * (float)prm.neighborhood_ball_radius;
+  const float rad = (float)prm.neighborhood_ball_radius;
+  const float r2 = rad * rad;
   short* nbr = ws.nbr + (size_t)p * NMAX * MAXNB;
+  constexpr int MAXCELL = 4096;
+  int* cell_start = reinterpret_cast<int*>(table);                        // [ncell + 1] (hash table is dead now)
+  unsigned short* sorted = reinterpret_cast<unsigned short*>(cell_start + MAXCELL + 8);   // [N] point ids by cell
+  __shared__ float s_red[4][PT / 32];
+  __shared__ float s_box[4];
+  {
+    float mnu = INFINITY, mnv = INFINITY, mxu = -INFINITY, mxv = -INFINITY;
+    for (int i = tid; i < N; i += PT) {
+      mnu = fminf(mnu, q[i]); mxu = fmaxf(mxu, q[i]); mnv = fminf(mnv, q[NMAX + i]); mxv = fmaxf(mxv, q[NMAX + i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mnu = fminf(mnu, __shfl_xor_sync(0xffffffffu, mnu, o)); mxu = fmaxf(mxu, __shfl_xor_sync(0xffffffffu, mxu, o));
+      mnv = fminf(mnv, __shfl_xor_sync(0xffffffffu, mnv, o)); mxv = fmaxf(mxv, __shfl_xor_sync(0xffffffffu, mxv, o));
+    }
+    if ((tid & 31) == 0) { s_red[0][tid >> 5] = mnu; s_red[1][tid >> 5] = mxu; s_red[2][tid >> 5] = mnv; s_red[3][tid >> 5] = mxv; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int k = 1; k < PT / 32; ++k) {
+        s_red[0][0] = fminf(s_red[0][0], s_red[0][k]); s_red[1][0] = fmaxf(s_red[1][0], s_red[1][k]);
+        s_red[2][0] = fminf(s_red[2][0], s_red[2][k]); s_red[3][0] = fmaxf(s_red[3][0], s_red[3][k]);
+      }
+      float cs = rad * 1.0001f + 1e-6f;                                   // >= radius, so neighbours are within +-1 cell
+      int gw, gh;
+      for (;;) {
+        gw = (int)floorf((s_red[1][0] - s_red[0][0]) / cs) + 1;
+        gh = (int)floorf((s_red[3][0] - s_red[2][0]) / cs) + 1;
+        if (gw > 0 && gh > 0 && (long long)gw * gh <= MAXCELL) break;
+        cs *= 2.0f;
+        if (!(cs < 1e30f)) { gw = gh = 1; break; }                        // non-finite coordinates: one cell
+      }
+      s_box[0] = s_red[0][0]; s_box[1] = s_red[2][0]; s_box[2] = cs; s_box[3] = __int_as_float(gw | (gh << 16));
+    }
+    __syncthreads();
+  }
+  const float bu = s_box[0], bv = s_box[1], ics = 1.0f / s_box[2];
+  const int gw = __float_as_int(s_box[3]) & 0xffff, gh = __float_as_int(s_box[3]) >> 16;
+  const int ncell = gw * gh;
+  auto cell_of = [&](int i, int* cx, int* cy) {
+    int x = (int)floorf((q[i] - bu) * ics), y = (int)floorf((q[NMAX + i] - bv) * ics);
+    *cx = x < 0 ? 0 : (x >= gw ? gw - 1 : x);
+    *cy = y < 0 ? 0 : (y >= gh ? gh - 1 : y);
+  };
+  for (int c = tid; c <= ncell; c += PT) cell_start[c] = 0;
+  __syncthreads();
+  for (int i = tid; i < N; i += PT) { int cx, cy; cell_of(i, &cx, &cy); atomicAdd(&cell_start[cy * gw + cx + 1], 1); }
+  __syncthreads();
+  {
+    // inclusive scan of cell_start[1..ncell] (<= 8192 cells = 16 per thread)
+    const int per = (MAXCELL + PT - 1) / PT;
+    int loc = 0;
+    for (int k = 0; k < per; ++k) { const int c = tid * per + k + 1; if (c <= ncell) loc += cell_start[c]; }
+    int total;
+    int base = block_excl_scan<PT / 32>(loc, scan_sh, &total);
+    for (int k = 0; k < per; ++k) { const int c = tid * per + k + 1; if (c <= ncell) { base += cell_start[c]; cell_start[c] = base; } }
+  }
+  __syncthreads();
+  // fill: cursors run backwards from the cell ends; the order inside a cell is arbitrary (the selection below compares
+  // (distance, index) pairs, so the result does not depend on it)
+  int* cursor = cell_start + MAXCELL + 8 + (NMAX / 2) + 8;                // after `sorted`
+  for (int c = tid; c < ncell; c += PT) cursor[c] = cell_start[c + 1];
+  __syncthreads();
+  for (int i = tid; i < N; i += PT) { int cx, cy; cell_of(i, &cx, &cy); sorted[atomicSub(&cursor[cy * gw + cx], 1) - 1] = (unsigned short)i; }
+  __syncthreads();
   for (int i = tid; i < N; i += PT) {
     float bd[MAXNB];
     int bj[MAXNB];
 #pragma unroll
     for (int k = 0; k < MAXNB; ++k) { bd[k] = INFINITY; bj[k] = -1; }
     const float a0 = q[i], a1 = q[NMAX + i], a2 = q[2 * NMAX + i], a3 = q[3 * NMAX + i], a4 = q[4 * NMAX + i];
-    for (int j = 0; j < N; ++j) {
-      float e, d = 0.f;
-      e = a0 - q[j]; d = __fmaf_rn(e, e, d);
-      e = a1 - q[NMAX + j]; d = __fmaf_rn(e, e, d);
-      e = a2 - q[2 * NMAX + j]; d = __fmaf_rn(e, e, d);
-      e = a3 - q[3 * NMAX + j]; d = __fmaf_rn(e, e, d);
-      e = a4 - q[4 * NMAX + j]; d = __fmaf_rn(e, e, d);
-      if (j == i || !(d <= r2)) continue;
-      if (!(d < bd[MAXNB - 1]) && bj[MAXNB - 1] >= 0) continue;
-      // insert keeping (d, j) ascending; equal d keeps the smaller (earlier) index first
-      float cd = d; int cj = j;
-      bool ins = false;
+    int cx, cy;
+    cell_of(i, &cx, &cy);
+    for (int yy = max(cy - 1, 0); yy <= min(cy + 1, gh - 1); ++yy) {
+      const int c0 = yy * gw + max(cx - 1, 0), c1 = yy * gw + min(cx + 1, gw - 1);
+      for (int s_ = cell_start[c0]; s_ < cell_start[c1 + 1]; ++s_) {      // the <= 3 cells of a row are contiguous
+        const int j = sorted[s_];
+        float e, d = 0.f;
+        e = a0 - q[j]; d = __fmaf_rn(e, e, d);
+        e = a1 - q[NMAX + j]; d = __fmaf_rn(e, e, d);
+        e = a2 - q[2 * NMAX + j]; d = __fmaf_rn(e, e, d);
+        e = a3 - q[3 * NMAX + j]; d = __fmaf_rn(e, e, d);
+        e = a4 - q[4 * NMAX + j]; d = __fmaf_rn(e, e, d);
+        if (j == i || !(d <= r2)) continue;
+        // insert keeping (d, j) ascending lexicographically
+        float cd = d; int cj = j;
+        bool ins = false;
 #pragma unroll
-      for (int k = 0; k < MAXNB; ++k) {
-        if (ins || bj[k] < 0 || cd < bd[k]) {
-          const float td = bd[k]; const int tj = bj[k];
-          bd[k] = cd; bj[k] = cj; cd = td; cj = tj;
-          ins = true;
-          if (cj < 0) break;
+        for (int k = 0; k < MAXNB; ++k) {
+          if (ins || bj[k] < 0 || cd < bd[k] || (cd == bd[k] && cj < bj[k])) {
+            const float td = bd[k]; const int tj = bj[k];
+            bd[k] = cd; bj[k] = cj; cd = td; cj = tj;
+            ins = true;
+            if (cj < 0) break;
+          }
         }
       }
     }

@@ -18,12 +18,12 @@
 //               split-bf16 stores; double-buffered accumulators (2 x BLOCK_N TMEM columns) overlap the
 //               epilogue of tile i with the main loop of tile i+1
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace epos {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;          // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;
 
@@ -91,14 +91,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       : "memory");
 }
 
-// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart.
+// K-major operand tile with BLOCK_K bf16 per row: BLOCK_K = 64 -> rows of 128 B, 128-byte swizzle, 8-row groups 1024 B
+// apart; BLOCK_K = 32 -> rows of 64 B, 64-byte swizzle, 8-row groups 512 B apart.
+template <int BLOCK_K>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address
   d |= (uint64_t)0 << 16;                               // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset
+  d |= (uint64_t)((8 * BLOCK_K * 2) >> 4) << 32;        // stride byte offset: one 8-row group
   d |= (uint64_t)1 << 46;                               // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                               // SWIZZLE_128B
+  d |= (uint64_t)(BLOCK_K == 64 ? 2 : 4) << 61;         // SWIZZLE_128B / SWIZZLE_64B
   return d;
 }
 
@@ -115,21 +117,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int BLOCK_K>
 struct GemmCfg {
   static constexpr int A_BYTES = 2 * BLOCK_M * BLOCK_K * 2;       // both planes
   static constexpr int B_BYTES = 2 * BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES < 2 ? 2 : ((200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES);
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES < 2 ? 2 : ((200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int BLOCK_K>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                const GemmEpilogue ep, int M, int N, int K) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, BLOCK_K>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -211,8 +213,8 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint32_t koff = k * UMMA_K * 2;
-            const uint64_t da_hi = make_smem_desc(a_hi + koff), da_lo = make_smem_desc(a_lo + koff);
-            const uint64_t db_hi = make_smem_desc(b_hi + koff), db_lo = make_smem_desc(b_lo + koff);
+            const uint64_t da_hi = make_smem_desc<BLOCK_K>(a_hi + koff), da_lo = make_smem_desc<BLOCK_K>(a_lo + koff);
+            const uint64_t db_hi = make_smem_desc<BLOCK_K>(b_hi + koff), db_lo = make_smem_desc<BLOCK_K>(b_lo + koff);
             umma_bf16(tmem_d, da_lo, db_hi, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             umma_bf16(tmem_d, da_hi, db_lo, idesc, 1u);
             umma_bf16(tmem_d, da_hi, db_hi, idesc, 1u);
@@ -351,16 +353,18 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-// [2][rows][ld] bf16, box {64, box_rows, 2}
-static int make_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, size_t plane_stride, int box_rows) {
+// [2][rows][ld] bf16, box {block_k, box_rows, 2}
+static int make_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, size_t plane_stride, int box_rows,
+                    int block_k) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled not available"); return EPOS_ERR_CUDA; }
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane_stride * 2};
-  cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows, 2};
+  cuuint32_t box[3] = {(cuuint32_t)block_k, (cuuint32_t)box_rows, 2};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d plane=%zu box_rows=%d", (int)r, rows, cols, ld,
@@ -381,18 +385,18 @@ static int num_sms() {
   return n;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int BLOCK_K>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const GemmEpilogue& ep, int M, int N, int K,
                        cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, BLOCK_K>;
   static bool attr = false;
   if (!attr) {
-    EPOS_CUDA(cudaFuncSetAttribute(pw_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    EPOS_CUDA(cudaFuncSetAttribute(pw_gemm_kernel<BLOCK_N, BLOCK_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr = true;
   }
   const int tiles = ceil_div(M, BLOCK_M) * ceil_div(N, BLOCK_N);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  pw_gemm_kernel<BLOCK_N><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mw, ep, M, N, K);
+  pw_gemm_kernel<BLOCK_N, BLOCK_K><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mw, ep, M, N, K);
   EPOS_LAUNCH_CHECK();
   return EPOS_OK;
 }
@@ -413,20 +417,38 @@ extern "C" int epos_pwconv_gemm(const uint16_t* a_split, int lda, size_t a_plane
   EPOS_CHECK_ARG(!d_split || ldd_split >= N);
   EPOS_CHECK_ARG(!residual || ldr >= N);
   int bn = N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
+  // K block: 64 (128-byte swizzle, 2 pipeline stages at BLOCK_N = 256) or 32 (64-byte swizzle, 4 stages).  Measured on
+  // B200 (B = 8, full network): BK = 32 is 4 % slower -- the kernel is bound by L2->SM throughput, not by pipeline depth
+  // (DESIGN.md section 3), so the default stays 64.  EPOS_GEMM_BK overrides for A/B measurements.
+  static int bk_env = -1;
+  if (bk_env < 0) {
+    const char* e = getenv("EPOS_GEMM_BK");
+    bk_env = e ? atoi(e) : 0;
+    if (bk_env != 32 && bk_env != 64) bk_env = 0;
+  }
+  const int bk = bk_env ? bk_env : 64;
   CUtensorMap ma, mw;
-  int rc = make_map(&ma, a_split, M, K, lda, a_plane_stride, BLOCK_M);
+  int rc = make_map(&ma, a_split, M, K, lda, a_plane_stride, BLOCK_M, bk);
   if (rc) return rc;
-  rc = make_map(&mw, w_split, N, K, K, (size_t)N * K, bn);
+  rc = make_map(&mw, w_split, N, K, K, (size_t)N * K, bn, bk);
   if (rc) return rc;
   GemmEpilogue ep;
   ep.bias = bias; ep.residual = residual; ep.d_f32 = d_f32; ep.d_split = d_split;
   ep.d_plane_stride = (long long)d_plane_stride; ep.bias_group_rows = bias_group_rows;
   ep.ldr = ldr; ep.ldd = ldd; ep.ldd_split = ldd_split; ep.relu = relu;
   cudaStream_t s = (cudaStream_t)stream;
+  if (bk == 32) {
+    switch (bn) {
+      case 256: return launch_gemm<256, 32>(ma, mw, ep, M, N, K, s);
+      case 128: return launch_gemm<128, 32>(ma, mw, ep, M, N, K, s);
+      case 64: return launch_gemm<64, 32>(ma, mw, ep, M, N, K, s);
+      default: return launch_gemm<32, 32>(ma, mw, ep, M, N, K, s);
+    }
+  }
   switch (bn) {
-    case 256: return launch_gemm<256>(ma, mw, ep, M, N, K, s);
-    case 128: return launch_gemm<128>(ma, mw, ep, M, N, K, s);
-    case 64: return launch_gemm<64>(ma, mw, ep, M, N, K, s);
-    default: return launch_gemm<32>(ma, mw, ep, M, N, K, s);
+    case 256: return launch_gemm<256, 64>(ma, mw, ep, M, N, K, s);
+    case 128: return launch_gemm<128, 64>(ma, mw, ep, M, N, K, s);
+    case 64: return launch_gemm<64, 64>(ma, mw, ep, M, N, K, s);
+    default: return launch_gemm<32, 64>(ma, mw, ep, M, N, K, s);
   }
 }
