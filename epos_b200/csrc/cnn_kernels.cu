@@ -185,12 +185,12 @@ __global__ void __launch_bounds__(256, 3) dwconv3x3_kernel(const float* __restri
     const int q = blockIdx.x / strips_per_row;
     oy = (q % row_blocks) * 8 + warp; b = q / row_blocks;
   } else {
-    const int col_blocks = (strips_per_row + 7) >> 3;
-    sx = (blockIdx.x % col_blocks) * 8 + warp;
-    const int q = blockIdx.x / col_blocks;
+    const int strip = blockIdx.x * 8 + warp;                    // strips linearised over (b, oy, sx)
+    sx = strip % strips_per_row;
+    const int q = strip / strips_per_row;
     oy = q % Ho; b = q / Ho;
   }
-  if (oy >= Ho || sx >= strips_per_row || g >= G) return;
+  if (b >= B || oy >= Ho || g >= G) return;
   const int ox0 = sx * DW_PX;
   const int npx = min(DW_PX, Wo - ox0);
   float4 wk[9];
@@ -481,7 +481,7 @@ int epos_dwconv3x3(const float* x, int ldx, const float* w, const float* bias, f
   EPOS_CHECK_ARG((stride == 1 || stride == 2) && rate >= 1);
   const int Ho = stride == 1 ? H : (H - 1) / 2 + 1, Wo = stride == 1 ? W : (W - 1) / 2 + 1;
   const int spr = (Wo + DW_PX - 1) / DW_PX;
-  const long long blocks = rate <= 2 ? (long long)B * ((Ho + 7) / 8) * spr : (long long)B * Ho * ((spr + 7) / 8);
+  const long long blocks = rate <= 2 ? (long long)B * ((Ho + 7) / 8) * spr : ((long long)B * Ho * spr + 7) / 8;
   EPOS_CHECK_ARG(blocks < (1LL << 31) && ceil_div(C / 4, 32) <= 65535 && (long long)H * W * (ldx / 4) < (1LL << 30));
   dim3 grid((unsigned)blocks, (unsigned)ceil_div(C / 4, 32));
   static int variant = -1;

@@ -69,6 +69,6 @@ def all_gather_poses(poses, world):
     """poses [b, O, 16] f64 on this rank -> [world*b, O, 16] (rank-major, i.e. global image order)."""
     if world == 1:
         return poses
-    out = torch.empty((world,) + tuple(poses.shape), dtype=poses.dtype, device=poses.device)
+    out = torch.empty((world * poses.shape[0],) + tuple(poses.shape[1:]), dtype=poses.dtype, device=poses.device)
     dist.all_gather_into_tensor(out, poses.contiguous())
-    return out.view((-1,) + tuple(poses.shape[1:]))
+    return out
