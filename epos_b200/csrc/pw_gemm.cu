@@ -104,7 +104,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return d;
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+// tcgen05.ld of 32 lanes x 32 columns, split into issue and wait so that independent global loads can be put in flight
+// in between.  The wait names the destination registers as in/out operands: nothing may read them before it.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -113,8 +115,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
 }
 
 template <int BLOCK_N, int BLOCK_K>
@@ -124,17 +135,20 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES < 2 ? 2 : ((200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGING_BYTES = 4 * 32 * 32 * 4;            // epilogue transpose buffers, one per warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STAGING_BYTES;
 };
 
 template <int BLOCK_N, int BLOCK_K>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-               const GemmEpilogue ep, int M, int N, int K) {
+               const GemmEpilogue ep, int M, int N, int K, int dbg) {
   using Cfg = GemmCfg<BLOCK_N, BLOCK_K>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment (128B swizzle atoms) by an offset from the __shared__ symbol, so that the compiler still knows
+  // the address space (STS/LDS instead of generic accesses in the epilogue)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
@@ -143,6 +157,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* staging = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -179,9 +194,9 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int n0 = (tile % n_tiles) * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_3d(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K, m0, 0);
-          tma_load_3d(smem_b + stage * Cfg::B_BYTES, &tmap_w, &full_bar[stage], kb * BLOCK_K, n0, 0);
+          mbar_expect_tx(&full_bar[stage], (dbg & 64) ? Cfg::A_BYTES : ((dbg & 128) ? Cfg::B_BYTES : Cfg::STAGE_BYTES));
+          if (!(dbg & 128)) tma_load_3d(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K, m0, 0);
+          if (!(dbg & 64)) tma_load_3d(smem_b + stage * Cfg::B_BYTES, &tmap_w, &full_bar[stage], kb * BLOCK_K, n0, 0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -215,7 +230,9 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint32_t koff = k * UMMA_K * 2;
             const uint64_t da_hi = make_smem_desc<BLOCK_K>(a_hi + koff), da_lo = make_smem_desc<BLOCK_K>(a_lo + koff);
             const uint64_t db_hi = make_smem_desc<BLOCK_K>(b_hi + koff), db_lo = make_smem_desc<BLOCK_K>(b_lo + koff);
+            if (dbg & 8) continue;
             umma_bf16(tmem_d, da_lo, db_hi, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (dbg & 16) continue;
             umma_bf16(tmem_d, da_hi, db_lo, idesc, 1u);
             umma_bf16(tmem_d, da_hi, db_hi, idesc, 1u);
           }
@@ -232,10 +249,22 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool vec_f32 = ep.d_f32 && (ep.ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.d_f32) & 15) == 0);
-    const bool vec_res = ep.residual && (ep.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0);
-    const bool vec_split = ep.d_split && (ep.ldd_split % 8 == 0) && ((reinterpret_cast<uintptr_t>(ep.d_split) & 15) == 0) &&
-                           (ep.d_plane_stride % 8 == 0);
+    // Fast path precondition (uniform over the launch): 16-byte aligned rows everywhere, N a multiple of 4, and a
+    // per-group bias whose groups are at least one warp-quarter tall (at most one group boundary per 32 rows).
+    const bool fast =
+        (N % 4 == 0) &&
+        (!ep.d_f32 || ((ep.ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.d_f32) & 15) == 0))) &&
+        (!ep.residual || ((ep.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0))) &&
+        (!ep.d_split || ((ep.ldd_split % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.d_split) & 7) == 0) &&
+                         (ep.d_plane_stride % 4 == 0))) &&
+        (!ep.bias || (((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0) &&
+                      (ep.bias_group_rows == 0 || ep.bias_group_rows >= 32)));
+    // Each warp transposes its 32x32 accumulator chunk through a private XOR-swizzled smem buffer (conflict-free both
+    // ways): tcgen05.ld hands a lane one ROW, but coalesced global access wants 8 consecutive lanes on 128 contiguous
+    // bytes of a row.  After the transpose lane (rsub, jj) owns columns 4*jj..4*jj+3 of rows rsub, rsub+4, ...
+    float4* stg = reinterpret_cast<float4*>(staging + (warp - 2) * 1024);
+    const int rsub = lane >> 3, jj = lane & 7;
+    const float relu_floor = ep.relu ? 0.f : -INFINITY;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_tiles) * BLOCK_M;
       const int n0 = (tile % n_tiles) * BLOCK_N;
@@ -243,80 +272,107 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (n_valid > BLOCK_N) n_valid = BLOCK_N;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int m = m0 + quarter * 32 + lane;
-      const bool row_ok = m < M;
-      const float* brow = ep.bias ? ep.bias + (ep.bias_group_rows > 0 ? (long long)(m / ep.bias_group_rows) * N : 0) : nullptr;
-      for (int c0 = 0; c0 < n_valid; c0 += 32) {
-        uint32_t r[32];
-        __syncwarp();                                  // .sync.aligned: the whole warp issues the load together
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), r);
-        if (row_ok) {
-        const int nb = n0 + c0;
-        const int cnt = (n_valid - c0) < 32 ? (n_valid - c0) : 32;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float t = __uint_as_float(r[j]);
-          if (brow && j < cnt) t += __ldg(brow + nb + j);
-          if (ep.relu) t = fmaxf(t, 0.f);
-          v[j] = t;
+      const int row_base = m0 + quarter * 32;
+      const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      if (dbg & 32) {
+      } else if (fast) {
+        int g0 = 0, boundary = 0x7fffffff;
+        if (ep.bias && ep.bias_group_rows > 0) {
+          g0 = row_base / ep.bias_group_rows;
+          boundary = (g0 + 1) * ep.bias_group_rows;
         }
-        if (ep.residual) {
-          const float* rr = ep.residual + (long long)m * ep.ldr + nb;
-          if (vec_res && cnt == 32) {
+        const bool two_groups = boundary < row_base + 32 && boundary < M;
+        const int rows_left = M - row_base - rsub;                 // row rsub + 4 i is valid iff 4 i < rows_left
+#pragma unroll 1
+        for (int c0 = 0; c0 < n_valid; c0 += 32) {
+          const int col = n0 + c0 + jj * 4;
+          const bool col_ok = col < N;
+          uint32_t r[32];
+          __syncwarp();
+          tmem_ld32_issue(tacc + (uint32_t)c0, r);
+          // bias and residual do not depend on the accumulator: fetch them while the TMEM load is in flight
+          float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+          if (ep.bias && col_ok) {
+            b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + (long long)g0 * N + col));
+            b1 = two_groups ? __ldg(reinterpret_cast<const float4*>(ep.bias + (long long)(g0 + 1) * N + col)) : b0;
+          }
+          float4 res[8];
+          if (ep.residual && !(dbg & 4)) {
+            const float* rp = ep.residual + (long long)(row_base + rsub) * ep.ldr + col;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 q = __ldg(reinterpret_cast<const float4*>(rr) + j);
-              v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
-            }
+            for (int i = 0; i < 8; ++i)
+              res[i] = (col_ok && 4 * i < rows_left) ? __ldg(reinterpret_cast<const float4*>(rp + (long long)(4 * i) * ep.ldr))
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < cnt) v[j] += __ldg(rr + j);
+            for (int i = 0; i < 8; ++i) res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
-        }
-        if (ep.d_f32) {
-          float* dd = ep.d_f32 + (long long)m * ep.ldd + nb;
-          if (vec_f32 && cnt == 32 && (nb % 4 == 0)) {
+          tmem_ld32_wait(r);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              reinterpret_cast<float4*>(dd)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
+          for (int j = 0; j < 8; ++j)
+            stg[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                           __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          __syncwarp();
+          float* df = ep.d_f32 ? ep.d_f32 + (long long)(row_base + rsub) * ep.ldd + col : nullptr;
+          uint16_t* dh = ep.d_split ? ep.d_split + (long long)(row_base + rsub) * ep.ldd_split + col : nullptr;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < cnt) dd[j] = v[j];
-          }
-        }
-        if (ep.d_split) {
-          uint16_t* dh = ep.d_split + (long long)m * ep.ldd_split + nb;
-          uint16_t* dl = dh + ep.d_plane_stride;
-          if (vec_split && cnt == 32 && (nb % 8 == 0)) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t h[4], l[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                __nv_bfloat16 h0, l0, h1, l1;
-                split_bf16(v[8 * j + 2 * q], h0, l0);
-                split_bf16(v[8 * j + 2 * q + 1], h1, l1);
-                h[q] = pack_bf16x2(h0, h1);
-                l[q] = pack_bf16x2(l0, l1);
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + rsub;
+            float4 v = stg[rr * 8 + (jj ^ (rr & 7))];
+            const float4 b = (row_base + rr >= boundary) ? b1 : b0;
+            v.x = fmaxf(v.x + b.x, relu_floor) + res[i].x;
+            v.y = fmaxf(v.y + b.y, relu_floor) + res[i].y;
+            v.z = fmaxf(v.z + b.z, relu_floor) + res[i].z;
+            v.w = fmaxf(v.w + b.w, relu_floor) + res[i].w;
+            if (col_ok && 4 * i < rows_left && !(dbg & 2)) {
+              if (df) *reinterpret_cast<float4*>(df + (long long)(4 * i) * ep.ldd) = v;
+              if (dh) {
+                uint2 hi, lo;
+                split_bf16x2(v.x, v.y, hi.x, lo.x);
+                split_bf16x2(v.z, v.w, hi.y, lo.y);
+                uint16_t* ph = dh + (long long)(4 * i) * ep.ldd_split;
+                *reinterpret_cast<uint2*>(ph) = hi;
+                *reinterpret_cast<uint2*>(ph + ep.d_plane_stride) = lo;
               }
-              reinterpret_cast<uint4*>(dh)[j] = make_uint4(h[0], h[1], h[2], h[3]);
-              reinterpret_cast<uint4*>(dl)[j] = make_uint4(l[0], l[1], l[2], l[3]);
             }
-          } else {
+          }
+        }
+      } else {
+        // Generic path (odd N or unaligned views; only the 22-channel object head takes it): lane = row, scalar stores.
+        const int m = row_base + lane;
+        const float* brow = ep.bias ? ep.bias + (ep.bias_group_rows > 0 ? (long long)(m / ep.bias_group_rows) * N : 0) : nullptr;
+#pragma unroll 1
+        for (int c0 = 0; c0 < n_valid; c0 += 32) {
+          uint32_t r[32];
+          __syncwarp();
+          tmem_ld32_issue(tacc + (uint32_t)c0, r);
+          tmem_ld32_wait(r);
+          // stage through smem so that the scalar loop below can index dynamically without local memory
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < cnt) {
+          for (int j = 0; j < 8; ++j)
+            stg[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                           __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          __syncwarp();
+          const int cnt = (n_valid - c0) < 32 ? (n_valid - c0) : 32;
+          if (m < M) {
+            const float* srow = reinterpret_cast<const float*>(stg + lane * 8);
+#pragma unroll 1
+            for (int j = 0; j < cnt; ++j) {
+              const int nn = n0 + c0 + j;
+              float t = srow[(((j >> 2) ^ (lane & 7)) << 2) + (j & 3)];
+              if (brow) t += __ldg(brow + nn);
+              t = fmaxf(t, relu_floor);
+              if (ep.residual) t += __ldg(ep.residual + (long long)m * ep.ldr + nn);
+              if (ep.d_f32) ep.d_f32[(long long)m * ep.ldd + nn] = t;
+              if (ep.d_split) {
                 __nv_bfloat16 h0, l0;
-                split_bf16(v[j], h0, l0);
-                dh[j] = __bfloat16_as_ushort(h0);
-                dl[j] = __bfloat16_as_ushort(l0);
+                split_bf16(t, h0, l0);
+                ep.d_split[(long long)m * ep.ldd_split + nn] = __bfloat16_as_ushort(h0);
+                ep.d_split[ep.d_plane_stride + (long long)m * ep.ldd_split + nn] = __bfloat16_as_ushort(l0);
               }
+            }
           }
         }
-        }  // row_ok
       }
       tc_fence_before();
       __syncwarp();
@@ -387,7 +443,7 @@ static int num_sms() {
 
 template <int BLOCK_N, int BLOCK_K>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const GemmEpilogue& ep, int M, int N, int K,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, int dbg) {
   using Cfg = GemmCfg<BLOCK_N, BLOCK_K>;
   static bool attr = false;
   if (!attr) {
@@ -396,7 +452,7 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const GemmE
   }
   const int tiles = ceil_div(M, BLOCK_M) * ceil_div(N, BLOCK_N);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  pw_gemm_kernel<BLOCK_N, BLOCK_K><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mw, ep, M, N, K);
+  pw_gemm_kernel<BLOCK_N, BLOCK_K><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mw, ep, M, N, K, dbg);
   EPOS_LAUNCH_CHECK();
   return EPOS_OK;
 }
@@ -427,6 +483,8 @@ extern "C" int epos_pwconv_gemm(const uint16_t* a_split, int lda, size_t a_plane
     if (bk_env != 32 && bk_env != 64) bk_env = 0;
   }
   const int bk = bk_env ? bk_env : 64;
+  const char* de = getenv("EPOS_GEMM_DEBUG");   // developer A/B switches (scripts/dev_gemm.py); 0 in production
+  const int dbg = de ? atoi(de) : 0;
   CUtensorMap ma, mw;
   int rc = make_map(&ma, a_split, M, K, lda, a_plane_stride, BLOCK_M, bk);
   if (rc) return rc;
@@ -439,16 +497,16 @@ extern "C" int epos_pwconv_gemm(const uint16_t* a_split, int lda, size_t a_plane
   cudaStream_t s = (cudaStream_t)stream;
   if (bk == 32) {
     switch (bn) {
-      case 256: return launch_gemm<256, 32>(ma, mw, ep, M, N, K, s);
-      case 128: return launch_gemm<128, 32>(ma, mw, ep, M, N, K, s);
-      case 64: return launch_gemm<64, 32>(ma, mw, ep, M, N, K, s);
-      default: return launch_gemm<32, 32>(ma, mw, ep, M, N, K, s);
+      case 256: return launch_gemm<256, 32>(ma, mw, ep, M, N, K, s, dbg);
+      case 128: return launch_gemm<128, 32>(ma, mw, ep, M, N, K, s, dbg);
+      case 64: return launch_gemm<64, 32>(ma, mw, ep, M, N, K, s, dbg);
+      default: return launch_gemm<32, 32>(ma, mw, ep, M, N, K, s, dbg);
     }
   }
   switch (bn) {
-    case 256: return launch_gemm<256, 64>(ma, mw, ep, M, N, K, s);
-    case 128: return launch_gemm<128, 64>(ma, mw, ep, M, N, K, s);
-    case 64: return launch_gemm<64, 64>(ma, mw, ep, M, N, K, s);
-    default: return launch_gemm<32, 64>(ma, mw, ep, M, N, K, s);
+    case 256: return launch_gemm<256, 64>(ma, mw, ep, M, N, K, s, dbg);
+    case 128: return launch_gemm<128, 64>(ma, mw, ep, M, N, K, s, dbg);
+    case 64: return launch_gemm<64, 64>(ma, mw, ep, M, N, K, s, dbg);
+    default: return launch_gemm<32, 64>(ma, mw, ep, M, N, K, s, dbg);
   }
 }
