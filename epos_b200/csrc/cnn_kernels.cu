@@ -485,8 +485,13 @@ int epos_dwconv3x3(const float* x, int ldx, const float* w, const float* bias, f
   EPOS_CHECK_ARG(blocks < (1LL << 31) && ceil_div(C / 4, 32) <= 65535 && (long long)H * W * (ldx / 4) < (1LL << 30));
   dim3 grid((unsigned)blocks, (unsigned)ceil_div(C / 4, 32));
   static int variant = -1;
-  if (variant < 0) { const char* e = getenv("EPOS_DW_VARIANT"); variant = e ? atoi(e) : 1; }
-  if (variant == 1) {
+  if (variant < 0) { const char* e = getenv("EPOS_DW_VARIANT"); variant = e ? atoi(e) : 3; }
+  if (variant == 3 && stride == 1) {
+    // TMA-staged smem-tiled kernel (dw_tile.cu) for rate 1/2/4; other shapes use the register-strip kernel below
+    const int rc = dwconv3x3_tiled(x, ldx, w, bias, y_f32, y_split, B, H, W, C, rate, relu_in, relu_out, (cudaStream_t)stream);
+    if (rc != EPOS_ERR_UNSUPPORTED) return rc;
+  }
+  if (variant != 2) {
     dwconv3x3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, w, bias, y_f32, y_split,
                                                              (long long)B * Ho * Wo * C, B, H, W, C, Ho, Wo,
                                                              stride, rate, relu_in, relu_out);

@@ -1,0 +1,158 @@
+// Depthwise 3x3 (stride 1, rate 1/2/4) + folded BatchNorm (+ReLU before/after) as a TMA-staged, shared-memory tiled
+// kernel for sm_100a.  Replaces slim.separable_conv2d(depth_multiplier=1, num_outputs=None) + BatchNorm of
+// /root/reference/epos_lib/net_xception.py:150-170,270-296 and model.py:70-89 on the stride-1 layers.
+//
+// HBM-bound: algorithmic traffic = one f32 read of the input + one write of the output (f32 and/or split-bf16).
+// A CTA owns a TH x 16 spatial tile of one 32-channel slab.  One cp.async.bulk.tensor.4d brings the haloed
+// (TH+2r) x (16+2r) x 32-channel box into shared memory (rows of 128 B per pixel); out-of-image taps are zero-filled
+// by the TMA unit, so the compute loop has no bounds tests.  A thread = 4 channels x a strip of 4 output pixels: the
+// strip's 4+2r input columns are read once per filter row (LDS.128, 8 lanes cover the 128 B of a pixel: conflict-free)
+// and reused across the 3 horizontal taps; the 9 taps of the lane's channels live in registers.
+#include <cuda.h>
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace epos {
+
+constexpr int DT_TW = 16;          // tile width (output pixels)
+constexpr int DT_SLAB = 32;        // channels per CTA
+constexpr int DT_THREADS = 256;    // 8 channel groups x (4 strips per row x 8 rows per pass)
+
+template <int R>
+__global__ void __launch_bounds__(DT_THREADS) dwconv3x3_tile_kernel(
+    const __grid_constant__ CUtensorMap tmap, const float* __restrict__ w, const float* __restrict__ bias,
+    float* __restrict__ y_f32, uint16_t* __restrict__ y_split, long long plane_stride, int H, int W, int C, int TH,
+    int tiles_y, int slabs, int relu_in, int relu_out) {
+  constexpr int IW = DT_TW + 2 * R;
+  extern __shared__ __align__(128) uint8_t dt_smem[];
+  float4* tile = reinterpret_cast<float4*>(dt_smem + ((128u - (smem_u32(dt_smem) & 127u)) & 127u));
+  __shared__ uint64_t bar;
+  const int x0 = blockIdx.x * DT_TW;
+  const int y0 = (blockIdx.y % tiles_y) * TH;
+  const int b = blockIdx.y / tiles_y;
+  const int slab = blockIdx.z;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&bar, (uint32_t)((TH + 2 * R) * IW * DT_SLAB * 4));
+    tma_load_4d(tile, &tmap, &bar, slab * DT_SLAB, x0 - R, y0 - R, b);
+  }
+  const int cg = threadIdx.x & 7;              // 4-channel group inside the slab
+  const int sx = (threadIdx.x >> 3) & 3;       // strip (4 pixels) inside the tile row
+  const int sy = threadIdx.x >> 5;             // row inside a pass of 8 rows
+  const int c = slab * DT_SLAB + cg * 4;
+  const bool c_ok = c < C;
+  float4 wk[9];
+  float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c_ok) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wk[t] = __ldg(reinterpret_cast<const float4*>(w + (size_t)t * C + c));
+    bb = __ldg(reinterpret_cast<const float4*>(bias + c));
+  } else {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wk[t] = bb;
+  }
+  const float in_floor = relu_in ? 0.f : -INFINITY;
+  const float out_floor = relu_out ? 0.f : -INFINITY;
+  __syncthreads();                              // barrier initialised before anyone polls it
+  mbar_wait(&bar, 0);
+  for (int row = sy; row < TH; row += 8) {
+    float4 acc[4] = {bb, bb, bb, bb};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const float4* rp = tile + ((row + ky * R) * IW + sx * 4) * 8 + cg;
+#pragma unroll
+      for (int col = 0; col < 4 + 2 * R; ++col) {
+        float4 v = rp[col * 8];
+        v.x = fmaxf(v.x, in_floor); v.y = fmaxf(v.y, in_floor); v.z = fmaxf(v.z, in_floor); v.w = fmaxf(v.w, in_floor);
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int p = col - kx * R;
+          if (p >= 0 && p < 4) {
+            const float4 ww = wk[ky * 3 + kx];
+            acc[p].x = fmaf(v.x, ww.x, acc[p].x); acc[p].y = fmaf(v.y, ww.y, acc[p].y);
+            acc[p].z = fmaf(v.z, ww.z, acc[p].z); acc[p].w = fmaf(v.w, ww.w, acc[p].w);
+          }
+        }
+      }
+    }
+    const int oy = y0 + row;
+    if (!c_ok || oy >= H) continue;
+    const long long pix0 = ((long long)b * H + oy) * W + x0 + sx * 4;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      if (x0 + sx * 4 + p >= W) break;
+      float4 a = acc[p];
+      a.x = fmaxf(a.x, out_floor); a.y = fmaxf(a.y, out_floor); a.z = fmaxf(a.z, out_floor); a.w = fmaxf(a.w, out_floor);
+      const long long o = (pix0 + p) * C + c;
+      if (y_f32) *reinterpret_cast<float4*>(y_f32 + o) = a;
+      if (y_split) {
+        uint2 hi, lo;
+        split_bf16x2(a.x, a.y, hi.x, lo.x);
+        split_bf16x2(a.z, a.w, hi.y, lo.y);
+        *reinterpret_cast<uint2*>(y_split + o) = hi;
+        *reinterpret_cast<uint2*>(y_split + plane_stride + o) = lo;
+      }
+    }
+  }
+}
+
+// f32 NHWC [B][H][W][ldx] viewed as {C, W, H, B}; box {32, 16+2r, TH+2r, 1}, no swizzle, zero fill outside.
+static int make_dw_map(CUtensorMap* map, const float* x, int ldx, int B, int H, int W, int C, int TH, int R) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled not available"); return EPOS_ERR_CUDA; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)W * ldx * 4, (cuuint64_t)H * W * ldx * 4};
+  cuuint32_t box[4] = {(cuuint32_t)DT_SLAB, (cuuint32_t)(DT_TW + 2 * R), (cuuint32_t)(TH + 2 * R), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (dw) failed (%d) B=%d H=%d W=%d C=%d ldx=%d TH=%d R=%d", (int)r, B, H, W, C, ldx, TH, R);
+    return EPOS_ERR_CUDA;
+  }
+  return EPOS_OK;
+}
+
+template <int R>
+static int launch_dw_tile(const CUtensorMap& map, const float* w, const float* bias, float* y_f32, uint16_t* y_split,
+                          int B, int H, int W, int C, int TH, int relu_in, int relu_out, cudaStream_t stream) {
+  const int smem = (TH + 2 * R) * (DT_TW + 2 * R) * DT_SLAB * 4 + 128;
+  static int attr = 0;
+  if (smem > attr) {
+    EPOS_CUDA(cudaFuncSetAttribute(dwconv3x3_tile_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = smem;
+  }
+  const int tiles_y = ceil_div(H, TH), slabs = ceil_div(C, DT_SLAB);
+  dim3 grid(ceil_div(W, DT_TW), tiles_y * B, slabs);
+  dwconv3x3_tile_kernel<R><<<grid, DT_THREADS, smem, stream>>>(map, w, bias, y_f32, y_split, (long long)B * H * W * C, H,
+                                                              W, C, TH, tiles_y, slabs, relu_in, relu_out);
+  EPOS_LAUNCH_CHECK();
+  return EPOS_OK;
+}
+
+// Returns EPOS_ERR_UNSUPPORTED (without setting an error) when the shape is not one this kernel handles; the caller
+// then uses the register-strip kernel in cnn_kernels.cu.
+int dwconv3x3_tiled(const float* x, int ldx, const float* w, const float* bias, float* y_f32, uint16_t* y_split, int B,
+                    int H, int W, int C, int rate, int relu_in, int relu_out, cudaStream_t stream) {
+  if (!(rate == 1 || rate == 2 || rate == 4)) return EPOS_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || (ldx % 4) != 0 || (C % 4) != 0) return EPOS_ERR_UNSUPPORTED;
+  // tile height: a multiple of 4 in [8, 24] with the least padded rows (ties: the taller tile)
+  int TH = 8, best = 1 << 30;
+  for (int t = 8; t <= 24; t += 4) {
+    const int waste = ceil_div(H, t) * t - H;
+    if (waste <= best) { best = waste; TH = t; }
+  }
+  if ((long long)ceil_div(H, TH) * B > 65535 || ceil_div(C, DT_SLAB) > 65535) return EPOS_ERR_UNSUPPORTED;
+  CUtensorMap map;
+  int rc = make_dw_map(&map, x, ldx, B, H, W, C, TH, rate);
+  if (rc) return rc;
+  switch (rate) {
+    case 1: return launch_dw_tile<1>(map, w, bias, y_f32, y_split, B, H, W, C, TH, relu_in, relu_out, stream);
+    case 2: return launch_dw_tile<2>(map, w, bias, y_f32, y_split, B, H, W, C, TH, relu_in, relu_out, stream);
+    default: return launch_dw_tile<4>(map, w, bias, y_f32, y_split, B, H, W, C, TH, relu_in, relu_out, stream);
+  }
+}
+
+}  // namespace epos

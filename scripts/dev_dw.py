@@ -4,7 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from epos_b200 import _lib
 lib = _lib.lib(); dev = torch.device('cuda:0')
-shapes = [(8, 60, 80, 728, 1, 2), (8, 60, 80, 2048, 1, 12), (8, 120, 160, 256, 2, 1), (8, 240, 320, 128, 1, 1), (8, 60, 80, 1536, 1, 4)]
+shapes = [(8, 60, 80, 728, 1, 2), (8, 60, 80, 2048, 1, 12), (8, 120, 160, 256, 2, 1), (8, 240, 320, 128, 1, 1), (8, 60, 80, 1536, 1, 4),
+          (8, 120, 160, 304, 1, 1), (8, 60, 80, 1024, 1, 2), (8, 120, 160, 256, 1, 1)]
 for (B, H, W, C, stride, rate) in shapes:
     Ho, Wo = (H, W) if stride == 1 else ((H - 1) // 2 + 1, (W - 1) // 2 + 1)
     nb = 3
@@ -22,4 +23,4 @@ for (B, H, W, C, stride, rate) in shapes:
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / n * 1e3
     bytes_ = (B * H * W * C * 4 + B * Ho * Wo * C * 4)
-    print('variant %s  B%d %dx%dx%d s%d r%d: %.1f us  %.0f GB/s (alg)' % (os.environ.get('EPOS_DW_VARIANT', '0'), B, H, W, C, stride, rate, us, bytes_ / us / 1e3))
+    print('variant %s  B%d %dx%dx%d s%d r%d: %.1f us  %.0f GB/s (alg)' % (os.environ.get('EPOS_DW_VARIANT', 'default'), B, H, W, C, stride, rate, us, bytes_ / us / 1e3))

@@ -77,7 +77,8 @@ def test_pw_gemm_grouped_bias_and_slices(env):
 @pytest.mark.parametrize('C,H,W,stride,rate,relu_in,relu_out', [
     (64, 24, 32, 1, 1, True, False), (128, 24, 32, 2, 1, True, False), (728, 15, 20, 1, 2, True, False),
     (1024, 15, 20, 1, 4, False, True), (2048, 15, 20, 1, 12, False, True), (304, 30, 40, 1, 1, False, True),
-    (256, 9, 11, 2, 1, True, False), (2048, 15, 20, 1, 36, False, True)])
+    (256, 9, 11, 2, 1, True, False), (2048, 15, 20, 1, 36, False, True),
+    (728, 60, 80, 1, 2, True, False), (132, 50, 33, 1, 4, True, True), (20, 17, 19, 1, 1, False, False)])
 def test_dwconv(env, C, H, W, stride, rate, relu_in, relu_out):
     from epos_b200 import _lib
     from oracle import cnn
