@@ -37,6 +37,7 @@ struct GemmEpilogue {
   int bias_group_rows;
   int ldr, ldd, ldd_split;
   int relu;
+  int softmax64;    // act == 2: softmax over aligned groups of 64 output columns (after bias), fused into the epilogue
 };
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -95,10 +96,64 @@ __device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
                : "memory");
 }
 
+// Work distribution.  Full waves of 128 x BLOCK_N tiles are dealt round-robin in n-major order (CTAs that run together
+// share A tiles in L2).  A plain tile grid then loses up to a whole wave on the remainder (the 38400 x 728 layers are
+// 900 tiles = 6.08 waves on 148 SMs), so when the remainder is at most half a wave its tiles are cut into blocks of
+// 64 columns that are spread evenly over all CTAs: the tail costs a fraction of a tile time instead of a full one.
+// All three warp roles walk the same sequence of pieces (rows [m0, m0+128) x columns [n0, n0+n_cols)).
+struct PieceIter {
+  int n_tiles, bulk_end, tile, block_n, N;
+  int unit, upt;                       // tail: columns per block, blocks per full tile
+  int tail_tile, tail_acc, lo, hi;     // tail cursor: current tile, blocks before it, this CTA's block range
+  int num_tiles;
+  __device__ PieceIter(int M, int N_, int block_n_) {
+    N = N_; block_n = block_n_;
+    n_tiles = (N + block_n - 1) / block_n;
+    num_tiles = ((M + BLOCK_M - 1) / BLOCK_M) * n_tiles;
+    const int G = gridDim.x;
+    int rem = num_tiles % G;
+    unit = block_n < 64 ? block_n : 64;
+    upt = block_n / unit;
+    if (rem * 2 > G || upt == 1) rem = 0;          // a remainder above half a wave (or unsplittable tiles) stays whole
+    bulk_end = num_tiles - rem;
+    tile = blockIdx.x;
+    tail_tile = bulk_end; tail_acc = 0; lo = hi = 0;
+    if (rem) {
+      long long total = 0;
+      for (int t = bulk_end; t < num_tiles; ++t) total += blocks_of(t);
+      lo = (int)(total * blockIdx.x / G);
+      hi = (int)(total * (blockIdx.x + 1) / G);
+    }
+  }
+  __device__ int blocks_of(int t) const {
+    int w = N - (t % n_tiles) * block_n;
+    if (w > block_n) w = block_n;
+    return (w + unit - 1) / unit;
+  }
+  __device__ bool next(int& m0, int& n0, int& n_cols) {
+    if (tile < bulk_end) {
+      m0 = (tile / n_tiles) * BLOCK_M; n0 = (tile % n_tiles) * block_n; n_cols = block_n;
+      tile += gridDim.x;
+      return true;
+    }
+    if (lo >= hi) return false;
+    int nb = blocks_of(tail_tile);
+    while (tail_acc + nb <= lo) { tail_acc += nb; ++tail_tile; nb = blocks_of(tail_tile); }
+    const int first = lo - tail_acc;
+    int cnt = nb - first;
+    if (cnt > hi - lo) cnt = hi - lo;
+    m0 = (tail_tile / n_tiles) * BLOCK_M; n0 = (tail_tile % n_tiles) * block_n + first * unit; n_cols = cnt * unit;
+    lo += cnt;
+    return true;
+  }
+};
+
 template <int BLOCK_N, int BLOCK_K>
 struct GemmCfg {
   static constexpr int A_BYTES = 2 * BLOCK_M * BLOCK_K * 2;       // both planes
   static constexpr int B_BYTES = 2 * BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_BOX_ROWS = BLOCK_N < 64 ? BLOCK_N : 64;    // W is loaded in boxes of this many rows per plane
+  static constexpr int B_BOX_BYTES = B_BOX_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES < 2 ? 2 : ((200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
@@ -109,6 +164,7 @@ struct GemmCfg {
 template <int BLOCK_N, int BLOCK_K>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+               const __grid_constant__ CUtensorMap tmap_w64,
                const GemmEpilogue ep, int M, int N, int K, int dbg) {
   using Cfg = GemmCfg<BLOCK_N, BLOCK_K>;
   constexpr int STAGES = Cfg::STAGES;
@@ -128,14 +184,12 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
-  const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
-  const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w64) : "memory");
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -156,14 +210,28 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * BLOCK_M;
-        const int n0 = (tile % n_tiles) * BLOCK_N;
+      PieceIter it(M, N, BLOCK_N);
+      int m0, n0, n_cols;
+      while (it.next(m0, n0, n_cols)) {
+        int n_rows = N - n0;                                       // W rows this piece needs
+        if (n_rows > n_cols) n_rows = n_cols;
+        const bool full = n_cols == BLOCK_N;                        // whole tile: one box (rows past N are zero-filled)
+        const int n_boxes = (n_rows + Cfg::B_BOX_ROWS - 1) / Cfg::B_BOX_ROWS;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], (dbg & 64) ? Cfg::A_BYTES : ((dbg & 128) ? Cfg::B_BYTES : Cfg::STAGE_BYTES));
+          mbar_expect_tx(&full_bar[stage], ((dbg & 128) ? 0 : Cfg::A_BYTES) + ((dbg & 64) ? 0 : (full ? Cfg::B_BYTES : 2 * n_boxes * Cfg::B_BOX_BYTES)));
           if (!(dbg & 128)) tma_load_3d(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K, m0, 0);
-          if (!(dbg & 64)) tma_load_3d(smem_b + stage * Cfg::B_BYTES, &tmap_w, &full_bar[stage], kb * BLOCK_K, n0, 0);
+          if (!(dbg & 64)) {
+            uint8_t* b_hi = smem_b + stage * Cfg::B_BYTES;
+            uint8_t* b_lo = b_hi + BLOCK_N * BLOCK_K * 2;
+            if (full) {
+              tma_load_3d(b_hi, &tmap_w, &full_bar[stage], kb * BLOCK_K, n0, 0);      // both planes, all BLOCK_N rows
+            } else
+            for (int j = 0; j < n_boxes; ++j) {
+              tma_load_3d(b_hi + j * Cfg::B_BOX_BYTES, &tmap_w64, &full_bar[stage], kb * BLOCK_K, n0 + j * Cfg::B_BOX_ROWS, 0);
+              tma_load_3d(b_lo + j * Cfg::B_BOX_BYTES, &tmap_w64, &full_bar[stage], kb * BLOCK_K, n0 + j * Cfg::B_BOX_ROWS, 1);
+            }
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -176,10 +244,12 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n0 = (tile % n_tiles) * BLOCK_N;
+      PieceIter it(M, N, BLOCK_N);
+      int m0, n0, n_cols;
+      while (it.next(m0, n0, n_cols)) {
         int umma_n = N - n0;
-        umma_n = umma_n >= BLOCK_N ? BLOCK_N : ((umma_n + 15) & ~15);
+        if (umma_n > n_cols) umma_n = n_cols;
+        umma_n = (umma_n + 15) & ~15;                              // columns past the piece are computed but never stored
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(umma_n >> 3) << 17) |
                                ((uint32_t)(BLOCK_M >> 4) << 24);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -192,8 +262,12 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint32_t a_lo = a_hi + BLOCK_M * BLOCK_K * 2;
           const uint32_t b_hi = smem_u32(smem_b + stage * Cfg::B_BYTES);
           const uint32_t b_lo = b_hi + BLOCK_N * BLOCK_K * 2;
+          // the last K block of a ragged K (728 = 11 x 64 + 24) only needs the UMMA_K steps that hold data
+          const int k_left = K - kb * BLOCK_K;
+          const int k_steps = k_left >= BLOCK_K ? BLOCK_K / UMMA_K : (k_left + UMMA_K - 1) / UMMA_K;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            if (k >= k_steps) break;
             const uint32_t koff = k * UMMA_K * 2;
             const uint64_t da_hi = make_smem_desc<BLOCK_K>(a_hi + koff), da_lo = make_smem_desc<BLOCK_K>(a_lo + koff);
             const uint64_t db_hi = make_smem_desc<BLOCK_K>(b_hi + koff), db_lo = make_smem_desc<BLOCK_K>(b_lo + koff);
@@ -232,16 +306,73 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     float4* stg = reinterpret_cast<float4*>(staging + (warp - 2) * 1024);
     const int rsub = lane >> 3, jj = lane & 7;
     const float relu_floor = ep.relu ? 0.f : -INFINITY;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_tiles) * BLOCK_M;
-      const int n0 = (tile % n_tiles) * BLOCK_N;
+    PieceIter it(M, N, BLOCK_N);
+    int m0, n0, n_cols;
+    while (it.next(m0, n0, n_cols)) {
       int n_valid = N - n0;
-      if (n_valid > BLOCK_N) n_valid = BLOCK_N;
+      if (n_valid > n_cols) n_valid = n_cols;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int row_base = m0 + quarter * 32;
       const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
       if (dbg & 32) {
+      } else if (fast && ep.softmax64) {
+        // Fused softmax over groups of 64 columns (tf.nn.softmax over the fragment axis, model.py:676-678): a lane owns
+        // one row, so the 64 logits of a group are 2 x 32 registers and max / sum need no cross-lane traffic.
+        const int rows_left = M - row_base - rsub;
+#pragma unroll 1
+        for (int c0 = 0; c0 < n_valid; c0 += 64) {
+          uint32_t r0[32], r1[32];
+          __syncwarp();
+          tmem_ld32_issue(tacc + (uint32_t)c0, r0);
+          tmem_ld32_wait(r0);
+          tmem_ld32_issue(tacc + (uint32_t)(c0 + 32), r1);
+          tmem_ld32_wait(r1);
+          float mx = -INFINITY;
+          if (ep.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(ep.bias + n0 + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 qa = __ldg(bp + j), qb = __ldg(bp + 8 + j);
+              r0[4 * j] = __float_as_uint(__uint_as_float(r0[4 * j]) + qa.x);
+              r0[4 * j + 1] = __float_as_uint(__uint_as_float(r0[4 * j + 1]) + qa.y);
+              r0[4 * j + 2] = __float_as_uint(__uint_as_float(r0[4 * j + 2]) + qa.z);
+              r0[4 * j + 3] = __float_as_uint(__uint_as_float(r0[4 * j + 3]) + qa.w);
+              r1[4 * j] = __float_as_uint(__uint_as_float(r1[4 * j]) + qb.x);
+              r1[4 * j + 1] = __float_as_uint(__uint_as_float(r1[4 * j + 1]) + qb.y);
+              r1[4 * j + 2] = __float_as_uint(__uint_as_float(r1[4 * j + 2]) + qb.z);
+              r1[4 * j + 3] = __float_as_uint(__uint_as_float(r1[4 * j + 3]) + qb.w);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[j]), __uint_as_float(r1[j])));
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float e0 = expf(__uint_as_float(r0[j]) - mx), e1 = expf(__uint_as_float(r1[j]) - mx);
+            r0[j] = __float_as_uint(e0); r1[j] = __float_as_uint(e1);
+            sum += e0 + e1;
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t* r = h ? r1 : r0;
+              stg[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]) / sum, __uint_as_float(r[4 * j + 1]) / sum,
+                                                             __uint_as_float(r[4 * j + 2]) / sum, __uint_as_float(r[4 * j + 3]) / sum);
+            }
+            __syncwarp();
+            const int col = n0 + c0 + 32 * h + jj * 4;
+            float* df = ep.d_f32 + (long long)(row_base + rsub) * ep.ldd + col;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = i * 4 + rsub;
+              const float4 v = stg[rr * 8 + (jj ^ (rr & 7))];
+              if (col < N && 4 * i < rows_left) *reinterpret_cast<float4*>(df + (long long)(4 * i) * ep.ldd) = v;
+            }
+          }
+        }
       } else if (fast) {
         int g0 = 0, boundary = 0x7fffffff;
         if (ep.bias && ep.bias_group_rows > 0) {
@@ -360,14 +491,14 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // ---------------------------------------------------------------------------------------------------------
 // Host side: tensor maps + launch
 // ---------------------------------------------------------------------------------------------------------
-// [2][rows][ld] bf16, box {block_k, box_rows, 2}
+// [2][rows][ld] bf16, box {block_k, box_rows, box_planes}
 static int make_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, size_t plane_stride, int box_rows,
-                    int block_k) {
+                    int block_k, int box_planes) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled not available"); return EPOS_ERR_CUDA; }
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane_stride * 2};
-  cuuint32_t box[3] = {(cuuint32_t)block_k, (cuuint32_t)box_rows, 2};
+  cuuint32_t box[3] = {(cuuint32_t)block_k, (cuuint32_t)box_rows, (cuuint32_t)box_planes};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -382,7 +513,7 @@ static int make_map(CUtensorMap* map, const void* base, int rows, int cols, int 
 }
 
 template <int BLOCK_N, int BLOCK_K>
-static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const GemmEpilogue& ep, int M, int N, int K,
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mw64, const GemmEpilogue& ep, int M, int N, int K,
                        cudaStream_t stream, int dbg) {
   using Cfg = GemmCfg<BLOCK_N, BLOCK_K>;
   static bool attr = false;
@@ -390,9 +521,10 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const GemmE
     EPOS_CUDA(cudaFuncSetAttribute(pw_gemm_kernel<BLOCK_N, BLOCK_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr = true;
   }
-  const int tiles = ceil_div(M, BLOCK_M) * ceil_div(N, BLOCK_N);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  pw_gemm_kernel<BLOCK_N, BLOCK_K><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mw, ep, M, N, K, dbg);
+  // one CTA per SM; with less than a wave of tiles the remainder logic of PieceIter spreads 64-column blocks
+  const long long blocks64 = (long long)ceil_div(M, BLOCK_M) * ceil_div(N, BLOCK_N < 64 ? BLOCK_N : 64);
+  const int grid = blocks64 < num_sms() ? (int)blocks64 : num_sms();
+  pw_gemm_kernel<BLOCK_N, BLOCK_K><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mw, mw64, ep, M, N, K, dbg);
   EPOS_LAUNCH_CHECK();
   return EPOS_OK;
 }
@@ -425,28 +557,35 @@ extern "C" int epos_pwconv_gemm(const uint16_t* a_split, int lda, size_t a_plane
   const int bk = bk_env ? bk_env : 64;
   const char* de = getenv("EPOS_GEMM_DEBUG");   // developer A/B switches (scripts/dev_gemm.py); 0 in production
   const int dbg = de ? atoi(de) : 0;
-  CUtensorMap ma, mw;
-  int rc = make_map(&ma, a_split, M, K, lda, a_plane_stride, BLOCK_M, bk);
+  CUtensorMap ma, mw, mw64;
+  int rc = make_map(&ma, a_split, M, K, lda, a_plane_stride, BLOCK_M, bk, 2);
   if (rc) return rc;
-  rc = make_map(&mw, w_split, N, K, K, (size_t)N * K, bn, bk);
+  rc = make_map(&mw, w_split, N, K, K, (size_t)N * K, bn, bk, 2);
+  if (rc) return rc;
+  rc = make_map(&mw64, w_split, N, K, K, (size_t)N * K, bn < 64 ? bn : 64, bk, 1);
   if (rc) return rc;
   GemmEpilogue ep;
   ep.bias = bias; ep.residual = residual; ep.d_f32 = d_f32; ep.d_split = d_split;
   ep.d_plane_stride = (long long)d_plane_stride; ep.bias_group_rows = bias_group_rows;
-  ep.ldr = ldr; ep.ldd = ldd; ep.ldd_split = ldd_split; ep.relu = relu;
+  ep.ldr = ldr; ep.ldd = ldd; ep.ldd_split = ldd_split; ep.relu = relu == 1; ep.softmax64 = relu == 2;
+  if (relu == 2) {
+    // fused softmax needs whole 64-column groups per piece and the aligned fast path; f32 output only
+    EPOS_CHECK_ARG(d_f32 && !d_split && !residual && bias_group_rows == 0 && (N % 64) == 0 && (ldd % 4) == 0 &&
+                   (reinterpret_cast<uintptr_t>(d_f32) & 15) == 0 && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0));
+  }
   cudaStream_t s = (cudaStream_t)stream;
   if (bk == 32) {
     switch (bn) {
-      case 256: return launch_gemm<256, 32>(ma, mw, ep, M, N, K, s, dbg);
-      case 128: return launch_gemm<128, 32>(ma, mw, ep, M, N, K, s, dbg);
-      case 64: return launch_gemm<64, 32>(ma, mw, ep, M, N, K, s, dbg);
-      default: return launch_gemm<32, 32>(ma, mw, ep, M, N, K, s, dbg);
+      case 256: return launch_gemm<256, 32>(ma, mw, mw64, ep, M, N, K, s, dbg);
+      case 128: return launch_gemm<128, 32>(ma, mw, mw64, ep, M, N, K, s, dbg);
+      case 64: return launch_gemm<64, 32>(ma, mw, mw64, ep, M, N, K, s, dbg);
+      default: return launch_gemm<32, 32>(ma, mw, mw64, ep, M, N, K, s, dbg);
     }
   }
   switch (bn) {
-    case 256: return launch_gemm<256, 64>(ma, mw, ep, M, N, K, s, dbg);
-    case 128: return launch_gemm<128, 64>(ma, mw, ep, M, N, K, s, dbg);
-    case 64: return launch_gemm<64, 64>(ma, mw, ep, M, N, K, s, dbg);
-    default: return launch_gemm<32, 64>(ma, mw, ep, M, N, K, s, dbg);
+    case 256: return launch_gemm<256, 64>(ma, mw, mw64, ep, M, N, K, s, dbg);
+    case 128: return launch_gemm<128, 64>(ma, mw, mw64, ep, M, N, K, s, dbg);
+    case 64: return launch_gemm<64, 64>(ma, mw, mw64, ep, M, N, K, s, dbg);
+    default: return launch_gemm<32, 64>(ma, mw, mw64, ep, M, N, K, s, dbg);
   }
 }

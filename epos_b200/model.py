@@ -303,11 +303,13 @@ class EposNet:
         M = B * h * w
         O, F = self.O, self.F
         obj, _ = self.gemm(feat_split, self.p['logits/' + PRED_OBJ_CONF], M, relu=False)
-        fc, _ = self.gemm(feat_split, self.p['logits/' + PRED_FRAG_CONF], M, relu=False)
+        fused = F % 64 == 0 and self.impl == 'tcgen05'      # softmax over F in the GEMM epilogue (relu = 2)
+        fc, _ = self.gemm(feat_split, self.p['logits/' + PRED_FRAG_CONF], M, relu=2 if fused else False)
         fl, _ = self.gemm(feat_split, self.p['logits/' + PRED_FRAG_LOC], M, relu=False)
         labels = torch.empty((M,), dtype=torch.int64, device=self.dev)
         _lib.check(self.lib.epos_softmax_rows(obj.data_ptr(), labels.data_ptr(), M, O + 1, self._s()), 'epos_softmax_rows')
-        _lib.check(self.lib.epos_softmax_rows(fc.data_ptr(), None, M * O, F, self._s()), 'epos_softmax_rows')
+        if not fused:
+            _lib.check(self.lib.epos_softmax_rows(fc.data_ptr(), None, M * O, F, self._s()), 'epos_softmax_rows')
         return {PRED_OBJ_CONF: obj.view(B, h, w, O + 1), PRED_OBJ_LABEL: labels.view(B, h, w),
                 PRED_FRAG_CONF: fc.view(B, h, w, O, F), PRED_FRAG_LOC: fl.view(B, h, w, O, F, 3)}
 

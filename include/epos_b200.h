@@ -67,7 +67,10 @@ int epos_dwconv3x3(const float* x, int ldx, const float* w, const float* bias,
  * model.py:90-97,223-258,350-352,448-456.
  * a_split [2][M][lda] bf16; w_split [2][N][K] bf16; bias [groups][N] f32 (bias_group_rows = 0: one row);
  * residual f32 with leading dim ldr or NULL; outputs: d_f32 (leading dim ldd) and/or d_split
- * ([2][M][ldd_split], plane stride = split_plane_stride elements), either may be NULL. */
+ * ([2][M][ldd_split], plane stride = split_plane_stride elements), either may be NULL.
+ * relu: 0 = identity, 1 = ReLU, 2 = softmax over aligned groups of 64 output columns fused into the
+ * epilogue (tf.nn.softmax over the fragment axis, model.py:676-678; needs N % 64 == 0, f32 output only,
+ * no residual). */
 int epos_pwconv_gemm(const uint16_t* a_split, int lda, size_t a_plane_stride,
                      const uint16_t* w_split, const float* bias, int bias_group_rows,
                      const float* residual, int ldr,

@@ -55,6 +55,45 @@ def test_pw_gemm(env, M, N, K, mode):
     assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) < tol
 
 
+@pytest.mark.parametrize('M,N,K', [(300, 128, 64), (4000, 1344, 256), (129, 64, 40)])
+def test_pw_gemm_fused_softmax64(env, M, N, K):
+    """relu = 2: softmax over aligned groups of 64 output columns in the GEMM epilogue (model.py:676-678)."""
+    from epos_b200 import _lib
+    lib, dev = env
+    g = torch.Generator(device='cpu').manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(dev)
+    w = (torch.randn(N, K, generator=g) * 0.5).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    ref = torch.softmax((a.double() @ w.double().T + bias.double()).view(M, N // 64, 64), dim=-1).view(M, N)
+    a_s, w_s = split(a), split(w)
+    d = torch.full((M, N), float('nan'), device=dev)
+    rc = lib.epos_pwconv_gemm(a_s.data_ptr(), K, a_s.stride(0), w_s.data_ptr(), bias.data_ptr(), 0, None, 0,
+                              d.data_ptr(), N, None, 0, 0, M, N, K, 2, torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, 'gemm')
+    torch.cuda.synchronize()
+    assert rel_err(d.cpu().numpy(), ref.cpu().numpy()) < 1e-4
+    assert abs(float(d.sum()) - M * N // 64) < 1e-2 * M
+
+
+def test_pw_gemm_balanced_pieces_cover_everything(env):
+    """Shapes whose (m-tile, 8-column) units do not divide by the SM count: every output must be written exactly once
+    (NaN-prefilled destination) and rows/columns outside [M, N) must stay untouched."""
+    from epos_b200 import _lib
+    lib, dev = env
+    for M, N, K in [(38400, 728, 72), (4800, 728, 40), (1000, 1000, 24), (129, 264, 16), (5000, 48, 32)]:
+        a = torch.randn(M, K, device=dev)
+        w = torch.randn(N, K, device=dev) * 0.1
+        a_s, w_s = split(a), split(w)
+        buf = torch.full((M + 3, N + 8), float('nan'), device=dev)
+        rc = lib.epos_pwconv_gemm(a_s.data_ptr(), K, a_s.stride(0), w_s.data_ptr(), None, 0, None, 0,
+                                  buf.data_ptr(), N + 8, None, 0, 0, M, N, K, 0, torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, 'gemm')
+        torch.cuda.synchronize()
+        ref = a.double() @ w.double().T
+        assert rel_err(buf[:M, :N].cpu().numpy(), ref.cpu().numpy()) < 2e-5, (M, N, K)
+        assert bool(torch.isnan(buf[M:]).all()) and bool(torch.isnan(buf[:, N:]).all()), (M, N, K)
+
+
 def test_pw_gemm_grouped_bias_and_slices(env):
     """per-image bias rows (image-pooling fold) and strided output slices (concat buffers)."""
     from epos_b200 import _lib
