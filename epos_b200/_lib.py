@@ -27,7 +27,10 @@ _SIGS = {
     'epos_version': (i32, []),
     'epos_compiled_arch': (i32, []),
     'epos_launch_count': (u64, []),
-    'epos_conv3x3_rgb_s2': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    'epos_conv3x3_rgb_s2': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    'epos_maxpool3x3_s2': (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
+    'epos_subsample_f32': (i32, [vp, i32, vp, i32, i32, i32, i32, i32, vp]),
+    'epos_conv3x3_gemm': (i32, [vp, i32, sz, vp, vp, vp, i32, vp, i32, vp, i32, sz, i32, i32, i32, i32, i32, i32, i32, vp]),
     'epos_conv3x3_dense': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     'epos_dwconv3x3': (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     'epos_pwconv_gemm': (i32, [vp, i32, sz, vp, vp, i32, vp, i32, vp, i32, vp, i32, sz, i32, i32, i32, i32, vp]),

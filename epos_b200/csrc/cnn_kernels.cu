@@ -25,6 +25,7 @@ void set_error(const char* fmt, ...) {
 template <int COUT>
 __global__ void __launch_bounds__(256) conv3x3_rgb_s2_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ bias, float* __restrict__ y,
+                                                             uint16_t* __restrict__ y_split, long long plane_stride,
                                                              int B, int H, int W, int Ho, int Wo) {
   __shared__ float sw[27 * COUT];
   __shared__ float sb[COUT];
@@ -61,7 +62,15 @@ __global__ void __launch_bounds__(256) conv3x3_rgb_s2_kernel(const float* __rest
       }
     }
     float4 o = make_float4(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
-    *reinterpret_cast<float4*>(y + (((long long)b * Ho + oy) * Wo + ox) * COUT + g * 4) = o;
+    const long long off = (((long long)b * Ho + oy) * Wo + ox) * COUT + g * 4;
+    if (y) *reinterpret_cast<float4*>(y + off) = o;
+    if (y_split) {
+      uint2 hi, lo;
+      split_bf16x2(o.x, o.y, hi.x, lo.x);
+      split_bf16x2(o.z, o.w, hi.y, lo.y);
+      *reinterpret_cast<uint2*>(y_split + off) = hi;
+      *reinterpret_cast<uint2*>(y_split + plane_stride + off) = lo;
+    }
   }
 }
 
@@ -271,6 +280,64 @@ __global__ void __launch_bounds__(256) dwconv3x3_flat_kernel(const float* __rest
 }
 
 
+// slim.max_pool2d(3, stride 2, 'SAME') (net_resnet_v1_beta.py:187): TF pads total = max((ceil(n/2)-1)*2+3-n, 0), before =
+// floor(total/2) (0/1 for even n, 1/1 for odd n); padded taps never win the max.
+__global__ void __launch_bounds__(256) maxpool3x3_s2_kernel(const float* __restrict__ x, float* __restrict__ y_f32,
+                                                            uint16_t* __restrict__ y_split, long long plane_stride, int B,
+                                                            int H, int W, int C, int Ho, int Wo) {
+  const int G = C >> 2;
+  const int pt = max((Ho - 1) * 2 + 3 - H, 0) / 2, pl = max((Wo - 1) * 2 + 3 - W, 0) / 2;
+  const long long total = (long long)B * Ho * Wo * G;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % G);
+    long long p = idx / G;
+    const int ox = (int)(p % Wo);
+    long long q = p / Wo;
+    const int oy = (int)(q % Ho);
+    const int b = (int)(q / Ho);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * 2 - pt + ky;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * 2 - pl + kx;
+        if (ix < 0 || ix >= W) continue;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + (((long long)b * H + iy) * W + ix) * C) + g);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    }
+    if (y_f32) *(reinterpret_cast<float4*>(y_f32 + p * C) + g) = m;
+    if (y_split) {
+      uint2 hi, lo;
+      split_bf16x2(m.x, m.y, hi.x, lo.x);
+      split_bf16x2(m.z, m.w, hi.y, lo.y);
+      *(reinterpret_cast<uint2*>(y_split + p * C) + g) = hi;
+      *(reinterpret_cast<uint2*>(y_split + plane_stride + p * C) + g) = lo;
+    }
+  }
+}
+
+// resnet_utils.subsample (external/slim/nets/resnet_utils.py:59-74): every factor-th pixel, f32 -> f32.
+__global__ void __launch_bounds__(256) subsample_f32_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y,
+                                                            int B, int H, int W, int C, int Ho, int Wo, int factor) {
+  const int G = C >> 2;
+  const long long total = (long long)B * Ho * Wo * G;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % G);
+    long long p = idx / G;
+    const int ox = (int)(p % Wo);
+    long long q = p / Wo;
+    const int oy = (int)(q % Ho);
+    const int b = (int)(q / Ho);
+    *(reinterpret_cast<float4*>(y + p * C) + g) =
+        __ldg(reinterpret_cast<const float4*>(x + (((long long)b * H + oy * factor) * W + ox * factor) * ldx) + g);
+  }
+}
+
 __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, int ldx, uint16_t* __restrict__ y,
                                                          int ldy, long long plane_stride, int B, int H, int W, int C,
                                                          int Ho, int Wo, int sub, int relu) {
@@ -420,8 +487,8 @@ __global__ void __launch_bounds__(256) pwconv_simt_kernel(const float* __restric
       const int n = n0 + tx * 4 + j;
       if (n >= N) continue;
       float v = acc[i][j] + (brow ? brow[n] : 0.f);
-      if (relu) v = fmaxf(v, 0.f);
       if (residual) v += residual[(long long)m * ldr + n];
+      if (relu) v = fmaxf(v, 0.f);                       // after the residual add, as in the tcgen05 kernel
       d[(long long)m * ldd + n] = v;
     }
   }
@@ -444,13 +511,39 @@ int epos_version(void) { return 1; }
 int epos_compiled_arch(void) { return 100; }
 uint64_t epos_launch_count(void) { return (uint64_t)g_launches.load(); }
 
-int epos_conv3x3_rgb_s2(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Cout,
-                        void* stream) {
-  EPOS_CHECK_ARG(x && w && bias && y && B > 0 && H > 0 && W > 0);
-  if (Cout != 32) { set_error("epos_conv3x3_rgb_s2: Cout=%d unsupported (32)", Cout); return EPOS_ERR_UNSUPPORTED; }
+int epos_conv3x3_rgb_s2(const float* x, const float* w, const float* bias, float* y, uint16_t* y_split, int B, int H,
+                        int W, int Cout, void* stream) {
+  EPOS_CHECK_ARG(x && w && bias && (y || y_split) && B > 0 && H > 0 && W > 0);
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const long long total = (long long)B * Ho * Wo * (Cout / 4);
-  conv3x3_rgb_s2_kernel<32><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, B, H, W, Ho, Wo);
+  const long long plane = (long long)B * Ho * Wo * Cout;
+  if (Cout == 32) {
+    conv3x3_rgb_s2_kernel<32><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, y_split, plane, B, H, W, Ho, Wo);
+  } else if (Cout == 64) {
+    conv3x3_rgb_s2_kernel<64><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, y_split, plane, B, H, W, Ho, Wo);
+  } else {
+    set_error("epos_conv3x3_rgb_s2: Cout=%d unsupported (32, 64)", Cout);
+    return EPOS_ERR_UNSUPPORTED;
+  }
+  EPOS_LAUNCH_CHECK();
+  return EPOS_OK;
+}
+
+int epos_maxpool3x3_s2(const float* x, float* y_f32, uint16_t* y_split, int B, int H, int W, int C, void* stream) {
+  EPOS_CHECK_ARG(x && (y_f32 || y_split) && B > 0 && H > 0 && W > 0 && C > 0 && (C % 4) == 0);
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const long long total = (long long)B * Ho * Wo * (C / 4);
+  maxpool3x3_s2_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, y_f32, y_split, (long long)B * Ho * Wo * C, B,
+                                                                         H, W, C, Ho, Wo);
+  EPOS_LAUNCH_CHECK();
+  return EPOS_OK;
+}
+
+int epos_subsample_f32(const float* x, int ldx, float* y, int B, int H, int W, int C, int factor, void* stream) {
+  EPOS_CHECK_ARG(x && y && B > 0 && H > 0 && W > 0 && C > 0 && (C % 4) == 0 && (ldx % 4) == 0 && factor >= 1);
+  const int Ho = (H - 1) / factor + 1, Wo = (W - 1) / factor + 1;
+  const long long total = (long long)B * Ho * Wo * (C / 4);
+  subsample_f32_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, ldx, y, B, H, W, C, Ho, Wo, factor);
   EPOS_LAUNCH_CHECK();
   return EPOS_OK;
 }

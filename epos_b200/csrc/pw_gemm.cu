@@ -26,6 +26,7 @@ namespace epos {
 
 constexpr int BLOCK_M = 128;
 constexpr int UMMA_K = 16;
+constexpr int GEMM_BK = 64;        // K block (bf16 elements): rows of 128 B, 128-byte swizzle
 constexpr int NUM_THREADS = 192;
 
 struct GemmEpilogue {
@@ -101,15 +102,27 @@ __device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
 // 900 tiles = 6.08 waves on 148 SMs), so when the remainder is at most half a wave its tiles are cut into blocks of
 // 64 columns that are spread evenly over all CTAs: the tail costs a fraction of a tile time instead of a full one.
 // All three warp roles walk the same sequence of pieces (rows [m0, m0+128) x columns [n0, n0+n_cols)).
+// 3x3 (atrous) convolution as an implicit GEMM: K = 9 taps x C channels, an M tile is an 8 x 16 block of output
+// pixels of one image, and the A box of tap (ky, kx) is the same block shifted by ((ky-1) rate, (kx-1) rate) --
+// out-of-image rows/columns are zero-filled by the TMA unit, which is exactly TF 'SAME' padding at stride 1.
+struct ConvGeom {
+  int enabled;
+  int H, W;                // output (= input) spatial size
+  int tiles_x, tiles_y;    // ceil(W / 16), ceil(H / 8)
+  int rate;
+  int cpb;                 // channel blocks per tap = C / BLOCK_K
+};
+constexpr int CONV_TW = 16, CONV_TH = 8;
+
 struct PieceIter {
   int n_tiles, bulk_end, tile, block_n, N;
   int unit, upt;                       // tail: columns per block, blocks per full tile
   int tail_tile, tail_acc, lo, hi;     // tail cursor: current tile, blocks before it, this CTA's block range
   int num_tiles;
-  __device__ PieceIter(int M, int N_, int block_n_) {
+  __device__ PieceIter(int m_tiles, int N_, int block_n_) {
     N = N_; block_n = block_n_;
     n_tiles = (N + block_n - 1) / block_n;
-    num_tiles = ((M + BLOCK_M - 1) / BLOCK_M) * n_tiles;
+    num_tiles = m_tiles * n_tiles;
     const int G = gridDim.x;
     int rem = num_tiles % G;
     unit = block_n < 64 ? block_n : 64;
@@ -165,7 +178,7 @@ template <int BLOCK_N, int BLOCK_K>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                const __grid_constant__ CUtensorMap tmap_w64,
-               const GemmEpilogue ep, int M, int N, int K, int dbg) {
+               const GemmEpilogue ep, const ConvGeom cg, int M, int N, int K, int dbg) {
   using Cfg = GemmCfg<BLOCK_N, BLOCK_K>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -185,6 +198,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  const int m_tiles = cg.enabled ? (M / (cg.H * cg.W)) * cg.tiles_x * cg.tiles_y : (M + BLOCK_M - 1) / BLOCK_M;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
@@ -210,17 +224,29 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      PieceIter it(M, N, BLOCK_N);
+      PieceIter it(m_tiles, N, BLOCK_N);
       int m0, n0, n_cols;
       while (it.next(m0, n0, n_cols)) {
         int n_rows = N - n0;                                       // W rows this piece needs
         if (n_rows > n_cols) n_rows = n_cols;
         const bool full = n_cols == BLOCK_N;                        // whole tile: one box (rows past N are zero-filled)
+        int cb = 0, cy0 = 0, cx0 = 0;
+        if (cg.enabled) {
+          const int t = m0 / BLOCK_M, per_img = cg.tiles_x * cg.tiles_y;
+          cb = t / per_img;
+          const int q = t - cb * per_img;
+          cy0 = (q / cg.tiles_x) * CONV_TH; cx0 = (q % cg.tiles_x) * CONV_TW;
+        }
         const int n_boxes = (n_rows + Cfg::B_BOX_ROWS - 1) / Cfg::B_BOX_ROWS;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], ((dbg & 128) ? 0 : Cfg::A_BYTES) + ((dbg & 64) ? 0 : (full ? Cfg::B_BYTES : 2 * n_boxes * Cfg::B_BOX_BYTES)));
-          if (!(dbg & 128)) tma_load_3d(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K, m0, 0);
+          if (cg.enabled) {
+            const int tap = kb / cg.cpb, c0 = (kb - tap * cg.cpb) * BLOCK_K;
+            const int ky = tap / 3, kx = tap - ky * 3;
+            tma_load_5d(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage], c0, cx0 + (kx - 1) * cg.rate,
+                        cy0 + (ky - 1) * cg.rate, cb, 0);
+          } else if (!(dbg & 128)) tma_load_3d(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K, m0, 0);
           if (!(dbg & 64)) {
             uint8_t* b_hi = smem_b + stage * Cfg::B_BYTES;
             uint8_t* b_lo = b_hi + BLOCK_N * BLOCK_K * 2;
@@ -244,7 +270,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      PieceIter it(M, N, BLOCK_N);
+      PieceIter it(m_tiles, N, BLOCK_N);
       int m0, n0, n_cols;
       while (it.next(m0, n0, n_cols)) {
         int umma_n = N - n0;
@@ -306,7 +332,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     float4* stg = reinterpret_cast<float4*>(staging + (warp - 2) * 1024);
     const int rsub = lane >> 3, jj = lane & 7;
     const float relu_floor = ep.relu ? 0.f : -INFINITY;
-    PieceIter it(M, N, BLOCK_N);
+    PieceIter it(m_tiles, N, BLOCK_N);
     int m0, n0, n_cols;
     while (it.next(m0, n0, n_cols)) {
       int n_valid = N - n0;
@@ -314,12 +340,26 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int row_base = m0 + quarter * 32;
+      // output row of accumulator row (quarter, rr = 4 i + rsub), or -1 when it lies outside the problem
+      long long mrow[8];
+      if (cg.enabled) {
+        const int t = m0 / BLOCK_M, per_img = cg.tiles_x * cg.tiles_y;
+        const int cb = t / per_img, q = t - cb * per_img;
+        const int cy0 = (q / cg.tiles_x) * CONV_TH + quarter * 2, cx0 = (q % cg.tiles_x) * CONV_TW;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int y = cy0 + (i >> 2), x = cx0 + 4 * (i & 3) + rsub;
+          mrow[i] = (y < cg.H && x < cg.W) ? ((long long)cb * cg.H + y) * cg.W + x : -1;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mrow[i] = (row_base + rsub + 4 * i < M) ? (long long)(row_base + rsub + 4 * i) : -1;
+      }
       const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
       if (dbg & 32) {
       } else if (fast && ep.softmax64) {
         // Fused softmax over groups of 64 columns (tf.nn.softmax over the fragment axis, model.py:676-678): a lane owns
         // one row, so the 64 logits of a group are 2 x 32 registers and max / sum need no cross-lane traffic.
-        const int rows_left = M - row_base - rsub;
 #pragma unroll 1
         for (int c0 = 0; c0 < n_valid; c0 += 64) {
           uint32_t r0[32], r1[32];
@@ -364,12 +404,11 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
             __syncwarp();
             const int col = n0 + c0 + 32 * h + jj * 4;
-            float* df = ep.d_f32 + (long long)(row_base + rsub) * ep.ldd + col;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int rr = i * 4 + rsub;
               const float4 v = stg[rr * 8 + (jj ^ (rr & 7))];
-              if (col < N && 4 * i < rows_left) *reinterpret_cast<float4*>(df + (long long)(4 * i) * ep.ldd) = v;
+              if (col < N && mrow[i] >= 0) *reinterpret_cast<float4*>(ep.d_f32 + mrow[i] * ep.ldd + col) = v;
             }
           }
         }
@@ -380,7 +419,6 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           boundary = (g0 + 1) * ep.bias_group_rows;
         }
         const bool two_groups = boundary < row_base + 32 && boundary < M;
-        const int rows_left = M - row_base - rsub;                 // row rsub + 4 i is valid iff 4 i < rows_left
 #pragma unroll 1
         for (int c0 = 0; c0 < n_valid; c0 += 32) {
           const int col = n0 + c0 + jj * 4;
@@ -396,11 +434,10 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           float4 res[8];
           if (ep.residual && !(dbg & 4)) {
-            const float* rp = ep.residual + (long long)(row_base + rsub) * ep.ldr + col;
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              res[i] = (col_ok && 4 * i < rows_left) ? __ldg(reinterpret_cast<const float4*>(rp + (long long)(4 * i) * ep.ldr))
-                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+              res[i] = (col_ok && mrow[i] >= 0) ? __ldg(reinterpret_cast<const float4*>(ep.residual + mrow[i] * ep.ldr + col))
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
           } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -411,24 +448,24 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             stg[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                                                            __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
           __syncwarp();
-          float* df = ep.d_f32 ? ep.d_f32 + (long long)(row_base + rsub) * ep.ldd + col : nullptr;
-          uint16_t* dh = ep.d_split ? ep.d_split + (long long)(row_base + rsub) * ep.ldd_split + col : nullptr;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = i * 4 + rsub;
             float4 v = stg[rr * 8 + (jj ^ (rr & 7))];
             const float4 b = (row_base + rr >= boundary) ? b1 : b0;
-            v.x = fmaxf(v.x + b.x, relu_floor) + res[i].x;
-            v.y = fmaxf(v.y + b.y, relu_floor) + res[i].y;
-            v.z = fmaxf(v.z + b.z, relu_floor) + res[i].z;
-            v.w = fmaxf(v.w + b.w, relu_floor) + res[i].w;
-            if (col_ok && 4 * i < rows_left && !(dbg & 2)) {
-              if (df) *reinterpret_cast<float4*>(df + (long long)(4 * i) * ep.ldd) = v;
-              if (dh) {
+            // ReLU follows the residual add (ResNet bottleneck: relu(shortcut + residual), net_resnet_v1_beta.py:88);
+            // the Xception units never combine the two
+            v.x = fmaxf(v.x + b.x + res[i].x, relu_floor);
+            v.y = fmaxf(v.y + b.y + res[i].y, relu_floor);
+            v.z = fmaxf(v.z + b.z + res[i].z, relu_floor);
+            v.w = fmaxf(v.w + b.w + res[i].w, relu_floor);
+            if (col_ok && mrow[i] >= 0 && !(dbg & 2)) {
+              if (ep.d_f32) *reinterpret_cast<float4*>(ep.d_f32 + mrow[i] * ep.ldd + col) = v;
+              if (ep.d_split) {
                 uint2 hi, lo;
                 split_bf16x2(v.x, v.y, hi.x, lo.x);
                 split_bf16x2(v.z, v.w, hi.y, lo.y);
-                uint16_t* ph = dh + (long long)(4 * i) * ep.ldd_split;
+                uint16_t* ph = ep.d_split + mrow[i] * ep.ldd_split + col;
                 *reinterpret_cast<uint2*>(ph) = hi;
                 *reinterpret_cast<uint2*>(ph + ep.d_plane_stride) = lo;
               }
@@ -437,8 +474,14 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       } else {
         // Generic path (odd N or unaligned views; only the 22-channel object head takes it): lane = row, scalar stores.
-        const int m = row_base + lane;
-        const float* brow = ep.bias ? ep.bias + (ep.bias_group_rows > 0 ? (long long)(m / ep.bias_group_rows) * N : 0) : nullptr;
+        long long m = row_base + lane < M ? row_base + lane : -1;
+        if (cg.enabled) {
+          const int t = m0 / BLOCK_M, per_img = cg.tiles_x * cg.tiles_y;
+          const int cb = t / per_img, q = t - cb * per_img, r_ = quarter * 32 + lane;
+          const int y = (q / cg.tiles_x) * CONV_TH + (r_ >> 4), x = (q % cg.tiles_x) * CONV_TW + (r_ & 15);
+          m = (y < cg.H && x < cg.W) ? ((long long)cb * cg.H + y) * cg.W + x : -1;
+        }
+        const float* brow = ep.bias ? ep.bias + (ep.bias_group_rows > 0 && m >= 0 ? (m / ep.bias_group_rows) * N : 0) : nullptr;
 #pragma unroll 1
         for (int c0 = 0; c0 < n_valid; c0 += 32) {
           uint32_t r[32];
@@ -452,21 +495,21 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                                            __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
           __syncwarp();
           const int cnt = (n_valid - c0) < 32 ? (n_valid - c0) : 32;
-          if (m < M) {
+          if (m >= 0) {
             const float* srow = reinterpret_cast<const float*>(stg + lane * 8);
 #pragma unroll 1
             for (int j = 0; j < cnt; ++j) {
               const int nn = n0 + c0 + j;
               float t = srow[(((j >> 2) ^ (lane & 7)) << 2) + (j & 3)];
               if (brow) t += __ldg(brow + nn);
+              if (ep.residual) t += __ldg(ep.residual + m * ep.ldr + nn);
               t = fmaxf(t, relu_floor);
-              if (ep.residual) t += __ldg(ep.residual + (long long)m * ep.ldr + nn);
-              if (ep.d_f32) ep.d_f32[(long long)m * ep.ldd + nn] = t;
+              if (ep.d_f32) ep.d_f32[m * ep.ldd + nn] = t;
               if (ep.d_split) {
                 __nv_bfloat16 h0, l0;
                 split_bf16(t, h0, l0);
-                ep.d_split[(long long)m * ep.ldd_split + nn] = __bfloat16_as_ushort(h0);
-                ep.d_split[ep.d_plane_stride + (long long)m * ep.ldd_split + nn] = __bfloat16_as_ushort(l0);
+                ep.d_split[m * ep.ldd_split + nn] = __bfloat16_as_ushort(h0);
+                ep.d_split[ep.d_plane_stride + m * ep.ldd_split + nn] = __bfloat16_as_ushort(l0);
               }
             }
           }
@@ -513,8 +556,8 @@ static int make_map(CUtensorMap* map, const void* base, int rows, int cols, int 
 }
 
 template <int BLOCK_N, int BLOCK_K>
-static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mw64, const GemmEpilogue& ep, int M, int N, int K,
-                       cudaStream_t stream, int dbg) {
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mw64, const GemmEpilogue& ep,
+                       const ConvGeom& cg, int M, int N, int K, cudaStream_t stream, int dbg) {
   using Cfg = GemmCfg<BLOCK_N, BLOCK_K>;
   static bool attr = false;
   if (!attr) {
@@ -522,10 +565,65 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const CUten
     attr = true;
   }
   // one CTA per SM; with less than a wave of tiles the remainder logic of PieceIter spreads 64-column blocks
-  const long long blocks64 = (long long)ceil_div(M, BLOCK_M) * ceil_div(N, BLOCK_N < 64 ? BLOCK_N : 64);
+  const long long m_tiles = cg.enabled ? (long long)(M / (cg.H * cg.W)) * cg.tiles_x * cg.tiles_y : ceil_div(M, BLOCK_M);
+  const long long blocks64 = m_tiles * ceil_div(N, BLOCK_N < 64 ? BLOCK_N : 64);
   const int grid = blocks64 < num_sms() ? (int)blocks64 : num_sms();
-  pw_gemm_kernel<BLOCK_N, BLOCK_K><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mw, mw64, ep, M, N, K, dbg);
+  pw_gemm_kernel<BLOCK_N, BLOCK_K><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mw, mw64, ep, cg, M, N, K, dbg);
   EPOS_LAUNCH_CHECK();
+  return EPOS_OK;
+}
+
+// W maps, epilogue descriptor and dispatch on the N tile shared by the pointwise and the 3x3 entry points.
+// K block = 64 bf16 (128-byte swizzle, 2 smem stages at BLOCK_N = 256).  A 32-wide K block (64-byte swizzle, 4 stages)
+// was measured 4-15 % slower on B200: the main loop is bound by L2->SM throughput, not by pipeline depth.
+static int run_gemm(const CUtensorMap& ma, const uint16_t* w_split, const float* bias, int bias_group_rows,
+                    const float* residual, int ldr, float* d_f32, int ldd, uint16_t* d_split, int ldd_split,
+                    size_t d_plane_stride, const ConvGeom& cg, int M, int N, int K, int relu, cudaStream_t s) {
+  EPOS_CHECK_ARG(!d_f32 || ldd >= N);
+  EPOS_CHECK_ARG(!d_split || ldd_split >= N);
+  EPOS_CHECK_ARG(!residual || ldr >= N);
+  EPOS_CHECK_ARG(relu >= 0 && relu <= 2);
+  const int bn = N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
+  const char* de = getenv("EPOS_GEMM_DEBUG");   // developer A/B switches (scripts/dev_gemm.py); 0 in production
+  const int dbg = de ? atoi(de) : 0;
+  CUtensorMap mw, mw64;
+  int rc = make_map(&mw, w_split, N, K, K, (size_t)N * K, bn, GEMM_BK, 2);
+  if (rc) return rc;
+  rc = make_map(&mw64, w_split, N, K, K, (size_t)N * K, bn < 64 ? bn : 64, GEMM_BK, 1);
+  if (rc) return rc;
+  GemmEpilogue ep;
+  ep.bias = bias; ep.residual = residual; ep.d_f32 = d_f32; ep.d_split = d_split;
+  ep.d_plane_stride = (long long)d_plane_stride; ep.bias_group_rows = bias_group_rows;
+  ep.ldr = ldr; ep.ldd = ldd; ep.ldd_split = ldd_split; ep.relu = relu == 1; ep.softmax64 = relu == 2;
+  if (relu == 2) {
+    // fused softmax needs whole 64-column groups per piece and the aligned fast path; f32 output only
+    EPOS_CHECK_ARG(d_f32 && !d_split && !residual && bias_group_rows == 0 && (N % 64) == 0 && (ldd % 4) == 0 &&
+                   (reinterpret_cast<uintptr_t>(d_f32) & 15) == 0 && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0));
+  }
+  switch (bn) {
+    case 256: return launch_gemm<256, GEMM_BK>(ma, mw, mw64, ep, cg, M, N, K, s, dbg);
+    case 128: return launch_gemm<128, GEMM_BK>(ma, mw, mw64, ep, cg, M, N, K, s, dbg);
+    case 64: return launch_gemm<64, GEMM_BK>(ma, mw, mw64, ep, cg, M, N, K, s, dbg);
+    default: return launch_gemm<32, GEMM_BK>(ma, mw, mw64, ep, cg, M, N, K, s, dbg);
+  }
+}
+
+// split-bf16 NHWC activations [2][B][H][W][C] viewed as {C, W, H, B, plane}; box {64, 16, 8, 1, 2} = the 128-row A tile
+static int make_conv_map(CUtensorMap* map, const uint16_t* x, int B, int H, int W, int C, int ldx, size_t plane_stride) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled not available"); return EPOS_ERR_CUDA; }
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, 2};
+  cuuint64_t strides[4] = {(cuuint64_t)ldx * 2, (cuuint64_t)W * ldx * 2, (cuuint64_t)H * W * ldx * 2,
+                           (cuuint64_t)plane_stride * 2};
+  cuuint32_t box[5] = {(cuuint32_t)GEMM_BK, CONV_TW, CONV_TH, 1, 2};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<uint16_t*>(x), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (conv) failed (%d) B=%d H=%d W=%d C=%d ldx=%d", (int)r, B, H, W, C, ldx);
+    return EPOS_ERR_CUDA;
+  }
   return EPOS_OK;
 }
 
@@ -541,51 +639,29 @@ extern "C" int epos_pwconv_gemm(const uint16_t* a_split, int lda, size_t a_plane
   EPOS_CHECK_ARG(M > 0 && N > 0 && K > 0);
   EPOS_CHECK_ARG(lda >= K && (lda % 8) == 0 && (K % 8) == 0 && (a_plane_stride % 8) == 0);
   EPOS_CHECK_ARG((reinterpret_cast<uintptr_t>(a_split) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_split) & 15) == 0);
-  EPOS_CHECK_ARG(!d_f32 || ldd >= N);
-  EPOS_CHECK_ARG(!d_split || ldd_split >= N);
-  EPOS_CHECK_ARG(!residual || ldr >= N);
-  int bn = N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
-  // K block: 64 (128-byte swizzle, 2 pipeline stages at BLOCK_N = 256) or 32 (64-byte swizzle, 4 stages).  Measured on
-  // B200 (B = 8, full network): BK = 32 is 4 % slower -- the kernel is bound by L2->SM throughput, not by pipeline depth
-  // (DESIGN.md section 3), so the default stays 64.  EPOS_GEMM_BK overrides for A/B measurements.
-  static int bk_env = -1;
-  if (bk_env < 0) {
-    const char* e = getenv("EPOS_GEMM_BK");
-    bk_env = e ? atoi(e) : 0;
-    if (bk_env != 32 && bk_env != 64) bk_env = 0;
-  }
-  const int bk = bk_env ? bk_env : 64;
-  const char* de = getenv("EPOS_GEMM_DEBUG");   // developer A/B switches (scripts/dev_gemm.py); 0 in production
-  const int dbg = de ? atoi(de) : 0;
-  CUtensorMap ma, mw, mw64;
-  int rc = make_map(&ma, a_split, M, K, lda, a_plane_stride, BLOCK_M, bk, 2);
+  CUtensorMap ma;
+  int rc = make_map(&ma, a_split, M, K, lda, a_plane_stride, BLOCK_M, GEMM_BK, 2);
   if (rc) return rc;
-  rc = make_map(&mw, w_split, N, K, K, (size_t)N * K, bn, bk, 2);
+  ConvGeom cg = {};
+  return run_gemm(ma, w_split, bias, bias_group_rows, residual, ldr, d_f32, ldd, d_split, ldd_split, d_plane_stride, cg,
+                  M, N, K, relu, (cudaStream_t)stream);
+}
+
+extern "C" int epos_conv3x3_gemm(const uint16_t* x_split, int ldx, size_t x_plane_stride, const uint16_t* w_split,
+                                 const float* bias, const float* residual, int ldr, float* d_f32, int ldd,
+                                 uint16_t* d_split, int ldd_split, size_t d_plane_stride, int B, int H, int W, int C,
+                                 int N, int rate, int relu, void* stream) {
+  EPOS_CHECK_ARG(x_split && w_split && (d_f32 || d_split));
+  EPOS_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && N > 0 && rate >= 1 && relu != 2);
+  EPOS_CHECK_ARG((C % GEMM_BK) == 0 && ldx >= C && (ldx % 8) == 0 && (x_plane_stride % 8) == 0);
+  EPOS_CHECK_ARG((reinterpret_cast<uintptr_t>(x_split) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_split) & 15) == 0);
+  EPOS_CHECK_ARG((long long)B * H * W < (1LL << 31));
+  CUtensorMap ma;
+  int rc = make_conv_map(&ma, x_split, B, H, W, C, ldx, x_plane_stride);
   if (rc) return rc;
-  rc = make_map(&mw64, w_split, N, K, K, (size_t)N * K, bn < 64 ? bn : 64, bk, 1);
-  if (rc) return rc;
-  GemmEpilogue ep;
-  ep.bias = bias; ep.residual = residual; ep.d_f32 = d_f32; ep.d_split = d_split;
-  ep.d_plane_stride = (long long)d_plane_stride; ep.bias_group_rows = bias_group_rows;
-  ep.ldr = ldr; ep.ldd = ldd; ep.ldd_split = ldd_split; ep.relu = relu == 1; ep.softmax64 = relu == 2;
-  if (relu == 2) {
-    // fused softmax needs whole 64-column groups per piece and the aligned fast path; f32 output only
-    EPOS_CHECK_ARG(d_f32 && !d_split && !residual && bias_group_rows == 0 && (N % 64) == 0 && (ldd % 4) == 0 &&
-                   (reinterpret_cast<uintptr_t>(d_f32) & 15) == 0 && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0));
-  }
-  cudaStream_t s = (cudaStream_t)stream;
-  if (bk == 32) {
-    switch (bn) {
-      case 256: return launch_gemm<256, 32>(ma, mw, mw64, ep, M, N, K, s, dbg);
-      case 128: return launch_gemm<128, 32>(ma, mw, mw64, ep, M, N, K, s, dbg);
-      case 64: return launch_gemm<64, 32>(ma, mw, mw64, ep, M, N, K, s, dbg);
-      default: return launch_gemm<32, 32>(ma, mw, mw64, ep, M, N, K, s, dbg);
-    }
-  }
-  switch (bn) {
-    case 256: return launch_gemm<256, 64>(ma, mw, mw64, ep, M, N, K, s, dbg);
-    case 128: return launch_gemm<128, 64>(ma, mw, mw64, ep, M, N, K, s, dbg);
-    case 64: return launch_gemm<64, 64>(ma, mw, mw64, ep, M, N, K, s, dbg);
-    default: return launch_gemm<32, 64>(ma, mw, mw64, ep, M, N, K, s, dbg);
-  }
+  ConvGeom cg;
+  cg.enabled = 1; cg.H = H; cg.W = W; cg.tiles_x = ceil_div(W, CONV_TW); cg.tiles_y = ceil_div(H, CONV_TH);
+  cg.rate = rate; cg.cpb = C / GEMM_BK;
+  return run_gemm(ma, w_split, bias, 0, residual, ldr, d_f32, ldd, d_split, ldd_split, d_plane_stride, cg, B * H * W, N,
+                  9 * C, relu, (cudaStream_t)stream);
 }

@@ -244,7 +244,7 @@ class EposNet:
         H1, W1 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
         c1 = torch.empty((B * H1 * W1, 32), dtype=torch.float32, device=self.dev)
         _lib.check(lib.epos_conv3x3_rgb_s2(images.data_ptr(), p['conv1_1'][0].data_ptr(), p['conv1_1'][1].data_ptr(),
-                                           c1.data_ptr(), B, H, W, 32, self._s()), 'epos_conv3x3_rgb_s2')
+                                           c1.data_ptr(), None, B, H, W, 32, self._s()), 'epos_conv3x3_rgb_s2')
         c2 = torch.empty((B * H1 * W1, 64), dtype=torch.float32, device=self.dev)
         _lib.check(lib.epos_conv3x3_dense(c1.data_ptr(), p['conv1_2'][0].data_ptr(), p['conv1_2'][1].data_ptr(),
                                           c2.data_ptr(), B, H1, W1, 32, 64, self._s()), 'epos_conv3x3_dense')

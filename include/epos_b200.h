@@ -40,11 +40,24 @@ uint64_t epos_launch_count(void);
 
 /* ---- CNN ops: replace the TF ops built by model.predict (epos_lib/model.py:629-687) ---------------- */
 
-/* entry_flow/conv1_1: (2/255)x-1 preprocessing (feature.py:171-174) + 3x3 stride-2 conv with explicit
- * padding (resnet_utils.conv2d_same, external/slim/nets/resnet_utils.py:77-122) + folded BN + ReLU.
- * x [B,H,W,3] f32 in [0,255]; w [3][3][3][Cout] (HWIO, BN scale folded); y [B,H/2,W/2,Cout] f32. */
-int epos_conv3x3_rgb_s2(const float* x, const float* w, const float* bias, float* y,
+/* entry_flow/conv1_1 (Xception, Cout = 32) and conv1_1 of the ResNet beta root (Cout = 64,
+ * net_resnet_v1_beta.py:108): (2/255)x-1 preprocessing (feature.py:171-174) + 3x3 stride-2 conv with
+ * explicit padding (resnet_utils.conv2d_same, external/slim/nets/resnet_utils.py:77-122) + folded BN +
+ * ReLU.  x [B,H,W,3] f32 in [0,255]; w [3][3][3][Cout] (HWIO, BN scale folded); outputs
+ * y [B,H/2,W/2,Cout] f32 and/or y_split [2][B*H/2*W/2][Cout] bf16 (either may be NULL). */
+int epos_conv3x3_rgb_s2(const float* x, const float* w, const float* bias, float* y, uint16_t* y_split,
                         int B, int H, int W, int Cout, void* stream);
+
+/* slim.max_pool2d(3, stride 2, padding='SAME') of the ResNet root (net_resnet_v1_beta.py:187).
+ * x [B,H,W,C] f32 -> y_f32 [B,ceil(H/2),ceil(W/2),C] and/or y_split (split-bf16 planes). */
+int epos_maxpool3x3_s2(const float* x, float* y_f32, uint16_t* y_split, int B, int H, int W, int C,
+                       void* stream);
+
+/* resnet_utils.subsample (external/slim/nets/resnet_utils.py:59-74): every factor-th pixel of
+ * x [B,H,W,ldx] (first C channels) -> y [B,ceil(H/f),ceil(W/f),C] f32 (identity shortcut of a strided
+ * bottleneck unit, net_resnet_v1_beta.py:69-70). */
+int epos_subsample_f32(const float* x, int ldx, float* y, int B, int H, int W, int C, int factor,
+                       void* stream);
 
 /* Dense 3x3 stride-1 SAME conv + folded BN + ReLU (entry_flow/conv1_2).  w [3][3][Cin][Cout]. */
 int epos_conv3x3_dense(const float* x, const float* w, const float* bias, float* y,
@@ -68,7 +81,8 @@ int epos_dwconv3x3(const float* x, int ldx, const float* w, const float* bias,
  * a_split [2][M][lda] bf16; w_split [2][N][K] bf16; bias [groups][N] f32 (bias_group_rows = 0: one row);
  * residual f32 with leading dim ldr or NULL; outputs: d_f32 (leading dim ldd) and/or d_split
  * ([2][M][ldd_split], plane stride = split_plane_stride elements), either may be NULL.
- * relu: 0 = identity, 1 = ReLU, 2 = softmax over aligned groups of 64 output columns fused into the
+ * relu: 0 = identity, 1 = ReLU (after the residual add, as the ResNet bottleneck needs,
+ * net_resnet_v1_beta.py:88; the Xception units never combine the two), 2 = softmax over aligned groups of 64 output columns fused into the
  * epilogue (tf.nn.softmax over the fragment axis, model.py:676-678; needs N % 64 == 0, f32 output only,
  * no residual). */
 int epos_pwconv_gemm(const uint16_t* a_split, int lda, size_t a_plane_stride,
@@ -77,6 +91,19 @@ int epos_pwconv_gemm(const uint16_t* a_split, int lda, size_t a_plane_stride,
                      float* d_f32, int ldd,
                      uint16_t* d_split, int ldd_split, size_t d_plane_stride,
                      int M, int N, int K, int relu, void* stream);
+
+/* Dense 3x3 (atrous) stride-1 'SAME' convolution + folded BN (+ residual) (+ReLU) as an implicit GEMM on
+ * the same tcgen05 kernel: K = 9 taps x C, the A tile of tap (ky,kx) is an 8x16 pixel block shifted by
+ * ((ky-1) rate, (kx-1) rate) fetched with a 5-D TMA box (zero fill outside the image = TF SAME padding).
+ * Replaces resnet_utils.conv2d_same (external/slim/nets/resnet_utils.py:77-122) at stride 1 as used by
+ * net_resnet_v1_beta.py:85,108-110; a stride-2 conv2d_same equals this followed by subsampling
+ * (resnet_v1_test.py:72-149).  x_split [2][B,H,W,ldx] bf16 (C % 64 == 0);
+ * w_split [2][N][9*C] bf16 with k = (ky*3+kx)*C + c; outputs and residual are indexed by the output
+ * pixel (b*H + y)*W + x as in epos_pwconv_gemm.  relu: 0 / 1 (applied after the residual add). */
+int epos_conv3x3_gemm(const uint16_t* x_split, int ldx, size_t x_plane_stride, const uint16_t* w_split,
+                      const float* bias, const float* residual, int ldr, float* d_f32, int ldd,
+                      uint16_t* d_split, int ldd_split, size_t d_plane_stride,
+                      int B, int H, int W, int C, int N, int rate, int relu, void* stream);
 
 /* Same contract computed by an fp32 SIMT kernel from f32 operands (validation / tiny shapes):
  * a [M][lda] f32, w [N][K] f32. */

@@ -38,10 +38,10 @@ def test_pw_gemm(env, M, N, K, mode):
     res = torch.randn(M, N, generator=g).to(dev) if mode == 'relu_res' else None
     relu = mode != 'plain'
     ref = a.double() @ w.double().T + bias.double()
-    if relu:
-        ref = ref.clamp_min(0)
     if res is not None:
         ref = ref + res.double()
+    if relu:
+        ref = ref.clamp_min(0)                       # ReLU follows the residual add (net_resnet_v1_beta.py:88)
     a_s, w_s = split(a), split(w)
     d = torch.full((M, N), float('nan'), device=dev) if mode != 'split_out' else None
     ds = torch.zeros((2, M, N), dtype=torch.bfloat16, device=dev) if mode == 'split_out' else None
@@ -153,6 +153,64 @@ def test_dwconv(env, C, H, W, stride, rate, relu_in, relu_out):
     assert rel_err((ys[0].float() + ys[1].float()).cpu().numpy().reshape(ref.shape), ref) < 3e-5
 
 
+@pytest.mark.parametrize('B,H,W,C,N,rate,mode', [
+    (2, 16, 32, 64, 64, 1, 'relu'), (1, 15, 20, 128, 128, 2, 'relu'), (2, 17, 19, 64, 40, 1, 'plain'),
+    (1, 30, 40, 256, 256, 4, 'res'), (1, 12, 16, 512, 512, 8, 'relu'), (3, 8, 16, 64, 128, 1, 'split')])
+def test_conv3x3_gemm(env, B, H, W, C, N, rate, mode):
+    """Implicit-GEMM 3x3 atrous conv (TMA-shifted taps) against F.conv2d with TF SAME padding."""
+    from epos_b200 import _lib
+    from oracle import cnn
+    lib, dev = env
+    rng = np.random.default_rng(H * W + C + N + rate)
+    x = rng.standard_normal((B, H, W, C)).astype(np.float32)
+    k = (rng.standard_normal((3, 3, C, N)) * 0.05).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    res = rng.standard_normal((B, H, W, N)).astype(np.float32) if mode == 'res' else None
+    o = cnn.Oracle({'s/weights': k}, dtype=torch.float64)
+    y = o.conv(torch.from_numpy(x).double().permute(0, 3, 1, 2), 's', 1, rate, 'SAME').permute(0, 2, 3, 1)
+    y = y + torch.from_numpy(bias).double()
+    if res is not None:
+        y = y + torch.from_numpy(res).double()
+    if mode != 'plain':
+        y = y.clamp_min(0)
+    ref = y.numpy().reshape(B * H * W, N)
+    xs = split(torch.from_numpy(x).to(dev).view(B * H * W, C))
+    ws = split(torch.from_numpy(k.reshape(9 * C, N).T.copy()).to(dev))          # [N][9C], k = (ky*3+kx)*C + c
+    bd = torch.from_numpy(bias).to(dev)
+    rd = torch.from_numpy(res).to(dev).view(B * H * W, N) if res is not None else None
+    d = torch.full((B * H * W, N), float('nan'), device=dev) if mode != 'split' else None
+    ds = torch.zeros((2, B * H * W, N), dtype=torch.bfloat16, device=dev) if mode == 'split' else None
+    rc = lib.epos_conv3x3_gemm(xs.data_ptr(), C, xs.stride(0), ws.data_ptr(), bd.data_ptr(), _lib.ptr(rd), N,
+                               _lib.ptr(d), N, _lib.ptr(ds), N, 0 if ds is None else ds.stride(0), B, H, W, C, N, rate,
+                               int(mode != 'plain'), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, 'conv3x3_gemm')
+    torch.cuda.synchronize()
+    got = d if d is not None else ds[0].float() + ds[1].float()
+    assert rel_err(got.cpu().numpy(), ref) < (2e-5 if d is not None else 5e-5)
+
+
+@pytest.mark.parametrize('H,W', [(16, 24), (15, 21), (9, 8)])
+def test_maxpool_and_subsample(env, H, W):
+    from epos_b200 import _lib
+    lib, dev = env
+    B, C = 2, 72
+    x = torch.randn(B, H, W, C, device=dev)
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    ph, pw = max((Ho - 1) * 2 + 3 - H, 0), max((Wo - 1) * 2 + 3 - W, 0)
+    xp = torch.nn.functional.pad(x.permute(0, 3, 1, 2), (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2), value=float('-inf'))
+    ref = torch.nn.functional.max_pool2d(xp, 3, 2).permute(0, 2, 3, 1)
+    y = torch.empty(B, Ho, Wo, C, device=dev)
+    ys = torch.empty(2, B * Ho * Wo, C, dtype=torch.bfloat16, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.epos_maxpool3x3_s2(x.data_ptr(), y.data_ptr(), ys.data_ptr(), B, H, W, C, s), 'maxpool')
+    z = torch.empty(B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C, device=dev)
+    _lib.check(lib.epos_subsample_f32(x.data_ptr(), C, z.data_ptr(), B, H, W, C, 2, s), 'subsample')
+    torch.cuda.synchronize()
+    assert torch.equal(y, ref)
+    assert rel_err((ys[0].float() + ys[1].float()).view(B, Ho, Wo, C).cpu().numpy(), ref.cpu().numpy()) < 3e-5
+    assert torch.equal(z, x[:, ::2, ::2])
+
+
 def test_entry_convs(env):
     from epos_b200 import _lib, weights as W
     from oracle import cnn
@@ -175,7 +233,7 @@ def test_entry_convs(env):
     c1 = torch.empty((2, 32, 48, 32), device=dev)
     c2 = torch.empty((2, 32, 48, 64), device=dev)
     s = torch.cuda.current_stream().cuda_stream
-    _lib.check(lib.epos_conv3x3_rgb_s2(xd.data_ptr(), k1.data_ptr(), b1.data_ptr(), c1.data_ptr(), 2, 64, 96, 32, s), 'c1')
+    _lib.check(lib.epos_conv3x3_rgb_s2(xd.data_ptr(), k1.data_ptr(), b1.data_ptr(), c1.data_ptr(), None, 2, 64, 96, 32, s), 'c1')
     _lib.check(lib.epos_conv3x3_dense(c1.data_ptr(), k2.data_ptr(), b2.data_ptr(), c2.data_ptr(), 2, 32, 48, 32, 64, s), 'c2')
     torch.cuda.synchronize()
     assert rel_err(c1.cpu().numpy(), r1.permute(0, 2, 3, 1).numpy()) < 1e-5
