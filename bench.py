@@ -29,13 +29,21 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 H, W = 480, 640
-TRUNK_FLOP = 401.97e9          # Xception-65 trunk + ASPP + decoder, per image
+TRUNK_FLOP = {'xception_65': 401.97e9,          # trunk + ASPP + decoder, per image
+              'resnet_v1_50_beta': 277.70e9}
 # Random-init logit weights (reference: truncated_normal(0.01), model.py:437) give uniform heads -> obj_conf = 1/22 < tau_a
 # -> ZERO correspondences.  The full workload therefore scales the logit initialiser so that the
 # random features produce a varied, mostly no-consensus correspondence load (0 .. >30k rows per object, top-K 4096):
 # every object runs all 400 RANSAC iterations and its graph-cut budget, i.e. the expensive case for pose fitting.
 HEAD_STD_FULL = 300.0
 MAX_CORR = 4096
+
+
+def head_std(kind, backbone):
+    """Logit initialiser stddev of the full workload (None = the reference's 0.01 for CNN-only runs)."""
+    if kind != 'full':
+        return None
+    return HEAD_STD_FULL
 
 
 def head_flop(O, F):
@@ -52,6 +60,9 @@ def parse_args():
     ap.add_argument('--batch', type=int, default=8, help='images per GPU per step')
     ap.add_argument('--objs', type=int, default=21)
     ap.add_argument('--frags', type=int, default=64)
+    ap.add_argument('--backbone', default='xception_65', choices=['xception_65', 'resnet_v1_50_beta'],
+                    help='model_variant (BASELINE configs[3] uses resnet_v1_50_beta)')
+    ap.add_argument('--max-iters', type=int, default=400, help='RANSAC iteration budget (configs[4]: 2000)')
     ap.add_argument('--cpu-images', type=int, default=3, help='images in the cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
@@ -65,7 +76,11 @@ def default_workload():
         return 'cnn'
 
 
-def workload_name(kind, B, O, F):
+def workload_name(kind, B, O, F, backbone='xception_65'):
+    if backbone != 'xception_65':
+        return ('BASELINE configs[3]-shaped: batch=%d/GPU 640x480 synthetic RGB, random-init %s backbone, %d-object / '
+                '%d-fragment heads, %s' % (B, backbone, O, F, 'CNN-only forward' if kind == 'cnn' else
+                                           'full CNN + corresp + GC-RANSAC pose fitting'))
     if kind == 'cnn':
         return ('BASELINE configs[1]: batch=%d/GPU 640x480 synthetic RGB, random-init Xception-65 f64 '
                 '(%d objects x %d fragments heads), CNN-only forward (model.predict)' % (B, O, F))
@@ -128,7 +143,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 # CPU restatement of the reference path (oracle): cpu_baseline leg and --impl reference
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference_run(kind, O, F, n_images, threads, seed=0):
+def cpu_reference_run(kind, O, F, n_images, threads, seed=0, backbone='xception_65'):
     """Times the oracle on `n_images` images, one at a time like scripts/infer.py (batch 1); the first image is
     dropped as warm-up like infer.py:741-749.  Returns (images_per_s, per-stage seconds)."""
     import numpy as np
@@ -136,8 +151,8 @@ def cpu_reference_run(kind, O, F, n_images, threads, seed=0):
     from epos_b200 import weights as Wt
     from oracle import cnn as ocnn
     torch.set_num_threads(threads)
-    w = Wt.random_init(O, F, seed=seed, logits_std=HEAD_STD_FULL if kind == 'full' else None)
-    net = ocnn.Oracle(w)
+    w = Wt.random_init(O, F, seed=seed, logits_std=head_std(kind, backbone), model_variant=backbone)
+    net = ocnn.Oracle(w, model_variant=backbone)
     fit = None
     if kind == 'full':
         from oracle import pipeline as opipe
@@ -173,12 +188,12 @@ def run_reference(args, kind):
     threads = min(10, cores)            # scripts/infer.py:695-698 pins TF to 10 intra/inter-op threads
     n = max(1, args.steps)
     # warm-up images are untimed; each "step" of the reference is ONE image (infer.py is batch 1).
-    ips, stages = cpu_reference_run(kind, args.objs, args.frags, n, threads)
+    ips, stages = cpu_reference_run(kind, args.objs, args.frags, n, threads, backbone=args.backbone)
     line = {
         'impl': 'reference', 'metric': 'images/sec (640x480, Xception-65 f64 + PnP-RANSAC)', 'value': ips,
         'unit': 'images/s', 'n_gpus': args.gpus, 'steps': n, 'warmup': 1, 'ms_per_step': 1e3 / ips,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_name(kind, args.batch, args.objs, args.frags),
+        'config': {'workload': workload_name(kind, args.batch, args.objs, args.frags, args.backbone),
                    'note': 'reference CPU path = oracle port (TF-1.12/OpenCV-3.4/Eigen not installable); '
                            'batch 1 per step as in scripts/infer.py:610'},
         'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
@@ -213,15 +228,24 @@ def run_ours(args, kind):
 
     # weights: generated on rank 0 and broadcast once over NCCL
     from epos_b200 import dist as edist
-    w = edist.broadcast_weights(Wt.random_init(O, F, seed=0, logits_std=HEAD_STD_FULL if kind == 'full' else None)
-                                if rank == 0 else None, O, F, dev, world, rank)
+    w = edist.broadcast_weights(Wt.random_init(O, F, seed=0, logits_std=head_std(kind, args.backbone),
+                                               model_variant=args.backbone)
+                                if rank == 0 else None, O, F, dev, world, rank, model_variant=args.backbone)
     store = K = None
     if kind == 'full':
         from epos_b200 import synthetic
         store = synthetic.model_store(O, F)
         K = synthetic.default_K()
+    from epos_b200 import model as emodel
+    opts = emodel.ModelOptions(Wt.head_channels(O, F), model_variant=args.backbone)
+    fit_params = None
+    if kind == 'full' and args.max_iters != 400:
+        from epos_b200 import posefit
+        fit_params = posefit.default_params()
+        fit_params.max_iters = args.max_iters
     eng = engine.Engine(w, O, F, dev, stages=engine.STAGES_FULL if kind == 'full' else engine.STAGES_CNN,
-                        model_store=store, K=K, seed=1234 + rank, max_correspondences=MAX_CORR)
+                        model_store=store, K=K, seed=1234 + rank, max_correspondences=MAX_CORR, model_options=opts,
+                        fit_params=fit_params)
 
     # inputs: NROT distinct batches (> L2 in total) rotated between steps, both pinned-host and device copies
     NROT = 5
@@ -313,23 +337,24 @@ def run_ours(args, kind):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         threads = min(10, cores)
-        ips, stages = cpu_reference_run(kind, O, F, args.cpu_images, threads)
+        ips, stages = cpu_reference_run(kind, O, F, args.cpu_images, threads, backbone=args.backbone)
         cpu = {'value': ips, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
                'sample': '%d images of the same workload, batch 1 as scripts/infer.py, +1 warm-up image dropped; s/img %s'
                          % (args.cpu_images, json.dumps({k: round(v, 4) for k, v in stages.items()}))}
 
     if rank == 0:
-        flop_img = TRUNK_FLOP + head_flop(O, F)
+        flop_img = TRUNK_FLOP[args.backbone] + head_flop(O, F)
         line = {
             'metric': 'images/sec (640x480, Xception-65 f64 + PnP-RANSAC)', 'value': value, 'unit': 'images/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (split-bf16 x3 MMA, f32 accumulate; pose f64)',
             'data': 'synthetic',
-            'config': {'workload': workload_name(kind, B, O, F), 'images_per_gpu_per_step': B, 'global_batch': B * world,
+            'config': {'workload': workload_name(kind, B, O, F, args.backbone), 'images_per_gpu_per_step': B, 'global_batch': B * world,
                        'l2': 'inputs rotate over %d distinct batches (%.0f MB) and per-layer activations (>=112 MB at B=8) '
                              'exceed the 126 MB L2' % (NROT, NROT * host_batches[0].numel() * 4 / 1e6),
                        'algorithmic_gflop_per_image': flop_img / 1e9,
-                       'heads': 'random-init; logit initialiser stddev %s' % (HEAD_STD_FULL if kind == 'full' else 0.01),
+                       'heads': 'random-init; logit initialiser stddev %s' % (head_std(kind, args.backbone) or 0.01),
+                       'ransac_max_iters': args.max_iters if kind == 'full' else None,
                        'max_correspondences': MAX_CORR if kind == 'full' else None,
                        'parallelism': 'image-sharded dp%d' % world},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu,

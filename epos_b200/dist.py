@@ -16,10 +16,10 @@ def shard_range(n_items, world, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def pack_weights(weights, num_objs, num_frags):
+def pack_weights(weights, num_objs, num_frags, model_variant='xception_65'):
     """dict -> one contiguous f32 vector in variable_specs order (BN scopes expand to their 4 vectors)."""
     parts = []
-    for name, shape, init, _ in W.variable_specs(num_objs, num_frags):
+    for name, shape, init, _ in W.variable_specs(num_objs, num_frags, model_variant):
         if init == 'bn':
             for k in W.BN_KEYS:
                 parts.append(np.asarray(weights['%s/%s' % (name, k)], np.float32).ravel())
@@ -30,9 +30,9 @@ def pack_weights(weights, num_objs, num_frags):
     return np.concatenate(parts)
 
 
-def unpack_weights(blob, num_objs, num_frags):
+def unpack_weights(blob, num_objs, num_frags, model_variant='xception_65'):
     out, off = {}, 0
-    for name, shape, init, _ in W.variable_specs(num_objs, num_frags):
+    for name, shape, init, _ in W.variable_specs(num_objs, num_frags, model_variant):
         if init == 'bn':
             for k in W.BN_KEYS:
                 out['%s/%s' % (name, k)] = blob[off:off + shape[0]]
@@ -45,24 +45,24 @@ def unpack_weights(blob, num_objs, num_frags):
     return out
 
 
-def blob_size(num_objs, num_frags):
+def blob_size(num_objs, num_frags, model_variant='xception_65'):
     n = 0
-    for _, shape, init, _ in W.variable_specs(num_objs, num_frags):
+    for _, shape, init, _ in W.variable_specs(num_objs, num_frags, model_variant):
         n += 4 * shape[0] if init == 'bn' else int(np.prod(shape))
     return n
 
 
-def broadcast_weights(weights, num_objs, num_frags, device, world, rank, src=0):
+def broadcast_weights(weights, num_objs, num_frags, device, world, rank, src=0, model_variant='xception_65'):
     """Rank `src` holds `weights`; every rank returns the same dict.  One collective."""
     if world == 1:
         return weights
-    n = blob_size(num_objs, num_frags)
+    n = blob_size(num_objs, num_frags, model_variant)
     if rank == src:
-        t = torch.from_numpy(pack_weights(weights, num_objs, num_frags)).to(device)
+        t = torch.from_numpy(pack_weights(weights, num_objs, num_frags, model_variant)).to(device)
     else:
         t = torch.empty(n, dtype=torch.float32, device=device)
     dist.broadcast(t, src=src)
-    return unpack_weights(t.cpu().numpy(), num_objs, num_frags)
+    return unpack_weights(t.cpu().numpy(), num_objs, num_frags, model_variant)
 
 
 def all_gather_poses(poses, world):

@@ -15,9 +15,10 @@ STAGES_FULL = 'cnn+corresp+fit'
 
 class Engine:
     def __init__(self, weights, num_objs, num_frags, device, stages=STAGES_CNN, model_store=None, K=None,
-                 fit_params=None, max_correspondences=4096, seed=0, min_obj_conf=0.1, min_frag_rel_conf=0.5):
+                 fit_params=None, max_correspondences=4096, seed=0, min_obj_conf=0.1, min_frag_rel_conf=0.5,
+                 model_options=None):
         self.dev = torch.device(device)
-        self.net = model.EposNet(weights, num_objs, num_frags, self.dev)
+        self.net = model.EposNet(weights, num_objs, num_frags, self.dev, model_options=model_options)
         self.O, self.F = num_objs, num_frags
         self.stages = stages
         self.model_store = model_store

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .weights import XC, XCEPTION65_BLOCKS, head_channels
+from .weights import RESNET50_BLOCKS, RN, XC, XCEPTION65_BLOCKS, head_channels
 
 PRED_OBJ_CONF = 'pred_obj_conf'        # common.py:24-27
 PRED_OBJ_LABEL = 'pred_obj_label'
@@ -28,6 +28,8 @@ PRED_FRAG_LOC = 'pred_frag_loc'
 
 EPS_BACKBONE = 1e-3                    # feature.py:304
 EPS_HEAD = 1e-5                        # model.py:197,310
+EPS_RESNET = 1e-5                      # feature.py:277-281
+RESNET_END_POINT = 'block1/unit_2/bottleneck_v1/conv3'   # feature.py:40-44
 DECODER_END_POINT = 'entry_flow/block2/unit_1/xception_module/separable_conv2_pointwise'  # feature.py:61-66
 
 _BLOCK_STRIDES = {'entry_flow/block1': 2, 'entry_flow/block2': 2, 'entry_flow/block3': 2,
@@ -37,14 +39,15 @@ _RELU_INSIDE = {'exit_flow/block2'}    # activation_fn_in_separable_conv=True, n
 
 class ModelOptions(collections.namedtuple('ModelOptions', [
         'outputs_to_num_channels', 'crop_size', 'atrous_rates', 'encoder_output_stride',
-        'decoder_output_stride', 'model_variant'])):
+        'decoder_output_stride', 'model_variant', 'multi_grid'])):
     """Subset of common.ModelOptions (common.py:206-290) that the inference path reads."""
     __slots__ = ()
 
     def __new__(cls, outputs_to_num_channels, crop_size=(640, 480), atrous_rates=(12, 24, 36),
-                encoder_output_stride=8, decoder_output_stride=(4,), model_variant='xception_65'):
+                encoder_output_stride=8, decoder_output_stride=(4,), model_variant='xception_65', multi_grid=None):
         return super().__new__(cls, outputs_to_num_channels, tuple(crop_size), tuple(atrous_rates),
-                               encoder_output_stride, tuple(decoder_output_stride), model_variant)
+                               encoder_output_stride, tuple(decoder_output_stride), model_variant,
+                               tuple(multi_grid) if multi_grid else None)
 
 
 def scale_dimension(dim, scale):
@@ -83,8 +86,9 @@ class EposNet:
         self.dev = torch.device(device)
         self.O, self.F = num_objs, num_frags
         self.opts = model_options or ModelOptions(head_channels(num_objs, num_frags))
-        if self.opts.model_variant != 'xception_65' or self.opts.encoder_output_stride != 8:
-            raise NotImplementedError('only xception_65 at output stride 8 is built')
+        if self.opts.model_variant not in ('xception_65', 'resnet_v1_50_beta') or self.opts.encoder_output_stride != 8:
+            raise NotImplementedError('only xception_65 and resnet_v1_50_beta at output stride 8 are built')
+        self.variant = self.opts.model_variant
         self.keep_f32 = keep_f32
         self.impl = 'tcgen05'            # 'simt' = fp32 validation path (needs keep_f32=True)
         self.end_points = {}
@@ -109,8 +113,37 @@ class EposNet:
         scale, shift = _bn_fold(w, scope, eps)
         return self._dev((k * scale[None, None, :]).reshape(9, -1)), self._dev(shift)
 
+    def _conv3(self, w, scope, eps):
+        """3x3 conv + BN as an implicit-GEMM weight matrix [Cout, 9*Cin] with k = (ky*3+kx)*Cin + c."""
+        k, shift = self._conv_bn(w, scope, eps)                                    # [3,3,Cin,Cout]
+        return Gemm(k.reshape(-1, k.shape[3]).T, shift, self.dev, False)
+
+    def _prepare_resnet(self, w, p):
+        k, b = self._conv_bn(w, RN + '/conv1_1', EPS_RESNET)
+        p['conv1_1'] = (self._dev(k), self._dev(b))
+        p['conv1_2'] = self._conv3(w, RN + '/conv1_2', EPS_RESNET)
+        p['conv1_3'] = self._conv3(w, RN + '/conv1_3', EPS_RESNET)
+        cin = 128
+        for scope, base_depth, units, _ in RESNET50_BLOCKS:
+            for u in range(1, units + 1):
+                base = '%s/%s/unit_%d/bottleneck_v1' % (RN, scope, u)
+                if cin != base_depth * 4:
+                    p[base + '/shortcut'] = self._pw(w, base + '/shortcut', EPS_RESNET)
+                p[base + '/conv1'] = self._pw(w, base + '/conv1', EPS_RESNET)
+                p[base + '/conv2'] = self._conv3(w, base + '/conv2', EPS_RESNET)
+                p[base + '/conv3'] = self._pw(w, base + '/conv3', EPS_RESNET)
+                cin = base_depth * 4
+
     def _prepare(self, w):
         p = {}
+        if self.variant == 'resnet_v1_50_beta':
+            self._prepare_resnet(w, p)
+        else:
+            self._prepare_xception(w, p)
+        self._prepare_heads(w, p)
+        self.p = p
+
+    def _prepare_xception(self, w, p):
         k, b = self._conv_bn(w, XC + '/entry_flow/conv1_1', EPS_BACKBONE)
         p['conv1_1'] = (self._dev(k), self._dev(b))
         k, b = self._conv_bn(w, XC + '/entry_flow/conv1_2', EPS_BACKBONE)
@@ -123,6 +156,8 @@ class EposNet:
                     p['%s/pw%d' % (base, i)] = self._pw(w, '%s/separable_conv%d_pointwise' % (base, i + 1), EPS_BACKBONE)
                 if skip == 'conv':
                     p[base + '/shortcut'] = self._pw(w, base + '/shortcut', EPS_BACKBONE)
+
+    def _prepare_heads(self, w, p):
         p['image_pooling'] = self._pw(w, 'image_pooling', EPS_HEAD, keep_f32=True)   # M = batch: fp32 SIMT kernel
         p['aspp0'] = self._pw(w, 'aspp0', EPS_HEAD)
         for i in (1, 2, 3):
@@ -140,7 +175,6 @@ class EposNet:
         for name in (PRED_OBJ_CONF, PRED_FRAG_CONF, PRED_FRAG_LOC):
             k = np.asarray(w['logits/%s/weights' % name], np.float64)[0, 0].T
             p['logits/' + name] = Gemm(k, w['logits/%s/biases' % name], self.dev, self.keep_f32)
-        self.p = p
 
     # -- op wrappers ----------------------------------------------------------------------------------
     def _s(self):
@@ -206,6 +240,90 @@ class EposNet:
             self.gemm_events.append((ev[0], ev[1], M, N, K))
         return d_f32, d_split
 
+    def conv3x3(self, x_split, g, B, H, W, C, rate, relu=True, out_f32=False, out_split=True):
+        """x_split [2,B*H*W,C] bf16 -> 3x3 atrous conv + BN (+ReLU) as an implicit tcgen05 GEMM."""
+        M, N = B * H * W, g.N
+        d = torch.empty((M, N), dtype=torch.float32, device=self.dev) if out_f32 else None
+        ds = torch.empty((2, M, N), dtype=torch.bfloat16, device=self.dev) if out_split else None
+        ev = None
+        if self.gemm_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        _lib.check(self.lib.epos_conv3x3_gemm(
+            x_split.data_ptr(), x_split.shape[2], x_split.stride(0), g.w_split.data_ptr(), _lib.ptr(g.bias), None, 0,
+            _lib.ptr(d), N, _lib.ptr(ds), N, 0 if ds is None else ds.stride(0), B, H, W, C, N, rate, int(relu),
+            self._s()), 'epos_conv3x3_gemm')
+        if ev is not None:
+            ev[1].record()
+            self.gemm_events.append((ev[0], ev[1], M, N, 9 * C))
+        return d, ds
+
+    def bottleneck(self, x32, xs, B, H, W, cin, base, depth, depth_bottleneck, stride, rate, want_conv3=False):
+        """net_resnet_v1_beta.py:38-93.  x32 f32 [M,cin] (None when only the split form exists), xs split-bf16.
+        Returns (out f32, out split, Ho, Wo)."""
+        p = self.p
+        M = B * H * W
+        Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+        Mo = B * Ho * Wo
+        if depth == cin:
+            if stride == 1:
+                shortcut = x32
+            else:                                                 # resnet_utils.subsample
+                shortcut = torch.empty((Mo, cin), dtype=torch.float32, device=self.dev)
+                _lib.check(self.lib.epos_subsample_f32(x32.data_ptr(), cin, shortcut.data_ptr(), B, H, W, cin, stride,
+                                                       self._s()), 'epos_subsample_f32')
+        else:
+            xsc = xs if stride == 1 else self.split(x32, B, H, W, cin, cin, subsample=stride)
+            shortcut, _ = self.gemm(xsc, p[base + '/shortcut'], Mo, relu=False)
+        _, r1 = self.gemm(xs, p[base + '/conv1'], M, relu=True, out_f32=False, out_split=True)
+        if stride == 1:
+            _, r2 = self.conv3x3(r1, p[base + '/conv2'], B, H, W, depth_bottleneck, rate)
+        else:
+            # conv2d_same(stride 2) == the stride-1 SAME conv sampled at even pixels (resnet_v1_test.py:72-149)
+            full, _ = self.conv3x3(r1, p[base + '/conv2'], B, H, W, depth_bottleneck, rate, out_f32=True, out_split=False)
+            r2 = self.split(full, B, H, W, depth_bottleneck, depth_bottleneck, subsample=stride)
+        if want_conv3:                                            # end point = conv3 + BN before the residual add
+            c3, _ = self.gemm(r2, p[base + '/conv3'], Mo, relu=False)
+            self.end_points[base.replace(RN + '/', '') + '/conv3'] = (c3, Ho, Wo, depth)
+        out, outs = self.gemm(r2, p[base + '/conv3'], Mo, relu=True, residual=shortcut, out_f32=True, out_split=True)
+        return out, outs, Ho, Wo
+
+    def resnet_features(self, images):
+        """resnet_v1_50_beta at output stride 8 (net_resnet_v1_beta.py:302-373; resnet_utils.py:125-217)."""
+        lib, p = self.lib, self.p
+        B, H, W, _ = images.shape
+        H1, W1 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        c1 = torch.empty((2, B * H1 * W1, 64), dtype=torch.bfloat16, device=self.dev)
+        _lib.check(lib.epos_conv3x3_rgb_s2(images.data_ptr(), p['conv1_1'][0].data_ptr(), p['conv1_1'][1].data_ptr(),
+                                           None, c1.data_ptr(), B, H, W, 64, self._s()), 'epos_conv3x3_rgb_s2')
+        _, c2 = self.conv3x3(c1, p['conv1_2'], B, H1, W1, 64, 1)
+        c3, _ = self.conv3x3(c2, p['conv1_3'], B, H1, W1, 64, 1, out_f32=True, out_split=False)
+        h, w = (H1 + 1) // 2, (W1 + 1) // 2
+        x32 = torch.empty((B * h * w, 128), dtype=torch.float32, device=self.dev)
+        xs = torch.empty((2, B * h * w, 128), dtype=torch.bfloat16, device=self.dev)
+        _lib.check(lib.epos_maxpool3x3_s2(c3.data_ptr(), x32.data_ptr(), xs.data_ptr(), B, H1, W1, 128, self._s()),
+                   'epos_maxpool3x3_s2')
+        cin = 128
+        target = self.opts.encoder_output_stride // 4              # net_resnet_v1_beta.py:183-185
+        current_stride, rate = 1, 1
+        mg = self.opts.multi_grid or (1, 1, 1)
+        for scope, base_depth, units, last_stride in RESNET50_BLOCKS:
+            for u in range(1, units + 1):
+                base = '%s/%s/unit_%d/bottleneck_v1' % (RN, scope, u)
+                stride = last_stride if u == units else 1
+                unit_rate = mg[u - 1] if scope == 'block4' else 1
+                want = base.endswith(RESNET_END_POINT.rsplit('/', 1)[0])
+                if current_stride == target:                       # resnet_utils.py:191-197
+                    x32, xs, h, w = self.bottleneck(x32, xs, B, h, w, cin, base, base_depth * 4, base_depth, 1,
+                                                    rate * unit_rate, want)
+                    rate *= stride
+                else:
+                    x32, xs, h, w = self.bottleneck(x32, xs, B, h, w, cin, base, base_depth * 4, base_depth, stride,
+                                                    unit_rate, want)
+                    current_stride *= stride
+                cin = base_depth * 4
+        return x32, xs, h, w, cin
+
     def small_fc(self, a, w_f32, bias, relu):
         M, K = a.shape
         N = w_f32.shape[0]
@@ -241,6 +359,9 @@ class EposNet:
         B, H, W, _ = images.shape
         images = images.contiguous()
         self.end_points = {}
+        if self.variant == 'resnet_v1_50_beta':
+            x, xs, h, w, c = self.resnet_features(images)
+            return self.aspp_decoder(x, xs, B, H, W, h, w, c, RESNET_END_POINT)
         H1, W1 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
         c1 = torch.empty((B * H1 * W1, 32), dtype=torch.float32, device=self.dev)
         _lib.check(lib.epos_conv3x3_rgb_s2(images.data_ptr(), p['conv1_1'][0].data_ptr(), p['conv1_1'][1].data_ptr(),
@@ -261,6 +382,11 @@ class EposNet:
                 else:
                     x, h, w, c = self.xception_module(x, B, h, w, c, base, depths, skip, stride, 1, scope in _RELU_INSIDE)
                     current_stride *= stride
+        return self.aspp_decoder(x, None, B, H, W, h, w, c, DECODER_END_POINT)
+
+    def aspp_decoder(self, x, xs, B, H, W, h, w, c, end_point):
+        """ASPP + decoder on backbone features x (f32 [B*h*w, c]; xs = its split form if already available)."""
+        lib, p = self.lib, self.p
         self.end_points['backbone'] = (x, h, w, c)
         # ---- ASPP (model.py:217-258) ----
         M = B * h * w
@@ -270,7 +396,8 @@ class EposNet:
         cp_bias = self.small_fc(ip, p['concat_proj_img'].w_f32, p['concat_proj_img'].bias, relu=False)  # [B,256]
         nb = 1 + len(self.opts.atrous_rates)
         cat = torch.empty((2, M, 256 * nb), dtype=torch.bfloat16, device=self.dev)
-        xs = self.split(x, B, h, w, c, c)
+        if xs is None:
+            xs = self.split(x, B, h, w, c, c)
         self.gemm(xs, p['aspp0'], M, relu=True, out_f32=False, d_split=cat, ldd_split=256 * nb)
         for i, r_ in enumerate(self.opts.atrous_rates, 1):
             a, _, _ = self.dwconv(x, B, h, w, c, c, p['aspp%d_dw' % i], 1, r_, relu_in=False, relu_out=True)
@@ -279,7 +406,7 @@ class EposNet:
         aspp, _ = self.gemm(cat, p['concat_proj'], M, relu=True, bias=cp_bias, bias_group_rows=h * w)
         self.end_points['aspp'] = (aspp, h, w, 256)
         # ---- decoder (model.py:325-380) ----
-        skip, sh, sw, sc = self.end_points[DECODER_END_POINT]
+        skip, sh, sw, sc = self.end_points[end_point]
         dstride = self.opts.decoder_output_stride[0]
         dw_ = scale_dimension(W, 1.0 / dstride)     # crop_size == image size at inference (infer.py:650-654)
         dh_ = scale_dimension(H, 1.0 / dstride)

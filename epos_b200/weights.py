@@ -32,6 +32,13 @@ XCEPTION65_BLOCKS = [
 ]
 
 
+RN = 'resnet_v1_50'               # name_scope['resnet_v1_50_beta'] (feature.py:140-150)
+# (block scope, base depth, num_units, stride of the last unit)   -- net_resnet_v1_beta.py:352-363
+RESNET50_BLOCKS = [('block1', 64, 3, 2), ('block2', 128, 4, 2), ('block3', 256, 6, 2), ('block4', 512, 3, 1)]
+BACKBONE_DEPTH = {'xception_65': 2048, 'resnet_v1_50_beta': 2048}
+SKIP_DEPTH = {'xception_65': 256, 'resnet_v1_50_beta': 256}
+
+
 def head_channels(num_objs, num_frags):
     """common.get_outputs_to_num_channels (/root/reference/epos_lib/common.py:189-203)."""
     return {
@@ -41,11 +48,12 @@ def head_channels(num_objs, num_frags):
     }
 
 
-def variable_specs(num_objs, num_frags):
-    """List of (name, shape, init, stddev) for xception_65 + ASPP + decoder + logits.
+def variable_specs(num_objs, num_frags, model_variant='xception_65'):
+    """List of (name, shape, init, stddev) for the backbone + ASPP + decoder + logits.
 
-    `init` in {'tn' (truncated normal), 'xavier', 'zeros', 'bn'}.  For 'bn' the name is the
-    BatchNorm scope and four variables are created under it.
+    `init` in {'tn' (truncated normal), 'vs' (slim.variance_scaling_initializer: truncated normal with
+    stddev sqrt(1.3 * 2 / fan_in), external/slim/nets/resnet_utils.py:263), 'xavier', 'zeros', 'bn'}.
+    For 'bn' the name is the BatchNorm scope and four variables are created under it.
     """
     specs = []
 
@@ -58,20 +66,38 @@ def variable_specs(num_objs, num_frags):
         specs.append((scope + '/depthwise_weights', (3, 3, c, 1), 'tn', std))
         specs.append((scope + '/BatchNorm', (c,), 'bn', 0.0))
 
-    conv(XC + '/entry_flow/conv1_1', 3, 3, 32)
-    conv(XC + '/entry_flow/conv1_2', 3, 32, 64)
-    cin = 64
-    for scope, depths, skip, units in XCEPTION65_BLOCKS:
-        for u in range(1, units + 1):
-            base = '%s/%s/unit_%d/xception_module' % (XC, scope, u)
-            c = cin
-            for i, d in enumerate(depths):
-                dw('%s/separable_conv%d_depthwise' % (base, i + 1), c)
-                conv('%s/separable_conv%d_pointwise' % (base, i + 1), 1, c, d)
-                c = d
-            if skip == 'conv':
-                conv(base + '/shortcut', 1, cin, depths[-1])
-            cin = depths[-1]
+    if model_variant == 'xception_65':
+        conv(XC + '/entry_flow/conv1_1', 3, 3, 32)
+        conv(XC + '/entry_flow/conv1_2', 3, 32, 64)
+        cin = 64
+        for scope, depths, skip, units in XCEPTION65_BLOCKS:
+            for u in range(1, units + 1):
+                base = '%s/%s/unit_%d/xception_module' % (XC, scope, u)
+                c = cin
+                for i, d in enumerate(depths):
+                    dw('%s/separable_conv%d_depthwise' % (base, i + 1), c)
+                    conv('%s/separable_conv%d_pointwise' % (base, i + 1), 1, c, d)
+                    c = d
+                if skip == 'conv':
+                    conv(base + '/shortcut', 1, cin, depths[-1])
+                cin = depths[-1]
+    elif model_variant == 'resnet_v1_50_beta':
+        # root of three 3x3 convs (net_resnet_v1_beta.py:96-112), then bottleneck units (:38-93)
+        conv(RN + '/conv1_1', 3, 3, 64, init='vs')
+        conv(RN + '/conv1_2', 3, 64, 64, init='vs')
+        conv(RN + '/conv1_3', 3, 64, 128, init='vs')
+        cin = 128
+        for scope, base_depth, units, _ in RESNET50_BLOCKS:
+            for u in range(1, units + 1):
+                base = '%s/%s/unit_%d/bottleneck_v1' % (RN, scope, u)
+                if cin != base_depth * 4:
+                    conv(base + '/shortcut', 1, cin, base_depth * 4, init='vs')
+                conv(base + '/conv1', 1, cin, base_depth, init='vs')
+                conv(base + '/conv2', 3, base_depth, base_depth, init='vs')
+                conv(base + '/conv3', 1, base_depth, base_depth * 4, init='vs')
+                cin = base_depth * 4
+    else:
+        raise ValueError('unsupported model_variant %r' % (model_variant,))
     # ASPP (model.py:217-258)
     conv('image_pooling', 1, 2048, 256, init='xavier')
     conv('aspp0', 1, 2048, 256, init='xavier')
@@ -102,7 +128,7 @@ def _truncated_normal(rng, shape, std):
     return (x * std).astype(np.float32)
 
 
-def random_init(num_objs, num_frags, seed=0, bn='init', logits_std=None):
+def random_init(num_objs, num_frags, seed=0, bn='init', logits_std=None, model_variant='xception_65'):
     """Synthetic weights with the reference's initialisers.
 
     bn='init'   : gamma=1, beta=0, mean=0, var=1 (what a freshly initialised TF graph holds).
@@ -112,8 +138,11 @@ def random_init(num_objs, num_frags, seed=0, bn='init', logits_std=None):
     """
     rng = np.random.Generator(np.random.PCG64(seed))
     w = {}
-    for name, shape, init, std in variable_specs(num_objs, num_frags):
-        if init == 'tn':
+    for name, shape, init, std in variable_specs(num_objs, num_frags, model_variant):
+        if init == 'vs':
+            kh, kw, cin, cout = shape
+            w[name] = _truncated_normal(rng, shape, np.sqrt(1.3 * 2.0 / (kh * kw * cin)))
+        elif init == 'tn':
             if logits_std is not None and name.startswith('logits/'):
                 std = logits_std
             w[name] = _truncated_normal(rng, shape, std)

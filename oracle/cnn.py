@@ -13,6 +13,8 @@ Follows, line by line in behaviour (not in code):
   /root/reference/epos_lib/net_xception.py:396-483,593-657  xception / xception_65
   /root/reference/external/slim/nets/resnet_utils.py:77-122  conv2d_same
   /root/reference/epos_lib/misc.py:94-107        resize_bilinear(align_corners=True)
+  /root/reference/epos_lib/net_resnet_v1_beta.py:38-93,96-112,168-204,302-373  bottleneck, beta root, resnet_v1_50_beta
+  /root/reference/external/slim/nets/resnet_utils.py:59-74,125-217  subsample, stack_blocks_dense
 
 Third-party arithmetic that is not under /root/reference (TensorFlow 1.12 kernels) is restated
 with PyTorch CPU ops: conv (TF 'SAME' = total pad max((ceil(n/s)-1)*s+k_eff-n,0), before =
@@ -40,6 +42,11 @@ BLOCKS = [  # scope, depth_list, skip, units, stride, relu-inside-separable-conv
 ]
 DECODER_END_POINT = 'entry_flow/block2/unit_1/xception_module/separable_conv2_pointwise'
 
+RN = 'resnet_v1_50'   # name_scope['resnet_v1_50_beta'], feature.py:140-150
+EPS_RESNET = 1e-5     # feature.py:277-281
+RESNET50_BLOCKS = [('block1', 64, 3, 2), ('block2', 128, 4, 2), ('block3', 256, 6, 2), ('block4', 512, 3, 1)]
+RESNET_END_POINT = 'block1/unit_2/bottleneck_v1/conv3'   # feature.py:40-44
+
 
 def scale_dimension(dim, scale):
     """model.py:100-114."""
@@ -52,9 +59,11 @@ def tf_same_pad(n, k_eff, s):
 
 
 class Oracle:
-    def __init__(self, weights, dtype=torch.float32, threads=None):
+    def __init__(self, weights, dtype=torch.float32, threads=None, model_variant='xception_65', multi_grid=None):
         self.w = weights
         self.dt = dtype
+        self.variant = model_variant
+        self.multi_grid = tuple(multi_grid) if multi_grid else (1, 1, 1)   # net_resnet_v1_beta.py:36
         if threads:
             torch.set_num_threads(threads)
         self.end_points = {}
@@ -148,8 +157,58 @@ class Oracle:
     def conv_bn_relu_head(self, x, scope):
         return F.relu(self.bn(self.conv(x, scope), scope, EPS_HEAD))
 
+    # -- ResNet-50 beta -------------------------------------------------------------------
+    def rn_conv(self, x, scope, k, stride=1, rate=1, relu=True):
+        """slim.conv2d / resnet_utils.conv2d_same under resnet_arg_scope: conv + BN(eps 1e-5) (+ReLU)."""
+        if k == 1:
+            y = self.conv(x, scope, stride, 1, 'SAME')              # 1x1: SAME at stride s samples every s-th pixel
+        elif stride == 1:
+            y = self.conv(x, scope, 1, rate, 'SAME')
+        else:
+            y = self.conv(self.fixed_padding(x, k, rate), scope, stride, rate, 'VALID')
+        y = self.bn(y, scope, EPS_RESNET)
+        return F.relu(y) if relu else y
+
+    def bottleneck(self, x, base, depth, depth_bottleneck, stride, rate):
+        """net_resnet_v1_beta.py:38-93."""
+        if depth == x.shape[1]:
+            shortcut = x if stride == 1 else x[:, :, ::stride, ::stride]      # subsample = 1x1 max-pool, stride s
+        else:
+            shortcut = self.rn_conv(x, base + '/shortcut', 1, stride, relu=False)
+        r = self.rn_conv(x, base + '/conv1', 1)
+        r = self.rn_conv(r, base + '/conv2', 3, stride, rate)
+        r = self.rn_conv(r, base + '/conv3', 1, relu=False)
+        self.end_points[base.replace(RN + '/', '') + '/conv3'] = r
+        return F.relu(shortcut + r)
+
+    def resnet_backbone(self, images_nhwc, output_stride=8):
+        x = torch.from_numpy(np.ascontiguousarray(images_nhwc)).to(self.dt).permute(0, 3, 1, 2)
+        x = (2.0 / 255.0) * x - 1.0                             # beta variants: feature.py:176-185
+        x = self.rn_conv(x, RN + '/conv1_1', 3, 2)              # root_block_fn_for_beta_variant
+        x = self.rn_conv(x, RN + '/conv1_2', 3, 1)
+        x = self.rn_conv(x, RN + '/conv1_3', 3, 1)
+        ph = tf_same_pad(x.shape[2], 3, 2)                      # slim.max_pool2d(3, 2, 'SAME')
+        pw = tf_same_pad(x.shape[3], 3, 2)
+        x = F.max_pool2d(F.pad(x, (pw[0], pw[1], ph[0], ph[1]), value=float('-inf')), 3, 2)
+        target = output_stride // 4                             # net_resnet_v1_beta.py:183-185
+        current_stride, rate = 1, 1
+        for scope, base_depth, units, last_stride in RESNET50_BLOCKS:
+            for u in range(1, units + 1):
+                base = '%s/%s/unit_%d/bottleneck_v1' % (RN, scope, u)
+                stride = last_stride if u == units else 1
+                unit_rate = self.multi_grid[u - 1] if scope == 'block4' else 1
+                if current_stride == target:                    # resnet_utils.py:191-197
+                    x = self.bottleneck(x, base, base_depth * 4, base_depth, 1, rate * unit_rate)
+                    rate *= stride
+                else:
+                    x = self.bottleneck(x, base, base_depth * 4, base_depth, stride, unit_rate)
+                    current_stride *= stride
+        return x
+
     # -- network ----------------------------------------------------------------------------
     def backbone(self, images_nhwc, output_stride=8):
+        if self.variant == 'resnet_v1_50_beta':
+            return self.resnet_backbone(images_nhwc, output_stride)
         x = torch.from_numpy(np.ascontiguousarray(images_nhwc)).to(self.dt).permute(0, 3, 1, 2)
         x = (2.0 / 255.0) * x - 1.0                             # feature.py:171-174
         x = self.conv2d_same(x, XC + '/entry_flow/conv1_1', 2)
@@ -179,7 +238,7 @@ class Oracle:
         return self.conv_bn_relu_head(x, 'concat_projection')  # dropout inactive
 
     def decoder(self, x, crop_size_wh, decoder_stride=4):
-        skip = self.end_points[DECODER_END_POINT]
+        skip = self.end_points[RESNET_END_POINT if self.variant == 'resnet_v1_50_beta' else DECODER_END_POINT]
         proj = self.conv_bn_relu_head(skip, 'decoder/feature_projection0')
         dw_ = scale_dimension(crop_size_wh[0], 1.0 / decoder_stride)
         dh_ = scale_dimension(crop_size_wh[1], 1.0 / decoder_stride)
@@ -216,9 +275,12 @@ class Oracle:
                 out['_aspp'] = a.permute(0, 2, 3, 1).contiguous().numpy()
                 out['_decoder'] = d.permute(0, 2, 3, 1).contiguous().numpy()
                 out['_obj_logits'] = lo.contiguous().numpy()
-                out['_skip'] = self.end_points[DECODER_END_POINT].permute(0, 2, 3, 1).contiguous().numpy()
+                ep = RESNET_END_POINT if self.variant == 'resnet_v1_50_beta' else DECODER_END_POINT
+                out['_skip'] = self.end_points[ep].permute(0, 2, 3, 1).contiguous().numpy()
             return out
 
 
-def predict(weights, images_nhwc, num_objs, num_frags, dtype=torch.float32, **kw):
-    return Oracle(weights, dtype).predict(images_nhwc, num_objs, num_frags, **kw)
+def predict(weights, images_nhwc, num_objs, num_frags, dtype=torch.float32, model_variant='xception_65',
+            multi_grid=None, **kw):
+    return Oracle(weights, dtype, model_variant=model_variant, multi_grid=multi_grid).predict(
+        images_nhwc, num_objs, num_frags, **kw)

@@ -263,18 +263,21 @@ def test_resize_mean_softmax(env):
         assert (lab == ref.argmax(-1)).float().mean() > 0.999
 
 
-def _net_parity(B, H, W, O, F, seed, check_simt=False):
+def _net_parity(B, H, W, O, F, seed, check_simt=False, variant='xception_65', multi_grid=None, logits_std=0.5):
     from epos_b200 import model, weights as Wt
     from oracle import cnn
     dev = torch.device('cuda:0')
-    w = Wt.random_init(O, F, seed=seed, bn='random', logits_std=0.5)
+    w = Wt.random_init(O, F, seed=seed, bn='random', logits_std=logits_std, model_variant=variant)
     img = Wt.synthetic_images(B, seed=seed, height=H, width=W)
-    net = model.EposNet(w, O, F, dev, keep_f32=True)
+    opts = model.ModelOptions(Wt.head_channels(O, F), crop_size=(W, H), model_variant=variant, multi_grid=multi_grid)
+    net = model.EposNet(w, O, F, dev, model_options=opts, keep_f32=True)
     out = net.predict(torch.from_numpy(img).to(dev))
     torch.cuda.synchronize()
-    ref = cnn.predict(w, img, O, F, return_features=True)
+    ref = cnn.predict(w, img, O, F, return_features=True, model_variant=variant, multi_grid=multi_grid)
     errs = {}
-    for name, key in (('backbone', '_backbone'), ('aspp', '_aspp'), ('decoder', '_decoder')):
+    ep = model.RESNET_END_POINT if variant == 'resnet_v1_50_beta' else model.DECODER_END_POINT
+    net.end_points['skip'] = net.end_points[ep]
+    for name, key in (('skip', '_skip'), ('backbone', '_backbone'), ('aspp', '_aspp'), ('decoder', '_decoder')):
         t, h, w_, c = net.end_points[name]
         errs[name] = rel_err(t.cpu().numpy().reshape(ref[key].shape), ref[key])
     for k in (model.PRED_OBJ_CONF, model.PRED_FRAG_CONF, model.PRED_FRAG_LOC):
@@ -312,3 +315,18 @@ def test_network_full_size_c1():
 def test_network_full_size_ycbv_heads():
     """21 objects x 64 fragments (YCB-V-shaped heads), batch 2."""
     _net_parity(2, 480, 640, 21, 64, seed=14)
+
+
+# The variance-scaling initialiser with perturbed BN statistics leaves decoder features of magnitude ~1e3-1e4; the logit
+# stddev is scaled down so that the logits stay O(1-10) and the softmax outputs are a meaningful comparison.
+def test_resnet50_beta_small():
+    """BASELINE config 4 backbone (resnet_v1_50_beta, net_resnet_v1_beta.py:302-373) at a small size."""
+    _net_parity(2, 96, 128, 3, 8, seed=21, variant='resnet_v1_50_beta', logits_std=0.002)
+
+
+def test_resnet50_beta_odd_size_multigrid():
+    _net_parity(1, 81, 113, 2, 4, seed=22, variant='resnet_v1_50_beta', multi_grid=(1, 2, 4), logits_std=0.002)
+
+
+def test_resnet50_beta_full_size():
+    _net_parity(1, 480, 640, 21, 64, seed=23, variant='resnet_v1_50_beta', logits_std=0.0005)

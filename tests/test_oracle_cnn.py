@@ -77,3 +77,27 @@ def test_shapes_and_layout_small():
     assert out['pred_frag_loc'].shape == (1, 16, 24, 2, 4, 3)
     np.testing.assert_allclose(out['pred_obj_conf'].sum(-1), 1.0, rtol=1e-5)
     np.testing.assert_allclose(out['pred_frag_conf'].sum(-1), 1.0, rtol=1e-5)
+
+
+def test_resnet_beta_atrous_equals_nominal_stride_subsampled():
+    """resnet_v1_test.py:470-495 (testAtrousFullyConvolutionalValues): dense features at output stride 8 sampled every
+    4th pixel equal the nominal-stride-32 features (same weights); pins the stride -> atrous-rate conversion of the
+    ResNet restatement (resnet_utils.py:125-217) and conv2d_same / subsample on an odd size."""
+    from epos_b200 import weights as W
+    w = W.random_init(1, 2, seed=3, bn='random', model_variant='resnet_v1_50_beta')
+    img = W.synthetic_images(1, seed=3, height=65, width=97)
+    o = cnn.Oracle(w, dtype=torch.float64, model_variant='resnet_v1_50_beta')
+    with torch.no_grad():
+        dense = o.resnet_backbone(img, output_stride=8)
+        nominal = o.resnet_backbone(img, output_stride=32)
+    assert dense.shape[2:] == (9, 13) and nominal.shape[2:] == (3, 4)
+    np.testing.assert_allclose(dense[:, :, ::4, ::4].numpy(), nominal.numpy(), rtol=1e-8, atol=1e-8 * float(nominal.abs().max()))
+
+
+def test_resnet_beta_shapes_and_end_point():
+    from epos_b200 import weights as W
+    w = W.random_init(2, 4, seed=1, model_variant='resnet_v1_50_beta')
+    img = W.synthetic_images(1, seed=1, height=64, width=96)
+    out = cnn.predict(w, img, 2, 4, model_variant='resnet_v1_50_beta', return_features=True)
+    assert out['_backbone'].shape == (1, 8, 12, 2048) and out['_skip'].shape == (1, 16, 24, 256)
+    assert out['pred_frag_loc'].shape == (1, 16, 24, 2, 4, 3)
