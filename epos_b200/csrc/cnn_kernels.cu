@@ -448,6 +448,38 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x
   }
 }
 
+// Tiny-M fp32 GEMM (M <= 16: the image-pooling branch has M = batch): one warp per output column, lanes stride over K
+// (coalesced W rows), the M accumulators live in registers and are reduced with shuffles.
+constexpr int SMALLM_MAX = 16;
+__global__ void __launch_bounds__(256) pwconv_smallm_kernel(const float* __restrict__ a, int lda, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, int bias_group_rows,
+                                                            float* __restrict__ d, int ldd, int M, int N, int K, int relu) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (n >= N) return;
+  float acc[SMALLM_MAX];
+#pragma unroll
+  for (int m = 0; m < SMALLM_MAX; ++m) acc[m] = 0.f;
+  const float* wr = w + (long long)n * K;
+  for (int k = lane; k < K; k += 32) {
+    const float wv = __ldg(wr + k);
+#pragma unroll
+    for (int m = 0; m < SMALLM_MAX; ++m)
+      if (m < M) acc[m] = fmaf(__ldg(a + (long long)m * lda + k), wv, acc[m]);
+  }
+#pragma unroll
+  for (int m = 0; m < SMALLM_MAX; ++m) {
+    float v = acc[m];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && m < M) {
+      if (bias) v += bias[(bias_group_rows > 0 ? (long long)(m / bias_group_rows) * N : 0) + n];
+      if (relu) v = fmaxf(v, 0.f);
+      d[(long long)m * ldd + n] = v;
+    }
+  }
+}
+
 // fp32 SIMT GEMM: D = act(A W^T + bias) (+ residual).  64x64 tile, 256 threads, 4x4 per thread.
 __global__ void __launch_bounds__(256) pwconv_simt_kernel(const float* __restrict__ a, int lda, const float* __restrict__ w,
                                                           const float* __restrict__ bias, int bias_group_rows,
@@ -638,6 +670,12 @@ int epos_softmax_rows(float* x, int64_t* labels, size_t rows, int n, void* strea
 int epos_pwconv_simt(const float* a, int lda, const float* w, const float* bias, int bias_group_rows,
                      const float* residual, int ldr, float* d, int ldd, int M, int N, int K, int relu, void* stream) {
   EPOS_CHECK_ARG(a && w && d && M > 0 && N > 0 && K > 0 && lda >= K && ldd >= N);
+  if (M <= SMALLM_MAX && !residual) {
+    pwconv_smallm_kernel<<<ceil_div(N, 8), 256, 0, (cudaStream_t)stream>>>(a, lda, w, bias, bias_group_rows, d, ldd, M, N,
+                                                                          K, relu);
+    EPOS_LAUNCH_CHECK();
+    return EPOS_OK;
+  }
   dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
   pwconv_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, lda, w, bias, bias_group_rows, residual, ldr, d, ldd, M,
                                                             N, K, relu);

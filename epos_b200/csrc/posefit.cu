@@ -1049,7 +1049,25 @@ __global__ void __launch_bounds__(THREADS, 1)
 fit_kernel(Workspace ws, epos_fit_params prm, const int* __restrict__ offsets, double* __restrict__ poses,
            int* __restrict__ labeling) {
   extern __shared__ unsigned char smem_raw[];
-  const int p = blockIdx.x;
+  // Longest-processing-time-first: CTAs are dispatched in blockIdx order and P usually exceeds the SM count (one CTA
+  // per SM), so block b takes the problem with the b-th largest point count -- the expensive problems start in the
+  // first wave and the small ones fill the tail.  Problems are independent (own seed, own workspace slice), so the
+  // mapping does not change any result.
+  __shared__ int s_problem;
+  {
+    const int P = gridDim.x;
+    for (int j = threadIdx.x; j < P; j += THREADS) {
+      const int nj = ws.st[j].N;
+      int rank = 0;
+      for (int k = 0; k < P; ++k) {
+        const int nk = ws.st[k].N;
+        rank += (nk > nj || (nk == nj && k < j)) ? 1 : 0;
+      }
+      if (rank == (int)blockIdx.x) s_problem = j;
+    }
+    __syncthreads();
+  }
+  const int p = s_problem;
   ProbState* st = ws.st + p;
   bool pts_loaded = false;
   for (int guard = 0; guard < 1 << 14; ++guard) {

@@ -144,10 +144,14 @@ class EposNet:
         self.p = p
 
     def _prepare_xception(self, w, p):
+        # conv1_1 (3 -> 32) is emitted with 64 output channels, the upper 32 with zero weights and bias (ReLU(0) = 0), so
+        # that conv1_2 (32 -> 64, zero-padded to Cin = 64) can run as an implicit 3x3 GEMM on the tensor cores.
         k, b = self._conv_bn(w, XC + '/entry_flow/conv1_1', EPS_BACKBONE)
-        p['conv1_1'] = (self._dev(k), self._dev(b))
+        p['conv1_1'] = (self._dev(np.concatenate([k, np.zeros_like(k)], axis=3)),
+                        self._dev(np.concatenate([b, np.zeros_like(b)])))
         k, b = self._conv_bn(w, XC + '/entry_flow/conv1_2', EPS_BACKBONE)
-        p['conv1_2'] = (self._dev(k), self._dev(b))
+        k = np.concatenate([k, np.zeros_like(k)], axis=2)                           # [3,3,64,64]
+        p['conv1_2'] = Gemm(k.reshape(-1, k.shape[3]).T, b, self.dev, False)
         for scope, depths, skip, units in XCEPTION65_BLOCKS:
             for u in range(1, units + 1):
                 base = '%s/%s/unit_%d/xception_module' % (XC, scope, u)
@@ -363,12 +367,10 @@ class EposNet:
             x, xs, h, w, c = self.resnet_features(images)
             return self.aspp_decoder(x, xs, B, H, W, h, w, c, RESNET_END_POINT)
         H1, W1 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
-        c1 = torch.empty((B * H1 * W1, 32), dtype=torch.float32, device=self.dev)
+        c1 = torch.empty((2, B * H1 * W1, 64), dtype=torch.bfloat16, device=self.dev)
         _lib.check(lib.epos_conv3x3_rgb_s2(images.data_ptr(), p['conv1_1'][0].data_ptr(), p['conv1_1'][1].data_ptr(),
-                                           c1.data_ptr(), None, B, H, W, 32, self._s()), 'epos_conv3x3_rgb_s2')
-        c2 = torch.empty((B * H1 * W1, 64), dtype=torch.float32, device=self.dev)
-        _lib.check(lib.epos_conv3x3_dense(c1.data_ptr(), p['conv1_2'][0].data_ptr(), p['conv1_2'][1].data_ptr(),
-                                          c2.data_ptr(), B, H1, W1, 32, 64, self._s()), 'epos_conv3x3_dense')
+                                           None, c1.data_ptr(), B, H, W, 64, self._s()), 'epos_conv3x3_rgb_s2')
+        c2, _ = self.conv3x3(c1, p['conv1_2'], B, H1, W1, 64, 1, relu=True, out_f32=True, out_split=False)
         x, h, w, c = c2, H1, W1, 64
         target = self.opts.encoder_output_stride // 2              # net_xception.py:455-458
         current_stride, rate = 1, 1

@@ -1,5 +1,5 @@
 #!/bin/bash
-# One gpurun call: GPU parity tests, bench line, ncu launch list, ncu full capture of the top kernel.
+# One gpurun call: GPU parity tests, bench line, ncu launch list, ncu full captures of the top kernels.
 # usage: gpurun --timeout 1500 -- 'bash scripts/gpu_check.sh <tag>'
 TAG=${1:-dev}
 mkdir -p gpurun_out
@@ -11,8 +11,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 420 -c 700 --csv --
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench_stdout_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:pw_gemm -s 60 -c 3 -f -o gpurun_out/prof_gemm_$TAG \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:dwconv -s 40 -c 2 -f -o gpurun_out/prof_dw_$TAG \
+ncu --set full --clock-control none --import-source on -k regex:dwconv3x3_tile -s 40 -c 2 -f -o gpurun_out/prof_dw_$TAG \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:main_kernel -c 2 -f -o gpurun_out/prof_ransac_$TAG \
+ncu --set full --clock-control none --import-source on -k regex:fit_kernel -c 1 -f -o gpurun_out/prof_ransac_$TAG \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
 ls -la gpurun_out
