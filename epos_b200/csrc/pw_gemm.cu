@@ -97,11 +97,6 @@ __device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
                : "memory");
 }
 
-// Work distribution.  Full waves of 128 x BLOCK_N tiles are dealt round-robin in n-major order (CTAs that run together
-// share A tiles in L2).  A plain tile grid then loses up to a whole wave on the remainder (the 38400 x 728 layers are
-// 900 tiles = 6.08 waves on 148 SMs), so when the remainder is at most half a wave its tiles are cut into blocks of
-// 64 columns that are spread evenly over all CTAs: the tail costs a fraction of a tile time instead of a full one.
-// All three warp roles walk the same sequence of pieces (rows [m0, m0+128) x columns [n0, n0+n_cols)).
 // 3x3 (atrous) convolution as an implicit GEMM: K = 9 taps x C channels, an M tile is an 8 x 16 block of output
 // pixels of one image, and the A box of tap (ky, kx) is the same block shifted by ((ky-1) rate, (kx-1) rate) --
 // out-of-image rows/columns are zero-filled by the TMA unit, which is exactly TF 'SAME' padding at stride 1.
@@ -114,52 +109,42 @@ struct ConvGeom {
 };
 constexpr int CONV_TW = 16, CONV_TH = 8;
 
-struct PieceIter {
-  int n_tiles, bulk_end, tile, block_n, N;
-  int unit, upt;                       // tail: columns per block, blocks per full tile
-  int tail_tile, tail_acc, lo, hi;     // tail cursor: current tile, blocks before it, this CTA's block range
-  int num_tiles;
-  __device__ PieceIter(int m_tiles, int N_, int block_n_) {
-    N = N_; block_n = block_n_;
+// Work distribution.  The output is cut into PIECES: full 128 x BLOCK_N tiles in n-major order (pieces handed out
+// together share A tiles in L2), and -- when the tile count leaves a remainder of at most half a wave (the 38400 x 728
+// layers are 900 tiles = 6.08 waves on 148 SMs) -- the remainder tiles cut into blocks of 64 columns, so that the tail
+// costs a fraction of a tile time instead of a full one.  Pieces are handed out DYNAMICALLY: the producer warp takes
+// the next piece index from a global counter and publishes it to the MMA and epilogue warps through a small
+// shared-memory queue.  The kernel therefore makes progress with however many CTAs are resident -- it can share the
+// GPU with the long-running pose-fitting CTAs of the previous batch (engine.py) instead of waiting for their SMs.
+struct PieceMap {
+  int n_tiles, bulk_end, block_n, unit, bpr, g0, num_pieces;
+  __device__ PieceMap(int m_tiles, int N, int block_n_) {
+    block_n = block_n_;
     n_tiles = (N + block_n - 1) / block_n;
-    num_tiles = m_tiles * n_tiles;
+    const int num_tiles = m_tiles * n_tiles;
     const int G = gridDim.x;
     int rem = num_tiles % G;
     unit = block_n < 64 ? block_n : 64;
-    upt = block_n / unit;
+    const int upt = block_n / unit;
     if (rem * 2 > G || upt == 1) rem = 0;          // a remainder above half a wave (or unsplittable tiles) stays whole
     bulk_end = num_tiles - rem;
-    tile = blockIdx.x;
-    tail_tile = bulk_end; tail_acc = 0; lo = hi = 0;
-    if (rem) {
-      long long total = 0;
-      for (int t = bulk_end; t < num_tiles; ++t) total += blocks_of(t);
-      lo = (int)(total * blockIdx.x / G);
-      hi = (int)(total * (blockIdx.x + 1) / G);
-    }
+    bpr = (N + unit - 1) / unit;                   // 64-column blocks per row of tiles
+    g0 = (bulk_end / n_tiles) * bpr + (bulk_end % n_tiles) * upt;
+    num_pieces = bulk_end + (m_tiles * bpr - g0);
   }
-  __device__ int blocks_of(int t) const {
-    int w = N - (t % n_tiles) * block_n;
-    if (w > block_n) w = block_n;
-    return (w + unit - 1) / unit;
-  }
-  __device__ bool next(int& m0, int& n0, int& n_cols) {
-    if (tile < bulk_end) {
-      m0 = (tile / n_tiles) * BLOCK_M; n0 = (tile % n_tiles) * block_n; n_cols = block_n;
-      tile += gridDim.x;
-      return true;
+  // rows [m0, m0+128) x columns [n0, n0+n_cols) (n_cols may run past N: mask with N)
+  __device__ void decode(int id, int& m0, int& n0, int& n_cols) const {
+    if (id < bulk_end) {
+      m0 = (id / n_tiles) * BLOCK_M; n0 = (id % n_tiles) * block_n; n_cols = block_n;
+    } else {
+      const int g = g0 + (id - bulk_end);
+      const int row = g / bpr;
+      m0 = row * BLOCK_M; n0 = (g - row * bpr) * unit; n_cols = unit;
     }
-    if (lo >= hi) return false;
-    int nb = blocks_of(tail_tile);
-    while (tail_acc + nb <= lo) { tail_acc += nb; ++tail_tile; nb = blocks_of(tail_tile); }
-    const int first = lo - tail_acc;
-    int cnt = nb - first;
-    if (cnt > hi - lo) cnt = hi - lo;
-    m0 = (tail_tile / n_tiles) * BLOCK_M; n0 = (tail_tile % n_tiles) * block_n + first * unit; n_cols = cnt * unit;
-    lo += cnt;
-    return true;
   }
 };
+constexpr int SCHED_DEPTH = 4;
+struct SchedSlot { int next, done; };               // global: next piece index, CTAs finished (the last one resets both)
 
 template <int BLOCK_N, int BLOCK_K>
 struct GemmCfg {
@@ -171,14 +156,14 @@ struct GemmCfg {
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES < 2 ? 2 : ((200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   static constexpr int STAGING_BYTES = 4 * 32 * 32 * 4;            // epilogue transpose buffers, one per warp
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STAGING_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers, piece queue*/ + STAGING_BYTES;
 };
 
 template <int BLOCK_N, int BLOCK_K>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                const __grid_constant__ CUtensorMap tmap_w64,
-               const GemmEpilogue ep, const ConvGeom cg, int M, int N, int K, int dbg) {
+               const GemmEpilogue ep, const ConvGeom cg, SchedSlot* __restrict__ sched, int M, int N, int K, int dbg) {
   using Cfg = GemmCfg<BLOCK_N, BLOCK_K>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -192,8 +177,12 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* staging = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
+  uint64_t* sched_full = bars + 2 * STAGES + 4;
+  uint64_t* sched_empty = sched_full + SCHED_DEPTH;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sched_empty + SCHED_DEPTH);
+  volatile int* sched_ids = reinterpret_cast<volatile int*>(tmem_ptr_smem + 1);
+  static_assert((2 * STAGES + 4 + 2 * SCHED_DEPTH) * 8 + 4 + SCHED_DEPTH * 4 <= 512, "barrier area");
+  float* staging = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 512);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -206,6 +195,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w64) : "memory");
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < SCHED_DEPTH; ++i) { mbar_init(&sched_full[i], 1); mbar_init(&sched_empty[i], 5); }   // MMA + 4 epilogue warps
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -224,9 +214,21 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      PieceIter it(m_tiles, N, BLOCK_N);
+      const PieceMap pm(m_tiles, N, BLOCK_N);
+      int sslot = 0;
+      uint32_t sphase = 0;
       int m0, n0, n_cols;
-      while (it.next(m0, n0, n_cols)) {
+      int id = atomicAdd(&sched->next, 1);
+      while (true) {
+        // take the index after this one now: the atomic's round trip hides behind this piece's loads
+        const int id_next = id < pm.num_pieces ? atomicAdd(&sched->next, 1) : pm.num_pieces;
+        mbar_wait(&sched_empty[sslot], sphase ^ 1);
+        sched_ids[sslot] = id < pm.num_pieces ? id : -1;
+        mbar_arrive(&sched_full[sslot]);                            // release: publishes the index to the consumers
+        if (++sslot == SCHED_DEPTH) { sslot = 0; sphase ^= 1; }
+        if (id >= pm.num_pieces) break;
+        pm.decode(id, m0, n0, n_cols);
+        id = id_next;
         int n_rows = N - n0;                                       // W rows this piece needs
         if (n_rows > n_cols) n_rows = n_cols;
         const bool full = n_cols == BLOCK_N;                        // whole tile: one box (rows past N are zero-filled)
@@ -270,9 +272,17 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      PieceIter it(m_tiles, N, BLOCK_N);
+      const PieceMap pm(m_tiles, N, BLOCK_N);
+      int sslot = 0;
+      uint32_t sphase = 0;
       int m0, n0, n_cols;
-      while (it.next(m0, n0, n_cols)) {
+      while (true) {
+        mbar_wait(&sched_full[sslot], sphase);
+        const int id = sched_ids[sslot];
+        mbar_arrive(&sched_empty[sslot]);
+        if (++sslot == SCHED_DEPTH) { sslot = 0; sphase ^= 1; }
+        if (id < 0) break;
+        pm.decode(id, m0, n0, n_cols);
         int umma_n = N - n0;
         if (umma_n > n_cols) umma_n = n_cols;
         umma_n = (umma_n + 15) & ~15;                              // columns past the piece are computed but never stored
@@ -332,9 +342,18 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     float4* stg = reinterpret_cast<float4*>(staging + (warp - 2) * 1024);
     const int rsub = lane >> 3, jj = lane & 7;
     const float relu_floor = ep.relu ? 0.f : -INFINITY;
-    PieceIter it(m_tiles, N, BLOCK_N);
+    const PieceMap pm(m_tiles, N, BLOCK_N);
+    int sslot = 0;
+    uint32_t sphase = 0;
     int m0, n0, n_cols;
-    while (it.next(m0, n0, n_cols)) {
+    while (true) {
+      mbar_wait(&sched_full[sslot], sphase);
+      const int id = sched_ids[sslot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sched_empty[sslot]);
+      if (++sslot == SCHED_DEPTH) { sslot = 0; sphase ^= 1; }
+      if (id < 0) break;
+      pm.decode(id, m0, n0, n_cols);
       int n_valid = N - n0;
       if (n_valid > n_cols) n_valid = n_cols;
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -524,6 +543,14 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) {
+    // the last CTA to finish re-arms the counters for the next launch that uses this slot
+    __threadfence();
+    if (atomicAdd(&sched->done, 1) == (int)gridDim.x - 1) {
+      sched->next = 0; sched->done = 0;
+      __threadfence();
+    }
+  }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
@@ -555,6 +582,22 @@ static int make_map(CUtensorMap* map, const void* base, int rows, int cols, int 
   return EPOS_OK;
 }
 
+// Ring of scheduler slots in device memory (zeroed once; every kernel leaves its slot zeroed).  A slot is reused
+// SCHED_RING launches later, long after the launch that used it has drained.
+constexpr int SCHED_RING = 256;
+static SchedSlot* sched_slot() {
+  static SchedSlot* ring[64] = {};
+  static unsigned seq[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return nullptr;
+  if (!ring[dev]) {
+    if (cudaMalloc(&ring[dev], SCHED_RING * sizeof(SchedSlot)) != cudaSuccess) return nullptr;
+    if (cudaMemset(ring[dev], 0, SCHED_RING * sizeof(SchedSlot)) != cudaSuccess) return nullptr;
+  }
+  return ring[dev] + (seq[dev]++ % SCHED_RING);
+}
+
 template <int BLOCK_N, int BLOCK_K>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mw64, const GemmEpilogue& ep,
                        const ConvGeom& cg, int M, int N, int K, cudaStream_t stream, int dbg) {
@@ -564,11 +607,13 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const CUten
     EPOS_CUDA(cudaFuncSetAttribute(pw_gemm_kernel<BLOCK_N, BLOCK_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr = true;
   }
-  // one CTA per SM; with less than a wave of tiles the remainder logic of PieceIter spreads 64-column blocks
+  // one CTA per SM; with less than a wave of tiles the remainder logic of PieceMap spreads 64-column blocks
   const long long m_tiles = cg.enabled ? (long long)(M / (cg.H * cg.W)) * cg.tiles_x * cg.tiles_y : ceil_div(M, BLOCK_M);
   const long long blocks64 = m_tiles * ceil_div(N, BLOCK_N < 64 ? BLOCK_N : 64);
   const int grid = blocks64 < num_sms() ? (int)blocks64 : num_sms();
-  pw_gemm_kernel<BLOCK_N, BLOCK_K><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mw, mw64, ep, cg, M, N, K, dbg);
+  SchedSlot* slot = sched_slot();
+  if (!slot) { set_error("pw_gemm: cannot allocate the scheduler slots"); return EPOS_ERR_CUDA; }
+  pw_gemm_kernel<BLOCK_N, BLOCK_K><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mw, mw64, ep, cg, slot, M, N, K, dbg);
   EPOS_LAUNCH_CHECK();
   return EPOS_OK;
 }
