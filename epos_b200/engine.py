@@ -14,9 +14,15 @@ STAGES_FULL = 'cnn+corresp+fit'
 
 
 class Engine:
+    """pipelined=True (full path only): the CNN of batch i+1 runs on the caller's stream while correspondence extraction
+    and pose fitting of batch i run on a side stream.  Pose fitting is latency-bound (one CTA per (image, object)
+    problem, a few long problems at the end) and leaves most SMs idle; the CNN kernels fill them -- the tcgen05 GEMM
+    takes its tiles from a global counter, so it runs on whatever SMs are free.  Results are identical to the serial
+    order (every problem has its own seed and workspace)."""
+
     def __init__(self, weights, num_objs, num_frags, device, stages=STAGES_CNN, model_store=None, K=None,
                  fit_params=None, max_correspondences=4096, seed=0, min_obj_conf=0.1, min_frag_rel_conf=0.5,
-                 model_options=None):
+                 model_options=None, pipelined=False, post_fit=None):
         self.dev = torch.device(device)
         self.net = model.EposNet(weights, num_objs, num_frags, self.dev, model_options=model_options)
         self.O, self.F = num_objs, num_frags
@@ -27,31 +33,91 @@ class Engine:
         self.max_corr = max_correspondences
         self.seed = seed
         self._fitter = None
+        self.post_fit = post_fit                 # e.g. the NCCL all-gather of pose records (epos_b200/dist.py)
+        self.pipelined = bool(pipelined) and stages == STAGES_FULL
+        self._side = torch.cuda.Stream(device=self.dev) if self.pipelined else None
+        self._inflight = []                      # (maps kept alive, event after corresp) of batches still on the side stream
+        self._last_fit = None                    # event after the most recent fit
+        self._pending_host = None                # (pinned result, event) of the previous run_host call
         if stages == STAGES_FULL:
             from . import posefit
             self._fitter = posefit.BatchFitter(self.dev, num_objs, num_frags, model_store, K, fit_params,
                                                max_correspondences, seed, min_obj_conf=min_obj_conf,
                                                min_frag_rel_conf=min_frag_rel_conf)
 
+    def _fit(self, out, after_extract=None):
+        poses = self._fitter.fit(out, after_extract).clone()      # the fitter's record buffer is reused by the next batch
+        out['poses'] = poses
+        if self.post_fit is not None:
+            out['poses_all'] = self.post_fit(poses)
+
     def run_device(self, images_dev):
         """images_dev [B,H,W,3] f32 CUDA.  Returns a dict of CUDA tensors: model.predict's outputs for 'cnn',
-        plus 'poses' [B,O,16] f64 pose records for the full path."""
+        plus 'poses' [B,O,16] f64 pose records for the full path (pipelined: valid after join() / out['ready'])."""
         out = self.net.predict(images_dev)
-        if self._fitter is not None:
-            out['poses'] = self._fitter.fit(out)
+        if self._fitter is None:
+            return out
+        if not self.pipelined:
+            self._fit(out)
+            return out
+        main = torch.cuda.current_stream(self.dev)
+        done_cnn = torch.cuda.Event()
+        done_cnn.record(main)
+        # keep at most two batches of head maps alive; the older one is dropped once its correspondences are extracted
+        while len(self._inflight) >= 2:
+            _, ev = self._inflight.pop(0)
+            ev.synchronize()
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(done_cnn)
+            maps = [out[k] for k in (model.PRED_OBJ_CONF, model.PRED_FRAG_CONF, model.PRED_FRAG_LOC)]
+            for t in maps:
+                t.record_stream(self._side)
+            ev_maps = torch.cuda.Event()
+            self._fit(out, after_extract=lambda: ev_maps.record(self._side))
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        self._inflight.append((maps, ev_maps))
+        self._last_fit = ev
+        out['ready'] = ev
         return out
+
+    def join(self):
+        """Makes the caller's stream wait for everything queued on the side stream."""
+        if self._last_fit is not None:
+            torch.cuda.current_stream(self.dev).wait_event(self._last_fit)
 
     def result_tensor(self, out):
         """The tensor a caller reads back per batch: pose records (full path) or the object label map."""
         return out['poses'] if 'poses' in out else out[model.PRED_OBJ_LABEL]
 
     def run_host(self, images_pinned, result_pinned=None):
-        """End-to-end call with HOST buffers: H2D of the batch, the hot path, D2H of the result."""
+        """End-to-end call with HOST buffers: H2D of the batch, the hot path, D2H of the result.
+        Serial engine: returns this batch's result.  Pipelined engine: the D2H of this batch is queued behind its pose
+        fitting on the side stream and the call returns the PREVIOUS batch's result (None on the first call); flush()
+        returns the last one -- the host always holds batch i while the GPU works on batch i+1."""
         x = images_pinned.to(self.dev, non_blocking=True)
         out = self.run_device(x)
         r = self.result_tensor(out)
-        if result_pinned is None:
-            return r.cpu()
-        result_pinned.copy_(r, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return result_pinned
+        if not self.pipelined:
+            if result_pinned is None:
+                return r.cpu()
+            result_pinned.copy_(r, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return result_pinned
+        prev = self.flush()
+        buf = torch.empty(r.shape, dtype=r.dtype).pin_memory() if result_pinned is None else result_pinned
+        with torch.cuda.stream(self._side):
+            buf.copy_(r, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        self._pending_host = (buf, ev)
+        return prev
+
+    def flush(self):
+        """Pipelined engine: waits for and returns the host result of the last run_host call (None if none pending)."""
+        if self._pending_host is None:
+            return None
+        buf, ev = self._pending_host
+        self._pending_host = None
+        ev.synchronize()
+        return buf

@@ -88,21 +88,23 @@ class BatchFitter:
         """Stream key of problem (image b, slot j) in batch n: seed * 2^32 + n * P + b * J + j."""
         return self._base + (self.seed << 32) + self.batch_index * (B * self.J)
 
-    def fit_maps(self, obj_conf, frag_conf, frag_loc):
+    def fit_maps(self, obj_conf, frag_conf, frag_loc, after_extract=None):
         B = obj_conf.shape[0]
         self._prepare(B)
         bc = self.extract(obj_conf, frag_conf, frag_loc)
         self.corr = bc
+        if after_extract is not None:
+            after_extract()                       # the head maps are no longer needed from here on
         seeds = self.seeds_for(B)
         self.batch_index += 1
         poses, lab = self._fitter.fit(bc.coord_2d.view(-1, 2), bc.coord_3d.view(-1, 3), bc.offsets, bc.counts,
                                       self._Kdev, seeds, self._poses, self._labeling)
         return poses.view(B, self.J, 16)
 
-    def fit(self, predictions):
+    def fit(self, predictions, after_extract=None):
         from . import model
         return self.fit_maps(predictions[model.PRED_OBJ_CONF], predictions[model.PRED_FRAG_CONF],
-                             predictions[model.PRED_FRAG_LOC])
+                             predictions[model.PRED_FRAG_LOC], after_extract)
 
 
 def find6DPoses(x1y1, x2y2z2, K, threshold=4.0, max_model_number=-1, conf=0.5, proposal_engine_conf=1.0,

@@ -242,3 +242,39 @@ def test_engine_full_path_postprocessing_matches_oracle_on_its_own_maps():
     # second batch uses the next stream keys
     out2 = eng.run_device(img)
     assert eng._fitter.batch_index == 2
+
+
+def test_pipelined_engine_equals_serial_engine():
+    """pipelined=True overlaps pose fitting of batch i (side stream) with the CNN of batch i+1; every record must be
+    bit-identical to the serial engine's, for every batch, through run_device and through run_host/flush."""
+    from epos_b200 import engine, synthetic, weights as W
+    O, F, B = 3, 16, 2
+    w = W.random_init(O, F, seed=2, bn='random', logits_std=0.5)
+    store = synthetic.model_store(O, F)
+    K = synthetic.default_K()
+    imgs = [torch.from_numpy(W.synthetic_images(B, seed=20 + i, height=160, width=224)) for i in range(4)]
+    res = {}
+    for mode in (False, True):
+        eng = engine.Engine(w, O, F, DEV, stages=engine.STAGES_FULL, model_store=store, K=K, max_correspondences=1024,
+                            seed=4, pipelined=mode)
+        assert eng.pipelined == mode
+        outs = [eng.run_device(im.to(DEV)) for im in imgs]
+        eng.join()
+        torch.cuda.synchronize()
+        res[mode] = [o['poses'].cpu().numpy().copy() for o in outs]
+        host = []
+        for im in imgs:
+            r = eng.run_host(im.pin_memory())
+            if r is not None:
+                host.append(r.numpy().copy())
+        last = eng.flush()
+        if last is not None:
+            host.append(last.numpy().copy())
+        assert len(host) == len(imgs)
+        res[(mode, 'host')] = host
+    for a, b in zip(res[False], res[True]):
+        assert a.shape == (B, O, 16) and np.array_equal(a, b)
+    assert sum(float(r[..., 14].sum()) for r in res[False]) >= 1          # something was actually fitted
+    # run_host sees batches 4..7 of each engine's seed stream: same keys in both engines
+    for a, b in zip(res[(False, 'host')], res[(True, 'host')]):
+        assert np.array_equal(a, b)
