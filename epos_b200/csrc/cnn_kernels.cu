@@ -177,7 +177,7 @@ __device__ __forceinline__ void dw_strip(const float4* __restrict__ x0, int ld4,
 
 __global__ void __launch_bounds__(256, 3) dwconv3x3_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w,
                                                            const float* __restrict__ bias, float* __restrict__ y_f32,
-                                                           uint16_t* __restrict__ y_split, long long plane_stride,
+                                                           uint16_t* __restrict__ y_split, int ldy_split, long long plane_stride,
                                                            int B, int H, int W, int C, int Ho, int Wo, int stride, int rate,
                                                            int relu_in, int relu_out) {
   const int G = C >> 2;
@@ -228,8 +228,8 @@ __global__ void __launch_bounds__(256, 3) dwconv3x3_kernel(const float* __restri
       uint2 hi, lo;
       split_bf16x2(a.x, a.y, hi.x, lo.x);
       split_bf16x2(a.z, a.w, hi.y, lo.y);
-      *(reinterpret_cast<uint2*>(y_split + pix * C) + g) = hi;
-      *(reinterpret_cast<uint2*>(y_split + plane_stride + pix * C) + g) = lo;
+      *(reinterpret_cast<uint2*>(y_split + pix * ldy_split) + g) = hi;
+      *(reinterpret_cast<uint2*>(y_split + plane_stride + pix * ldy_split) + g) = lo;
     }
   }
 }
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(256, 3) dwconv3x3_kernel(const float* __restri
 // Variant A (flat): one thread = one output pixel x 4 channels, grid-stride; consecutive threads walk the channel axis.
 __global__ void __launch_bounds__(256) dwconv3x3_flat_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w,
                                                         const float* __restrict__ bias, float* __restrict__ y_f32,
-                                                        uint16_t* __restrict__ y_split, long long plane_stride,
+                                                        uint16_t* __restrict__ y_split, int ldy_split, long long plane_stride,
                                                         int B, int H, int W, int C, int Ho, int Wo, int stride, int rate,
                                                         int relu_in, int relu_out) {
   const int G = C >> 2;
@@ -599,9 +599,10 @@ int epos_conv3x3_dense(const float* x, const float* w, const float* bias, float*
   return EPOS_OK;
 }
 
-int epos_dwconv3x3(const float* x, int ldx, const float* w, const float* bias, float* y_f32, uint16_t* y_split, int B,
-                   int H, int W, int C, int stride, int rate, int relu_in, int relu_out, void* stream) {
+int epos_dwconv3x3(const float* x, int ldx, const float* w, const float* bias, float* y_f32, uint16_t* y_split,
+                   int ldy_split, int B, int H, int W, int C, int stride, int rate, int relu_in, int relu_out, void* stream) {
   EPOS_CHECK_ARG(x && w && bias && (y_f32 || y_split));
+  EPOS_CHECK_ARG(!y_split || (ldy_split >= C && (ldy_split % 4) == 0));
   EPOS_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && (C % 4) == 0 && (ldx % 4) == 0 && ldx >= C);
   EPOS_CHECK_ARG((stride == 1 || stride == 2) && rate >= 1);
   const int Ho = stride == 1 ? H : (H - 1) / 2 + 1, Wo = stride == 1 ? W : (W - 1) / 2 + 1;
@@ -613,17 +614,17 @@ int epos_dwconv3x3(const float* x, int ldx, const float* w, const float* bias, f
   if (variant < 0) { const char* e = getenv("EPOS_DW_VARIANT"); variant = e ? atoi(e) : 3; }
   if (variant == 3 && stride == 1) {
     // TMA-staged smem-tiled kernel (dw_tile.cu) for rate 1/2/4; other shapes use the register-strip kernel below
-    const int rc = dwconv3x3_tiled(x, ldx, w, bias, y_f32, y_split, B, H, W, C, rate, relu_in, relu_out, (cudaStream_t)stream);
+    const int rc = dwconv3x3_tiled(x, ldx, w, bias, y_f32, y_split, ldy_split, B, H, W, C, rate, relu_in, relu_out, (cudaStream_t)stream);
     if (rc != EPOS_ERR_UNSUPPORTED) return rc;
   }
   if (variant != 2) {
-    dwconv3x3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, w, bias, y_f32, y_split,
-                                                             (long long)B * Ho * Wo * C, B, H, W, C, Ho, Wo,
+    dwconv3x3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, w, bias, y_f32, y_split, ldy_split,
+                                                             (long long)B * Ho * Wo * ldy_split, B, H, W, C, Ho, Wo,
                                                              stride, rate, relu_in, relu_out);
   } else {
     const long long total = (long long)B * Ho * Wo * (C / 4);
-    dwconv3x3_flat_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, ldx, w, bias, y_f32, y_split,
-                                                                             (long long)B * Ho * Wo * C, B, H, W, C, Ho, Wo,
+    dwconv3x3_flat_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, ldx, w, bias, y_f32, y_split, ldy_split,
+                                                                             (long long)B * Ho * Wo * ldy_split, B, H, W, C, Ho, Wo,
                                                                              stride, rate, relu_in, relu_out);
   }
   EPOS_LAUNCH_CHECK();

@@ -39,8 +39,8 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n
   } while (0)
 
 // dw_tile.cu: TMA-staged tiled depthwise 3x3 (stride 1, rate 1/2/4); EPOS_ERR_UNSUPPORTED = use the strip kernel
-int dwconv3x3_tiled(const float* x, int ldx, const float* w, const float* bias, float* y_f32, uint16_t* y_split, int B,
-                    int H, int W, int C, int rate, int relu_in, int relu_out, cudaStream_t stream);
+int dwconv3x3_tiled(const float* x, int ldx, const float* w, const float* bias, float* y_f32, uint16_t* y_split,
+                    int ldy_split, int B, int H, int W, int C, int rate, int relu_in, int relu_out, cudaStream_t stream);
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

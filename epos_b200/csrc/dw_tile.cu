@@ -21,7 +21,8 @@ constexpr int DT_THREADS = 256;    // 8 channel groups x (4 strips per row x 8 r
 template <int R>
 __global__ void __launch_bounds__(DT_THREADS) dwconv3x3_tile_kernel(
     const __grid_constant__ CUtensorMap tmap, const float* __restrict__ w, const float* __restrict__ bias,
-    float* __restrict__ y_f32, uint16_t* __restrict__ y_split, long long plane_stride, int H, int W, int C, int TH,
+    float* __restrict__ y_f32, uint16_t* __restrict__ y_split, int ldy_split, long long plane_stride, int H, int W, int C,
+    int TH,
     int tiles_y, int slabs, int relu_in, int relu_out) {
   constexpr int IW = DT_TW + 2 * R;
   extern __shared__ __align__(128) uint8_t dt_smem[];
@@ -86,12 +87,13 @@ __global__ void __launch_bounds__(DT_THREADS) dwconv3x3_tile_kernel(
       a.x = fmaxf(a.x, out_floor); a.y = fmaxf(a.y, out_floor); a.z = fmaxf(a.z, out_floor); a.w = fmaxf(a.w, out_floor);
       const long long o = (pix0 + p) * C + c;
       if (y_f32) *reinterpret_cast<float4*>(y_f32 + o) = a;
+      const long long os = (pix0 + p) * ldy_split + c;
       if (y_split) {
         uint2 hi, lo;
         split_bf16x2(a.x, a.y, hi.x, lo.x);
         split_bf16x2(a.z, a.w, hi.y, lo.y);
-        *reinterpret_cast<uint2*>(y_split + o) = hi;
-        *reinterpret_cast<uint2*>(y_split + plane_stride + o) = lo;
+        *reinterpret_cast<uint2*>(y_split + os) = hi;
+        *reinterpret_cast<uint2*>(y_split + plane_stride + os) = lo;
       }
     }
   }
@@ -117,7 +119,7 @@ static int make_dw_map(CUtensorMap* map, const float* x, int ldx, int B, int H, 
 
 template <int R>
 static int launch_dw_tile(const CUtensorMap& map, const float* w, const float* bias, float* y_f32, uint16_t* y_split,
-                          int B, int H, int W, int C, int TH, int relu_in, int relu_out, cudaStream_t stream) {
+                          int ldy_split, int B, int H, int W, int C, int TH, int relu_in, int relu_out, cudaStream_t stream) {
   const int smem = (TH + 2 * R) * (DT_TW + 2 * R) * DT_SLAB * 4 + 128;
   static int attr = 0;
   if (smem > attr) {
@@ -126,7 +128,7 @@ static int launch_dw_tile(const CUtensorMap& map, const float* w, const float* b
   }
   const int tiles_y = ceil_div(H, TH), slabs = ceil_div(C, DT_SLAB);
   dim3 grid(ceil_div(W, DT_TW), tiles_y * B, slabs);
-  dwconv3x3_tile_kernel<R><<<grid, DT_THREADS, smem, stream>>>(map, w, bias, y_f32, y_split, (long long)B * H * W * C, H,
+  dwconv3x3_tile_kernel<R><<<grid, DT_THREADS, smem, stream>>>(map, w, bias, y_f32, y_split, ldy_split, (long long)B * H * W * ldy_split, H,
                                                               W, C, TH, tiles_y, slabs, relu_in, relu_out);
   EPOS_LAUNCH_CHECK();
   return EPOS_OK;
@@ -134,8 +136,8 @@ static int launch_dw_tile(const CUtensorMap& map, const float* w, const float* b
 
 // Returns EPOS_ERR_UNSUPPORTED (without setting an error) when the shape is not one this kernel handles; the caller
 // then uses the register-strip kernel in cnn_kernels.cu.
-int dwconv3x3_tiled(const float* x, int ldx, const float* w, const float* bias, float* y_f32, uint16_t* y_split, int B,
-                    int H, int W, int C, int rate, int relu_in, int relu_out, cudaStream_t stream) {
+int dwconv3x3_tiled(const float* x, int ldx, const float* w, const float* bias, float* y_f32, uint16_t* y_split,
+                    int ldy_split, int B, int H, int W, int C, int rate, int relu_in, int relu_out, cudaStream_t stream) {
   if (!(rate == 1 || rate == 2 || rate == 4)) return EPOS_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || (ldx % 4) != 0 || (C % 4) != 0) return EPOS_ERR_UNSUPPORTED;
   // tile height: a multiple of 4 in [8, 24] with the least padded rows (ties: the taller tile)
@@ -149,9 +151,9 @@ int dwconv3x3_tiled(const float* x, int ldx, const float* w, const float* bias, 
   int rc = make_dw_map(&map, x, ldx, B, H, W, C, TH, rate);
   if (rc) return rc;
   switch (rate) {
-    case 1: return launch_dw_tile<1>(map, w, bias, y_f32, y_split, B, H, W, C, TH, relu_in, relu_out, stream);
-    case 2: return launch_dw_tile<2>(map, w, bias, y_f32, y_split, B, H, W, C, TH, relu_in, relu_out, stream);
-    default: return launch_dw_tile<4>(map, w, bias, y_f32, y_split, B, H, W, C, TH, relu_in, relu_out, stream);
+    case 1: return launch_dw_tile<1>(map, w, bias, y_f32, y_split, ldy_split, B, H, W, C, TH, relu_in, relu_out, stream);
+    case 2: return launch_dw_tile<2>(map, w, bias, y_f32, y_split, ldy_split, B, H, W, C, TH, relu_in, relu_out, stream);
+    default: return launch_dw_tile<4>(map, w, bias, y_f32, y_split, ldy_split, B, H, W, C, TH, relu_in, relu_out, stream);
   }
 }
 

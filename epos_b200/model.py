@@ -187,10 +187,11 @@ class EposNet:
     def dwconv(self, x, B, H, W, C, ldx, wb, stride, rate, relu_in, relu_out, want_f32=False):
         Ho = H if stride == 1 else (H - 1) // 2 + 1
         Wo = W if stride == 1 else (W - 1) // 2 + 1
-        y_split = torch.empty((2, B * Ho * Wo, C), dtype=torch.bfloat16, device=self.dev)
+        ldy = (C + 15) // 16 * 16            # bf16 row pitch padded to 32 bytes (728 -> 736): sector-aligned rows
+        y_split = torch.empty((2, B * Ho * Wo, ldy), dtype=torch.bfloat16, device=self.dev)
         y32 = torch.empty((B * Ho * Wo, C), dtype=torch.float32, device=self.dev) if want_f32 else None
         _lib.check(self.lib.epos_dwconv3x3(x.data_ptr(), ldx, wb[0].data_ptr(), wb[1].data_ptr(), _lib.ptr(y32),
-                                           y_split.data_ptr(), B, H, W, C, stride, rate, int(relu_in), int(relu_out),
+                                           y_split.data_ptr(), ldy, B, H, W, C, stride, rate, int(relu_in), int(relu_out),
                                            self._s()), 'epos_dwconv3x3')
         return (y_split, y32, Ho, Wo) if want_f32 else (y_split, Ho, Wo)
 

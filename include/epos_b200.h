@@ -66,10 +66,12 @@ int epos_conv3x3_dense(const float* x, const float* w, const float* bias, float*
 /* Depthwise 3x3 conv (net_xception.py:167-177 separable_conv2d_same depthwise half; model.py:80-89):
  * optional ReLU on the input (xception_module pre-activation, net_xception.py:276), dilation `rate`,
  * stride 1 (TF SAME) or 2 (fixed_padding then VALID), folded BN bias, optional ReLU on the output.
- * x [B,H,W,ldx] f32 (first C channels used); w [9][C] f32; y_f32 [B,Ho,Wo,C] and/or y_split [2][B*Ho*Wo][C]
- * (either may be NULL). */
+ * x [B,H,W,ldx] f32 (first C channels used); w [9][C] f32; y_f32 [B,Ho,Wo,C] and/or
+ * y_split [2][B*Ho*Wo][ldy_split] (either may be NULL).  ldy_split >= C lets the caller pad the bf16 row
+ * pitch to a multiple of 32 bytes (C = 728: 736), which keeps the rows sector-aligned for this kernel's
+ * stores and for the TMA loads of the GEMM that consumes them. */
 int epos_dwconv3x3(const float* x, int ldx, const float* w, const float* bias,
-                   float* y_f32, uint16_t* y_split,
+                   float* y_f32, uint16_t* y_split, int ldy_split,
                    int B, int H, int W, int C, int stride, int rate, int relu_in, int relu_out,
                    void* stream);
 

@@ -10,11 +10,12 @@ for (B, H, W, C, stride, rate) in shapes:
     Ho, Wo = (H, W) if stride == 1 else ((H - 1) // 2 + 1, (W - 1) // 2 + 1)
     nb = 3
     xs = [torch.randn(B * H * W, C, device=dev) for _ in range(nb)]
-    ys = [torch.empty(2, B * Ho * Wo, C, dtype=torch.bfloat16, device=dev) for _ in range(nb)]
+    LDY = (C + 15) // 16 * 16
+    ys = [torch.empty(2, B * Ho * Wo, LDY, dtype=torch.bfloat16, device=dev) for _ in range(nb)]
     w = torch.randn(9, C, device=dev); b = torch.randn(C, device=dev)
     s = torch.cuda.current_stream().cuda_stream
     def run(i):
-        _lib.check(lib.epos_dwconv3x3(xs[i % nb].data_ptr(), C, w.data_ptr(), b.data_ptr(), None, ys[i % nb].data_ptr(), B, H, W, C, stride, rate, 1, 0, s), 'dw')
+        _lib.check(lib.epos_dwconv3x3(xs[i % nb].data_ptr(), C, w.data_ptr(), b.data_ptr(), None, ys[i % nb].data_ptr(), LDY, B, H, W, C, stride, rate, 1, 0, s), 'dw')
     for i in range(3): run(i)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

@@ -144,13 +144,15 @@ def test_dwconv(env, C, H, W, stride, rate, relu_in, relu_out):
     wd = torch.from_numpy(k[:, :, :, 0].reshape(9, C).copy()).to(dev)
     bd = torch.from_numpy(b).to(dev)
     y32 = torch.empty((B * Ho * Wo, C), device=dev)
-    ys = torch.empty((2, B * Ho * Wo, C), dtype=torch.bfloat16, device=dev)
-    _lib.check(lib.epos_dwconv3x3(xd.data_ptr(), C, wd.data_ptr(), bd.data_ptr(), y32.data_ptr(), ys.data_ptr(), B, H, W,
+    ldy = (C + 15) // 16 * 16                      # padded bf16 row pitch, as model.py allocates it
+    ys = torch.full((2, B * Ho * Wo, ldy), 7.0, dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.epos_dwconv3x3(xd.data_ptr(), C, wd.data_ptr(), bd.data_ptr(), y32.data_ptr(), ys.data_ptr(), ldy, B, H, W,
                                   C, stride, rate, int(relu_in), int(relu_out),
                                   torch.cuda.current_stream().cuda_stream), 'dw')
     torch.cuda.synchronize()
     assert rel_err(y32.cpu().numpy().reshape(ref.shape), ref) < 1e-5
-    assert rel_err((ys[0].float() + ys[1].float()).cpu().numpy().reshape(ref.shape), ref) < 3e-5
+    assert rel_err((ys[0, :, :C].float() + ys[1, :, :C].float()).cpu().numpy().reshape(ref.shape), ref) < 3e-5
+    assert bool((ys[:, :, C:] == 7.0).all())       # the pad columns are never written
 
 
 @pytest.mark.parametrize('B,H,W,C,N,rate,mode', [
