@@ -78,6 +78,10 @@ def default_workload():
 
 
 def workload_name(kind, B, O, F, backbone='xception_65'):
+    if (O, F) == (30, 256):
+        return ('BASELINE configs[4] per-GPU shape: batch=%d/GPU 640x480 synthetic RGB, random-init %s, 30 objects / 256 '
+                'fragments, %s' % (B, backbone, 'CNN-only forward' if kind == 'cnn' else
+                                   'full CNN + corresp + GC-RANSAC pose fitting'))
     if backbone != 'xception_65':
         return ('BASELINE configs[3]-shaped: batch=%d/GPU 640x480 synthetic RGB, random-init %s backbone, %d-object / '
                 '%d-fragment heads, %s' % (B, backbone, O, F, 'CNN-only forward' if kind == 'cnn' else
@@ -325,11 +329,19 @@ def run_ours(args, kind):
         except Exception:
             pass
         peak = peaks.get('bf16_tflops_sustained') or 1400.0
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'gemm_traffic.json')) as f:
+                tj = json.load(f)
+            traffic = {'dram_bytes_per_launch': tj['bytes_per_launch'], 'algorithmic_mb_per_launch': tj['algorithmic_mb_per_launch'],
+                       'source': tj['source']}
+        except Exception:
+            pass
         achieved = gemm_flop / (gemm_ms * 1e-3) / 1e12
         roof = {'bound': 'tensor', 'kernel': 'pw_gemm_kernel (tcgen05 split-bf16 pointwise conv, %d launches/step)'
                 % (len(evs) // nat), 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
                 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peaks else 'fallback',
-                'traffic': None,
+                'traffic': traffic,
                 'mma_issue_frac': 3.0 * achieved / peak,
                 'note': 'achieved = algorithmic fp32-equivalent FLOPs (2MNK per launch, SURVEY 8d) / summed per-launch '
                         'event time; each product costs 3 bf16 MMAs (error-compensated split), mma_issue_frac = 3x',
