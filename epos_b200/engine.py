@@ -36,6 +36,7 @@ class Engine:
         self.post_fit = post_fit                 # e.g. the NCCL all-gather of pose records (epos_b200/dist.py)
         self.pipelined = bool(pipelined) and stages == STAGES_FULL
         self._side = torch.cuda.Stream(device=self.dev) if self.pipelined else None
+        self._copy = torch.cuda.Stream(device=self.dev) if self.pipelined else None    # H2D of the next batch
         self._inflight = []                      # (maps kept alive, event after corresp) of batches still on the side stream
         self._last_fit = None                    # event after the most recent fit
         self._pending_host = None                # (pinned result, event) of the previous run_host call
@@ -95,7 +96,17 @@ class Engine:
         Serial engine: returns this batch's result.  Pipelined engine: the D2H of this batch is queued behind its pose
         fitting on the side stream and the call returns the PREVIOUS batch's result (None on the first call); flush()
         returns the last one -- the host always holds batch i while the GPU works on batch i+1."""
-        x = images_pinned.to(self.dev, non_blocking=True)
+        if self.pipelined:
+            # the copy engine brings batch i+1 in while the SMs are still busy with batch i
+            main = torch.cuda.current_stream(self.dev)
+            with torch.cuda.stream(self._copy):
+                x = images_pinned.to(self.dev, non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(self._copy)
+            main.wait_event(ev_in)
+            x.record_stream(main)
+        else:
+            x = images_pinned.to(self.dev, non_blocking=True)
         out = self.run_device(x)
         r = self.result_tensor(out)
         if not self.pipelined:
