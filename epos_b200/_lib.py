@@ -30,10 +30,10 @@ _SIGS = {
     'epos_conv3x3_rgb_s2': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     'epos_maxpool3x3_s2': (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
     'epos_subsample_f32': (i32, [vp, i32, vp, i32, i32, i32, i32, i32, vp]),
-    'epos_conv3x3_gemm': (i32, [vp, i32, sz, vp, vp, vp, i32, vp, i32, vp, i32, sz, i32, i32, i32, i32, i32, i32, i32, vp]),
+    'epos_conv3x3_gemm': (i32, [vp, i32, sz, vp, i32, vp, vp, i32, vp, i32, vp, i32, sz, i32, i32, i32, i32, i32, i32, i32, vp]),
     'epos_conv3x3_dense': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     'epos_dwconv3x3': (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
-    'epos_pwconv_gemm': (i32, [vp, i32, sz, vp, vp, i32, vp, i32, vp, i32, vp, i32, sz, i32, i32, i32, i32, vp]),
+    'epos_pwconv_gemm': (i32, [vp, i32, sz, vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, sz, i32, i32, i32, i32, vp]),
     'epos_pwconv_simt': (i32, [vp, i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp]),
     'epos_split_bf16': (i32, [vp, i32, vp, i32, sz, i32, i32, i32, i32, i32, i32, vp]),
     'epos_global_mean': (i32, [vp, vp, i32, i32, i32, vp]),

@@ -60,6 +60,23 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       : "memory");
 }
 
+// CTA-pair (cta_group::2) forms: one MMA spans the two SMs of a TPC (M = 256: each CTA's tensor core computes its 128
+// rows, each CTA's smem holds half of the N rows of W); commits arrive on the same barrier offset in both CTAs.
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // K-major operand tile with BLOCK_K bf16 per row: BLOCK_K = 64 -> rows of 128 B, 128-byte swizzle, 8-row groups 1024 B
 // apart; BLOCK_K = 32 -> rows of 64 B, 64-byte swizzle, 8-row groups 512 B apart.
 template <int BLOCK_K>
@@ -117,12 +134,12 @@ constexpr int CONV_TW = 16, CONV_TH = 8;
 // shared-memory queue.  The kernel therefore makes progress with however many CTAs are resident -- it can share the
 // GPU with the long-running pose-fitting CTAs of the previous batch (engine.py) instead of waiting for their SMs.
 struct PieceMap {
-  int n_tiles, bulk_end, block_n, unit, bpr, g0, num_pieces;
-  __device__ PieceMap(int m_tiles, int N, int block_n_) {
-    block_n = block_n_;
+  int n_tiles, bulk_end, block_n, unit, bpr, g0, num_pieces, tile_m;
+  // m_tiles row-tiles of tile_m rows (128, or 256 for a CTA pair); G = CTAs (or CTA pairs) sharing the work
+  __device__ PieceMap(int m_tiles, int N, int block_n_, int tile_m_, int G) {
+    block_n = block_n_; tile_m = tile_m_;
     n_tiles = (N + block_n - 1) / block_n;
     const int num_tiles = m_tiles * n_tiles;
-    const int G = gridDim.x;
     int rem = num_tiles % G;
     unit = block_n < 64 ? block_n : 64;
     const int upt = block_n / unit;
@@ -132,25 +149,26 @@ struct PieceMap {
     g0 = (bulk_end / n_tiles) * bpr + (bulk_end % n_tiles) * upt;
     num_pieces = bulk_end + (m_tiles * bpr - g0);
   }
-  // rows [m0, m0+128) x columns [n0, n0+n_cols) (n_cols may run past N: mask with N)
+  // rows [m0, m0+tile_m) x columns [n0, n0+n_cols) (n_cols may run past N: mask with N)
   __device__ void decode(int id, int& m0, int& n0, int& n_cols) const {
     if (id < bulk_end) {
-      m0 = (id / n_tiles) * BLOCK_M; n0 = (id % n_tiles) * block_n; n_cols = block_n;
+      m0 = (id / n_tiles) * tile_m; n0 = (id % n_tiles) * block_n; n_cols = block_n;
     } else {
       const int g = g0 + (id - bulk_end);
       const int row = g / bpr;
-      m0 = row * BLOCK_M; n0 = (g - row * bpr) * unit; n_cols = unit;
+      m0 = row * tile_m; n0 = (g - row * bpr) * unit; n_cols = unit;
     }
   }
 };
 constexpr int SCHED_DEPTH = 4;
 struct SchedSlot { int next, done; };               // global: next piece index, CTAs finished (the last one resets both)
 
-template <int BLOCK_N, int BLOCK_K>
+template <int BLOCK_N, int BLOCK_K, bool PAIR = false>
 struct GemmCfg {
   static constexpr int A_BYTES = 2 * BLOCK_M * BLOCK_K * 2;       // both planes
-  static constexpr int B_BYTES = 2 * BLOCK_N * BLOCK_K * 2;
-  static constexpr int B_BOX_ROWS = BLOCK_N < 64 ? BLOCK_N : 64;    // W is loaded in boxes of this many rows per plane
+  static constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;     // W rows per plane held by one CTA
+  static constexpr int B_BYTES = 2 * B_ROWS * BLOCK_K * 2;
+  static constexpr int B_BOX_ROWS = PAIR ? 32 : (BLOCK_N < 64 ? BLOCK_N : 64);   // small W box (rows per plane) for partial pieces
   static constexpr int B_BOX_BYTES = B_BOX_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES < 2 ? 2 : ((200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES);
@@ -159,12 +177,12 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers, piece queue*/ + STAGING_BYTES;
 };
 
-template <int BLOCK_N, int BLOCK_K>
+template <int BLOCK_N, int BLOCK_K, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                const __grid_constant__ CUtensorMap tmap_w64,
                const GemmEpilogue ep, const ConvGeom cg, SchedSlot* __restrict__ sched, int M, int N, int K, int dbg) {
-  using Cfg = GemmCfg<BLOCK_N, BLOCK_K>;
+  using Cfg = GemmCfg<BLOCK_N, BLOCK_K, PAIR>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment (128B swizzle atoms) by an offset from the __shared__ symbol, so that the compiler still knows
@@ -189,20 +207,34 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
   const int m_tiles = cg.enabled ? (M / (cg.H * cg.W)) * cg.tiles_x * cg.tiles_y : (M + BLOCK_M - 1) / BLOCK_M;
 
+  // CTA pair: rank 0 (leader) issues the MMAs and owns the barriers that both CTAs signal
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  constexpr int NCTA = PAIR ? 2 : 1;
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w64) : "memory");
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
-    for (int i = 0; i < SCHED_DEPTH; ++i) { mbar_init(&sched_full[i], 1); mbar_init(&sched_empty[i], 5); }   // MMA + 4 epilogue warps
+    // full: one arrive.expect_tx per producer; tmem_empty: 4 epilogue warps per CTA; sched_empty: every consumer of the
+    // piece queue (single CTA: MMA + 4 epilogue warps; pair: + the peer's producer and its 4 epilogue warps)
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], NCTA); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4 * NCTA); }
+    for (int i = 0; i < SCHED_DEPTH; ++i) { mbar_init(&sched_full[i], 1); mbar_init(&sched_empty[i], 5 * NCTA); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if constexpr (PAIR) cluster_sync_all();            // both CTAs' barriers exist before anything remote touches them
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
-                 "r"((uint32_t)Cfg::TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                   "r"((uint32_t)Cfg::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                   "r"((uint32_t)Cfg::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -214,24 +246,45 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const PieceMap pm(m_tiles, N, BLOCK_N);
+      const PieceMap pm(PAIR ? (m_tiles + 1) / 2 : m_tiles, N, BLOCK_N, PAIR ? 2 * BLOCK_M : BLOCK_M,
+                        PAIR ? gridDim.x / 2 : gridDim.x);
       int sslot = 0;
       uint32_t sphase = 0;
       int m0, n0, n_cols;
-      int id = atomicAdd(&sched->next, 1);
+      int id = leader ? atomicAdd(&sched->next, 1) : 0;
       while (true) {
-        // take the index after this one now: the atomic's round trip hides behind this piece's loads
-        const int id_next = id < pm.num_pieces ? atomicAdd(&sched->next, 1) : pm.num_pieces;
-        mbar_wait(&sched_empty[sslot], sphase ^ 1);
-        sched_ids[sslot] = id < pm.num_pieces ? id : -1;
-        mbar_arrive(&sched_full[sslot]);                            // release: publishes the index to the consumers
-        if (++sslot == SCHED_DEPTH) { sslot = 0; sphase ^= 1; }
-        if (id >= pm.num_pieces) break;
-        pm.decode(id, m0, n0, n_cols);
-        id = id_next;
+        if (leader) {
+          // take the index after this one now: the atomic's round trip hides behind this piece's loads
+          const int id_next = id < pm.num_pieces ? atomicAdd(&sched->next, 1) : pm.num_pieces;
+          mbar_wait(&sched_empty[sslot], sphase ^ 1);
+          const int pub = id < pm.num_pieces ? id : -1;
+          sched_ids[sslot] = pub;
+          if constexpr (PAIR) {
+            st_cluster_u32(mapa_u32(const_cast<int*>(&sched_ids[sslot]), 1), (uint32_t)pub);
+            mbar_arrive_cluster(mapa_u32(&sched_full[sslot], 1));     // release.cluster: publishes the index to the peer
+          }
+          mbar_arrive(&sched_full[sslot]);                            // release: publishes the index to the consumers
+          if (++sslot == SCHED_DEPTH) { sslot = 0; sphase ^= 1; }
+          if (id >= pm.num_pieces) break;
+          pm.decode(id, m0, n0, n_cols);
+          id = id_next;
+        } else {
+          // peer CTA of a pair: a consumer of the leader's piece queue
+          mbar_wait_cluster(&sched_full[sslot], sphase);
+          const int got = sched_ids[sslot];
+          mbar_arrive_cluster(mapa_u32(&sched_empty[sslot], 0));
+          if (++sslot == SCHED_DEPTH) { sslot = 0; sphase ^= 1; }
+          if (got < 0) break;
+          pm.decode(got, m0, n0, n_cols);
+        }
+        if constexpr (PAIR) m0 += (int)rank * BLOCK_M;               // this CTA's 128 rows of the 256-row tile
         int n_rows = N - n0;                                       // W rows this piece needs
         if (n_rows > n_cols) n_rows = n_cols;
         const bool full = n_cols == BLOCK_N;                        // whole tile: one box (rows past N are zero-filled)
+        // pair: this CTA holds rows [wn0, wn0 + umma_n/2) of W (umma_n = the pair's MMA width)
+        int wn0 = n0;
+        if constexpr (PAIR) wn0 = n0 + (int)rank * (((n_rows + 15) & ~15) >> 1);
+        const uint32_t full_addr = PAIR ? mapa_u32(&full_bar[0], 0) : 0u;   // leader's full barriers (cluster address)
         int cb = 0, cy0 = 0, cx0 = 0;
         if (cg.enabled) {
           const int t = m0 / BLOCK_M, per_img = cg.tiles_x * cg.tiles_y;
@@ -242,6 +295,22 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int n_boxes = (n_rows + Cfg::B_BOX_ROWS - 1) / Cfg::B_BOX_ROWS;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if constexpr (PAIR) {
+            const uint32_t fb = full_addr + (uint32_t)stage * 8u;
+            mbar_expect_tx_cluster(fb, Cfg::A_BYTES + (full ? Cfg::B_BYTES : 2 * Cfg::B_BOX_BYTES));
+            if (cg.enabled) {
+              const int tap = kb / cg.cpb, c0 = (kb - tap * cg.cpb) * BLOCK_K;
+              const int ky = tap / 3, kx = tap - ky * 3;
+              tma_load_5d_pair(smem_a + stage * Cfg::A_BYTES, &tmap_a, fb, c0, cx0 + (kx - 1) * cg.rate,
+                               cy0 + (ky - 1) * cg.rate, cb, 0);
+            } else {
+              tma_load_3d_pair(smem_a + stage * Cfg::A_BYTES, &tmap_a, fb, kb * BLOCK_K, m0, 0);
+            }
+            // whole tiles: one box of BLOCK_N/2 rows per plane; 64-column tail pieces: one box of 32 rows per plane
+            tma_load_3d_pair(smem_b + stage * Cfg::B_BYTES, full ? &tmap_w : &tmap_w64, fb, kb * BLOCK_K, wn0, 0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_expect_tx(&full_bar[stage], ((dbg & 128) ? 0 : Cfg::A_BYTES) + ((dbg & 64) ? 0 : (full ? Cfg::B_BYTES : 2 * n_boxes * Cfg::B_BOX_BYTES)));
           if (cg.enabled) {
             const int tap = kb / cg.cpb, c0 = (kb - tap * cg.cpb) * BLOCK_K;
@@ -266,13 +335,14 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (the leader CTA of a pair issues for both) =====================
+    if (lane == 0 && leader) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const PieceMap pm(m_tiles, N, BLOCK_N);
+      const PieceMap pm(PAIR ? (m_tiles + 1) / 2 : m_tiles, N, BLOCK_N, PAIR ? 2 * BLOCK_M : BLOCK_M,
+                        PAIR ? gridDim.x / 2 : gridDim.x);
       int sslot = 0;
       uint32_t sphase = 0;
       int m0, n0, n_cols;
@@ -287,7 +357,9 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (umma_n > n_cols) umma_n = n_cols;
         umma_n = (umma_n + 15) & ~15;                              // columns past the piece are computed but never stored
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(umma_n >> 3) << 17) |
-                               ((uint32_t)(BLOCK_M >> 4) << 24);
+                               ((uint32_t)((NCTA * BLOCK_M) >> 4) << 24);
+        // rows per plane of the W box this piece was loaded with (pair: half of the MMA width per CTA)
+        const int b_plane_rows = PAIR ? (n_cols == BLOCK_N ? BLOCK_N / 2 : Cfg::B_BOX_ROWS) : BLOCK_N;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
@@ -297,7 +369,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint32_t a_hi = smem_u32(smem_a + stage * Cfg::A_BYTES);
           const uint32_t a_lo = a_hi + BLOCK_M * BLOCK_K * 2;
           const uint32_t b_hi = smem_u32(smem_b + stage * Cfg::B_BYTES);
-          const uint32_t b_lo = b_hi + BLOCK_N * BLOCK_K * 2;
+          const uint32_t b_lo = b_hi + (uint32_t)b_plane_rows * BLOCK_K * 2;
           // the last K block of a ragged K (728 = 11 x 64 + 24) only needs the UMMA_K steps that hold data
           const int k_left = K - kb * BLOCK_K;
           const int k_steps = k_left >= BLOCK_K ? BLOCK_K / UMMA_K : (k_left + UMMA_K - 1) / UMMA_K;
@@ -308,15 +380,23 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint64_t da_hi = make_smem_desc<BLOCK_K>(a_hi + koff), da_lo = make_smem_desc<BLOCK_K>(a_lo + koff);
             const uint64_t db_hi = make_smem_desc<BLOCK_K>(b_hi + koff), db_lo = make_smem_desc<BLOCK_K>(b_lo + koff);
             if (dbg & 8) continue;
+            if constexpr (PAIR) {
+              umma_bf16_pair(tmem_d, da_lo, db_hi, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_bf16_pair(tmem_d, da_hi, db_lo, idesc, 1u);
+              umma_bf16_pair(tmem_d, da_hi, db_hi, idesc, 1u);
+              continue;
+            }
             umma_bf16(tmem_d, da_lo, db_hi, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             if (dbg & 16) continue;
             umma_bf16(tmem_d, da_hi, db_lo, idesc, 1u);
             umma_bf16(tmem_d, da_hi, db_hi, idesc, 1u);
           }
-          umma_commit(&empty_bar[stage]);            // frees the smem slot when the MMAs above retire
+          // frees the smem slot (in both CTAs of a pair) when the MMAs above retire
+          if constexpr (PAIR) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);                // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if constexpr (PAIR) umma_commit_pair(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -342,18 +422,22 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     float4* stg = reinterpret_cast<float4*>(staging + (warp - 2) * 1024);
     const int rsub = lane >> 3, jj = lane & 7;
     const float relu_floor = ep.relu ? 0.f : -INFINITY;
-    const PieceMap pm(m_tiles, N, BLOCK_N);
+    const PieceMap pm(PAIR ? (m_tiles + 1) / 2 : m_tiles, N, BLOCK_N, PAIR ? 2 * BLOCK_M : BLOCK_M,
+                        PAIR ? gridDim.x / 2 : gridDim.x);
     int sslot = 0;
     uint32_t sphase = 0;
     int m0, n0, n_cols;
     while (true) {
-      mbar_wait(&sched_full[sslot], sphase);
+      if constexpr (PAIR) mbar_wait_cluster(&sched_full[sslot], sphase); else mbar_wait(&sched_full[sslot], sphase);
       const int id = sched_ids[sslot];
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sched_empty[sslot]);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(&sched_empty[sslot], 0)); else mbar_arrive(&sched_empty[sslot]);
+      }
       if (++sslot == SCHED_DEPTH) { sslot = 0; sphase ^= 1; }
       if (id < 0) break;
       pm.decode(id, m0, n0, n_cols);
+      if constexpr (PAIR) m0 += (int)rank * BLOCK_M;
       int n_valid = N - n0;
       if (n_valid > n_cols) n_valid = n_cols;
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -365,10 +449,11 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int t = m0 / BLOCK_M, per_img = cg.tiles_x * cg.tiles_y;
         const int cb = t / per_img, q = t - cb * per_img;
         const int cy0 = (q / cg.tiles_x) * CONV_TH + quarter * 2, cx0 = (q % cg.tiles_x) * CONV_TW;
+        const bool tile_ok = t < m_tiles;             // the second half of the last CTA-pair tile may not exist
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int y = cy0 + (i >> 2), x = cx0 + 4 * (i & 3) + rsub;
-          mrow[i] = (y < cg.H && x < cg.W) ? ((long long)cb * cg.H + y) * cg.W + x : -1;
+          mrow[i] = (tile_ok && y < cg.H && x < cg.W) ? ((long long)cb * cg.H + y) * cg.W + x : -1;
         }
       } else {
 #pragma unroll
@@ -408,18 +493,19 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           float sum = 0.f;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float e0 = expf(__uint_as_float(r0[j]) - mx), e1 = expf(__uint_as_float(r1[j]) - mx);
+            const float e0 = __expf(__uint_as_float(r0[j]) - mx), e1 = __expf(__uint_as_float(r1[j]) - mx);
             r0[j] = __float_as_uint(e0); r1[j] = __float_as_uint(e1);
             sum += e0 + e1;
           }
+          const float inv = 1.0f / sum;               // one division per row; 2 ulp from e / sum, far inside the 1e-3 bound
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const uint32_t* r = h ? r1 : r0;
-              stg[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]) / sum, __uint_as_float(r[4 * j + 1]) / sum,
-                                                             __uint_as_float(r[4 * j + 2]) / sum, __uint_as_float(r[4 * j + 3]) / sum);
+              stg[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]) * inv, __uint_as_float(r[4 * j + 1]) * inv,
+                                                             __uint_as_float(r[4 * j + 2]) * inv, __uint_as_float(r[4 * j + 3]) * inv);
             }
             __syncwarp();
             const int col = n0 + c0 + 32 * h + jj * 4;
@@ -498,7 +584,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int t = m0 / BLOCK_M, per_img = cg.tiles_x * cg.tiles_y;
           const int cb = t / per_img, q = t - cb * per_img, r_ = quarter * 32 + lane;
           const int y = (q / cg.tiles_x) * CONV_TH + (r_ >> 4), x = (q % cg.tiles_x) * CONV_TW + (r_ & 15);
-          m = (y < cg.H && x < cg.W) ? ((long long)cb * cg.H + y) * cg.W + x : -1;
+          m = (t < m_tiles && y < cg.H && x < cg.W) ? ((long long)cb * cg.H + y) * cg.W + x : -1;
         }
         const float* brow = ep.bias ? ep.bias + (ep.bias_group_rows > 0 && m >= 0 ? (m / ep.bias_group_rows) * N : 0) : nullptr;
 #pragma unroll 1
@@ -536,7 +622,9 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(&tmem_empty[acc], 0)); else mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -551,10 +639,16 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       __threadfence();
     }
   }
+  if constexpr (PAIR) cluster_sync_all();            // the peer may still read its TMEM / signal barriers in this CTA
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
-                 : "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
+                   : "memory");
+    } else {
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
+                   : "memory");
+    }
   }
 }
 
@@ -598,22 +692,48 @@ static SchedSlot* sched_slot() {
   return ring[dev] + (seq[dev]++ % SCHED_RING);
 }
 
-template <int BLOCK_N, int BLOCK_K>
+template <int BLOCK_N, int BLOCK_K, bool PAIR>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mw64, const GemmEpilogue& ep,
                        const ConvGeom& cg, int M, int N, int K, cudaStream_t stream, int dbg) {
-  using Cfg = GemmCfg<BLOCK_N, BLOCK_K>;
+  using Cfg = GemmCfg<BLOCK_N, BLOCK_K, PAIR>;
   static bool attr = false;
+  static int max_pairs = 0;
+  auto kern = pw_gemm_kernel<BLOCK_N, BLOCK_K, PAIR>;
   if (!attr) {
-    EPOS_CUDA(cudaFuncSetAttribute(pw_gemm_kernel<BLOCK_N, BLOCK_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    EPOS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    if (PAIR) {
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(2 * (num_sms() / 2)); q.blockDim = dim3(NUM_THREADS); q.dynamicSmemBytes = Cfg::SMEM_BYTES;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      q.attrs = at; q.numAttrs = 1;
+      EPOS_CUDA(cudaOccupancyMaxActiveClusters(&max_pairs, kern, &q));
+      if (getenv("EPOS_GEMM_VERBOSE")) fprintf(stderr, "[epos] pw_gemm pair: max active clusters %d (SMs %d)\n", max_pairs, num_sms());
+      if (max_pairs <= 0) { set_error("pw_gemm: no CTA pair fits (cudaOccupancyMaxActiveClusters = %d)", max_pairs); return EPOS_ERR_CUDA; }
+    }
     attr = true;
   }
-  // one CTA per SM; with less than a wave of tiles the remainder logic of PieceMap spreads 64-column blocks
+  // one CTA (or CTA pair) per SM (TPC); with less than a wave of tiles PieceMap spreads 64-column blocks
   const long long m_tiles = cg.enabled ? (long long)(M / (cg.H * cg.W)) * cg.tiles_x * cg.tiles_y : ceil_div(M, BLOCK_M);
-  const long long blocks64 = m_tiles * ceil_div(N, BLOCK_N < 64 ? BLOCK_N : 64);
-  const int grid = blocks64 < num_sms() ? (int)blocks64 : num_sms();
+  const long long units = (PAIR ? (m_tiles + 1) / 2 : m_tiles) * ceil_div(N, BLOCK_N < 64 ? BLOCK_N : 64);
+  const int cap = PAIR ? max_pairs : num_sms();
+  const int n_units = units < cap ? (int)units : cap;
   SchedSlot* slot = sched_slot();
   if (!slot) { set_error("pw_gemm: cannot allocate the scheduler slots"); return EPOS_ERR_CUDA; }
-  pw_gemm_kernel<BLOCK_N, BLOCK_K><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mw, mw64, ep, cg, slot, M, N, K, dbg);
+  if (PAIR) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * n_units); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    EPOS_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mw, mw64, ep, cg, slot, M, N, K, dbg));
+    count_launch();
+    return EPOS_OK;
+  }
+  kern<<<n_units, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mw, mw64, ep, cg, slot, M, N, K, dbg);
   EPOS_LAUNCH_CHECK();
   return EPOS_OK;
 }
@@ -621,20 +741,30 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const CUten
 // W maps, epilogue descriptor and dispatch on the N tile shared by the pointwise and the 3x3 entry points.
 // K block = 64 bf16 (128-byte swizzle, 2 smem stages at BLOCK_N = 256).  A 32-wide K block (64-byte swizzle, 4 stages)
 // was measured 4-15 % slower on B200: the main loop is bound by L2->SM throughput, not by pipeline depth.
-static int run_gemm(const CUtensorMap& ma, const uint16_t* w_split, const float* bias, int bias_group_rows,
+static int run_gemm(const CUtensorMap& ma, const uint16_t* w_split, int ldw, const float* bias, int bias_group_rows,
                     const float* residual, int ldr, float* d_f32, int ldd, uint16_t* d_split, int ldd_split,
                     size_t d_plane_stride, const ConvGeom& cg, int M, int N, int K, int relu, cudaStream_t s) {
   EPOS_CHECK_ARG(!d_f32 || ldd >= N);
   EPOS_CHECK_ARG(!d_split || ldd_split >= N);
   EPOS_CHECK_ARG(!residual || ldr >= N);
   EPOS_CHECK_ARG(relu >= 0 && relu <= 2);
+  EPOS_CHECK_ARG(ldw >= K && (ldw % 8) == 0);
   const int bn = N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
   const char* de = getenv("EPOS_GEMM_DEBUG");   // developer A/B switches (scripts/dev_gemm.py); 0 in production
   const int dbg = de ? atoi(de) : 0;
+  // CTA pairs (cta_group::2, 256 x 256 tiles, each CTA holds half of the W tile).  Measured on B200 (scripts/dev_gemm.py,
+  // profiles/gemm_ab_r01h.log): 3-4 % faster than single CTAs on the deep-K layers (K >= 1024: exit flow, ASPP), 5-8 %
+  // slower on K = 728 and on the K = 256 heads, where the per-tile hand-shakes between the two SMs are not amortised.
+  // EPOS_GEMM_PAIR = 0 / 2 forces single CTAs / pairs wherever BLOCK_N = 256.
+  static int pair_env = -1;
+  if (pair_env < 0) { const char* e = getenv("EPOS_GEMM_PAIR"); pair_env = e ? atoi(e) : 1; }
+  const long long m_tiles = cg.enabled ? (long long)(M / (cg.H * cg.W)) * cg.tiles_x * cg.tiles_y : ceil_div(M, BLOCK_M);
+  const bool pair = pair_env && bn == 256 && m_tiles >= 2 && (K >= 1024 || pair_env == 2);
   CUtensorMap mw, mw64;
-  int rc = make_map(&mw, w_split, N, K, K, (size_t)N * K, bn, GEMM_BK, 2);
+  int rc = make_map(&mw, w_split, N, K, ldw, (size_t)N * ldw, pair ? bn / 2 : bn, GEMM_BK, 2);
   if (rc) return rc;
-  rc = make_map(&mw64, w_split, N, K, K, (size_t)N * K, bn < 64 ? bn : 64, GEMM_BK, 1);
+  rc = pair ? make_map(&mw64, w_split, N, K, ldw, (size_t)N * ldw, 32, GEMM_BK, 2)
+            : make_map(&mw64, w_split, N, K, ldw, (size_t)N * ldw, bn < 64 ? bn : 64, GEMM_BK, 1);
   if (rc) return rc;
   GemmEpilogue ep;
   ep.bias = bias; ep.residual = residual; ep.d_f32 = d_f32; ep.d_split = d_split;
@@ -645,11 +775,12 @@ static int run_gemm(const CUtensorMap& ma, const uint16_t* w_split, const float*
     EPOS_CHECK_ARG(d_f32 && !d_split && !residual && bias_group_rows == 0 && (N % 64) == 0 && (ldd % 4) == 0 &&
                    (reinterpret_cast<uintptr_t>(d_f32) & 15) == 0 && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0));
   }
+  if (pair) return launch_gemm<256, GEMM_BK, true>(ma, mw, mw64, ep, cg, M, N, K, s, dbg);
   switch (bn) {
-    case 256: return launch_gemm<256, GEMM_BK>(ma, mw, mw64, ep, cg, M, N, K, s, dbg);
-    case 128: return launch_gemm<128, GEMM_BK>(ma, mw, mw64, ep, cg, M, N, K, s, dbg);
-    case 64: return launch_gemm<64, GEMM_BK>(ma, mw, mw64, ep, cg, M, N, K, s, dbg);
-    default: return launch_gemm<32, GEMM_BK>(ma, mw, mw64, ep, cg, M, N, K, s, dbg);
+    case 256: return launch_gemm<256, GEMM_BK, false>(ma, mw, mw64, ep, cg, M, N, K, s, dbg);
+    case 128: return launch_gemm<128, GEMM_BK, false>(ma, mw, mw64, ep, cg, M, N, K, s, dbg);
+    case 64: return launch_gemm<64, GEMM_BK, false>(ma, mw, mw64, ep, cg, M, N, K, s, dbg);
+    default: return launch_gemm<32, GEMM_BK, false>(ma, mw, mw64, ep, cg, M, N, K, s, dbg);
   }
 }
 
@@ -676,7 +807,7 @@ static int make_conv_map(CUtensorMap* map, const uint16_t* x, int B, int H, int 
 
 using namespace epos;
 
-extern "C" int epos_pwconv_gemm(const uint16_t* a_split, int lda, size_t a_plane_stride, const uint16_t* w_split,
+extern "C" int epos_pwconv_gemm(const uint16_t* a_split, int lda, size_t a_plane_stride, const uint16_t* w_split, int ldw,
                                 const float* bias, int bias_group_rows, const float* residual, int ldr, float* d_f32,
                                 int ldd, uint16_t* d_split, int ldd_split, size_t d_plane_stride, int M, int N, int K,
                                 int relu, void* stream) {
@@ -688,11 +819,11 @@ extern "C" int epos_pwconv_gemm(const uint16_t* a_split, int lda, size_t a_plane
   int rc = make_map(&ma, a_split, M, K, lda, a_plane_stride, BLOCK_M, GEMM_BK, 2);
   if (rc) return rc;
   ConvGeom cg = {};
-  return run_gemm(ma, w_split, bias, bias_group_rows, residual, ldr, d_f32, ldd, d_split, ldd_split, d_plane_stride, cg,
+  return run_gemm(ma, w_split, ldw, bias, bias_group_rows, residual, ldr, d_f32, ldd, d_split, ldd_split, d_plane_stride, cg,
                   M, N, K, relu, (cudaStream_t)stream);
 }
 
-extern "C" int epos_conv3x3_gemm(const uint16_t* x_split, int ldx, size_t x_plane_stride, const uint16_t* w_split,
+extern "C" int epos_conv3x3_gemm(const uint16_t* x_split, int ldx, size_t x_plane_stride, const uint16_t* w_split, int ldw,
                                  const float* bias, const float* residual, int ldr, float* d_f32, int ldd,
                                  uint16_t* d_split, int ldd_split, size_t d_plane_stride, int B, int H, int W, int C,
                                  int N, int rate, int relu, void* stream) {
@@ -707,6 +838,6 @@ extern "C" int epos_conv3x3_gemm(const uint16_t* x_split, int ldx, size_t x_plan
   ConvGeom cg;
   cg.enabled = 1; cg.H = H; cg.W = W; cg.tiles_x = ceil_div(W, CONV_TW); cg.tiles_y = ceil_div(H, CONV_TH);
   cg.rate = rate; cg.cpb = C / GEMM_BK;
-  return run_gemm(ma, w_split, bias, 0, residual, ldr, d_f32, ldd, d_split, ldd_split, d_plane_stride, cg, B * H * W, N,
+  return run_gemm(ma, w_split, ldw, bias, 0, residual, ldr, d_f32, ldd, d_split, ldd_split, d_plane_stride, cg, B * H * W, N,
                   9 * C, relu, (cudaStream_t)stream);
 }

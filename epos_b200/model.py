@@ -62,11 +62,14 @@ def _bn_fold(w, scope, eps):
     return scale, b - m * scale
 
 
-def _split(t):
-    """f32 [N,K] -> bf16 [2,N,K] (hi, lo)."""
+def _split(t, ld=None):
+    """f32 [N,K] -> bf16 [2,N,ld] (hi, lo), zero-padded to a row pitch of ld >= K elements."""
     hi = t.to(torch.bfloat16)
     lo = (t - hi.float()).to(torch.bfloat16)
-    return torch.stack([hi, lo]).contiguous()
+    out = torch.stack([hi, lo])
+    if ld is not None and ld != t.shape[1]:
+        out = torch.nn.functional.pad(out, (0, ld - t.shape[1]))
+    return out.contiguous()
 
 
 class Gemm:
@@ -75,7 +78,8 @@ class Gemm:
     def __init__(self, w_nk, bias, device, keep_f32):
         w32 = torch.from_numpy(np.ascontiguousarray(w_nk, dtype=np.float32)).to(device)
         self.N, self.K = w32.shape
-        self.w_split = _split(w32)
+        self.ldw = (self.K + 63) // 64 * 64          # weight rows padded to 128 B: aligned TMA rows (728 -> 768)
+        self.w_split = _split(w32, self.ldw)
         self.w_f32 = w32 if keep_f32 else None
         self.bias = None if bias is None else torch.from_numpy(np.ascontiguousarray(bias, dtype=np.float32)).to(device)
 
@@ -197,8 +201,9 @@ class EposNet:
 
     def split(self, x, B, H, W, C, ldx, subsample=1, relu=False):
         Ho, Wo = (H - 1) // subsample + 1, (W - 1) // subsample + 1
-        y = torch.empty((2, B * Ho * Wo, C), dtype=torch.bfloat16, device=self.dev)
-        _lib.check(self.lib.epos_split_bf16(x.data_ptr(), ldx, y.data_ptr(), C, y[0].numel(), B, H, W, C, subsample,
+        ldy = (C + 15) // 16 * 16            # 32-byte aligned bf16 rows (see dwconv)
+        y = torch.empty((2, B * Ho * Wo, ldy), dtype=torch.bfloat16, device=self.dev)
+        _lib.check(self.lib.epos_split_bf16(x.data_ptr(), ldx, y.data_ptr(), ldy, y[0].numel(), B, H, W, C, subsample,
                                             int(relu), self._s()), 'epos_split_bf16')
         return y
 
@@ -236,7 +241,7 @@ class EposNet:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
         _lib.check(self.lib.epos_pwconv_gemm(
-            a_split.data_ptr(), lda, a_split.stride(0), g.w_split.data_ptr(), _lib.ptr(bias_t), bias_group_rows,
+            a_split.data_ptr(), lda, a_split.stride(0), g.w_split.data_ptr(), g.ldw, _lib.ptr(bias_t), bias_group_rows,
             _lib.ptr(residual), 0 if residual is None else residual.shape[-1],
             _lib.ptr(d_f32), ldd or 0, _lib.ptr(d_split), ldd_split or 0, plane, M, N, K, int(relu), self._s()),
             'epos_pwconv_gemm')
@@ -255,7 +260,7 @@ class EposNet:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
         _lib.check(self.lib.epos_conv3x3_gemm(
-            x_split.data_ptr(), x_split.shape[2], x_split.stride(0), g.w_split.data_ptr(), _lib.ptr(g.bias), None, 0,
+            x_split.data_ptr(), x_split.shape[2], x_split.stride(0), g.w_split.data_ptr(), g.ldw, _lib.ptr(g.bias), None, 0,
             _lib.ptr(d), N, _lib.ptr(ds), N, 0 if ds is None else ds.stride(0), B, H, W, C, N, rate, int(relu),
             self._s()), 'epos_conv3x3_gemm')
         if ev is not None:

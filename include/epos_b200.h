@@ -80,7 +80,8 @@ int epos_dwconv3x3(const float* x, int ldx, const float* w, const float* bias,
  *   D[m][n] = act( sum_k A[m][k] * Wt[n][k] + bias[(m / bias_group_rows)][n] ) (+ residual[m][n])
  * Replaces slim.conv2d 1x1 + BatchNorm (+ReLU) (+ residual add), net_xception.py:178-182,297-313,
  * model.py:90-97,223-258,350-352,448-456.
- * a_split [2][M][lda] bf16; w_split [2][N][K] bf16; bias [groups][N] f32 (bias_group_rows = 0: one row);
+ * a_split [2][M][lda] bf16; w_split [2][N][ldw] bf16 (ldw >= K; a row pitch that is a multiple of 128 bytes
+ * -- K = 728 stored with ldw = 768 -- keeps the TMA rows aligned: measured 131 -> 109 us on the 728-channel layers); bias [groups][N] f32 (bias_group_rows = 0: one row);
  * residual f32 with leading dim ldr or NULL; outputs: d_f32 (leading dim ldd) and/or d_split
  * ([2][M][ldd_split], plane stride = split_plane_stride elements), either may be NULL.
  * relu: 0 = identity, 1 = ReLU (after the residual add, as the ResNet bottleneck needs,
@@ -88,7 +89,7 @@ int epos_dwconv3x3(const float* x, int ldx, const float* w, const float* bias,
  * epilogue (tf.nn.softmax over the fragment axis, model.py:676-678; needs N % 64 == 0, f32 output only,
  * no residual). */
 int epos_pwconv_gemm(const uint16_t* a_split, int lda, size_t a_plane_stride,
-                     const uint16_t* w_split, const float* bias, int bias_group_rows,
+                     const uint16_t* w_split, int ldw, const float* bias, int bias_group_rows,
                      const float* residual, int ldr,
                      float* d_f32, int ldd,
                      uint16_t* d_split, int ldd_split, size_t d_plane_stride,
@@ -100,9 +101,9 @@ int epos_pwconv_gemm(const uint16_t* a_split, int lda, size_t a_plane_stride,
  * Replaces resnet_utils.conv2d_same (external/slim/nets/resnet_utils.py:77-122) at stride 1 as used by
  * net_resnet_v1_beta.py:85,108-110; a stride-2 conv2d_same equals this followed by subsampling
  * (resnet_v1_test.py:72-149).  x_split [2][B,H,W,ldx] bf16 (C % 64 == 0);
- * w_split [2][N][9*C] bf16 with k = (ky*3+kx)*C + c; outputs and residual are indexed by the output
+ * w_split [2][N][ldw] bf16 (ldw >= 9*C) with k = (ky*3+kx)*C + c; outputs and residual are indexed by the output
  * pixel (b*H + y)*W + x as in epos_pwconv_gemm.  relu: 0 / 1 (applied after the residual add). */
-int epos_conv3x3_gemm(const uint16_t* x_split, int ldx, size_t x_plane_stride, const uint16_t* w_split,
+int epos_conv3x3_gemm(const uint16_t* x_split, int ldx, size_t x_plane_stride, const uint16_t* w_split, int ldw,
                       const float* bias, const float* residual, int ldr, float* d_f32, int ldd,
                       uint16_t* d_split, int ldd_split, size_t d_plane_stride,
                       int B, int H, int W, int C, int N, int rate, int relu, void* stream);

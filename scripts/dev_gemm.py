@@ -20,6 +20,8 @@ SHAPES = [  # M, N, K, residual, f32 out, split out, name
 ]
 flags = [int(a) for a in sys.argv[1:]] or [0, 1, 2, 6, 8, 16]
 only = os.environ.get('SHAPES')
+if os.environ.get('CUSTOM'):
+    SHAPES = [tuple(int(v) for v in c.split('x')) + (False, True, False, c) for c in os.environ['CUSTOM'].split(',')]
 
 
 def split(t):
@@ -30,9 +32,11 @@ def split(t):
 def run(M, N, K, res, f32, spl, nbuf=3, iters=6):
     g = torch.Generator(device='cuda').manual_seed(0)
     a32 = [torch.randn(M, K, device=dev, generator=g) for _ in range(nbuf)]
-    a = [split(t) for t in a32]
+    LDA = (K + int(os.environ.get('PADA', '16')) - 1) // int(os.environ.get('PADA', '16')) * int(os.environ.get('PADA', '16'))
+    a = [torch.nn.functional.pad(split(t), (0, LDA - K)).contiguous() for t in a32]
     w32 = torch.randn(N, K, device=dev, generator=g) * 0.05
-    w = split(w32)
+    LDW = (K + 63) // 64 * 64 if os.environ.get('PADW', '1') == '1' else K
+    w = torch.nn.functional.pad(split(w32), (0, LDW - K)).contiguous()
     bias = torch.randn(N, device=dev, generator=g)
     r = [torch.randn(M, N, device=dev, generator=g) for _ in range(nbuf)] if res else None
     d = [torch.empty(M, N, device=dev) for _ in range(nbuf)] if f32 else None
@@ -40,7 +44,7 @@ def run(M, N, K, res, f32, spl, nbuf=3, iters=6):
     s = torch.cuda.current_stream().cuda_stream
 
     def call(i):
-        _lib.check(lib.epos_pwconv_gemm(a[i].data_ptr(), K, a[i].stride(0), w.data_ptr(), bias.data_ptr(), 0,
+        _lib.check(lib.epos_pwconv_gemm(a[i].data_ptr(), LDA, a[i].stride(0), w.data_ptr(), LDW, bias.data_ptr(), 0,
                                         r[i].data_ptr() if res else None, N, d[i].data_ptr() if f32 else None, N,
                                         ds[i].data_ptr() if spl else None, N, ds[i].stride(0) if spl else 0,
                                         M, N, K, 1, s), 'gemm')

@@ -45,7 +45,7 @@ def test_pw_gemm(env, M, N, K, mode):
     a_s, w_s = split(a), split(w)
     d = torch.full((M, N), float('nan'), device=dev) if mode != 'split_out' else None
     ds = torch.zeros((2, M, N), dtype=torch.bfloat16, device=dev) if mode == 'split_out' else None
-    rc = lib.epos_pwconv_gemm(a_s.data_ptr(), K, a_s.stride(0), w_s.data_ptr(), bias.data_ptr(), 0,
+    rc = lib.epos_pwconv_gemm(a_s.data_ptr(), K, a_s.stride(0), w_s.data_ptr(), K, bias.data_ptr(), 0,
                               _lib.ptr(res), N, _lib.ptr(d), N, _lib.ptr(ds), N, 0 if ds is None else ds.stride(0),
                               M, N, K, int(relu), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, 'gemm')
@@ -67,7 +67,7 @@ def test_pw_gemm_fused_softmax64(env, M, N, K):
     ref = torch.softmax((a.double() @ w.double().T + bias.double()).view(M, N // 64, 64), dim=-1).view(M, N)
     a_s, w_s = split(a), split(w)
     d = torch.full((M, N), float('nan'), device=dev)
-    rc = lib.epos_pwconv_gemm(a_s.data_ptr(), K, a_s.stride(0), w_s.data_ptr(), bias.data_ptr(), 0, None, 0,
+    rc = lib.epos_pwconv_gemm(a_s.data_ptr(), K, a_s.stride(0), w_s.data_ptr(), K, bias.data_ptr(), 0, None, 0,
                               d.data_ptr(), N, None, 0, 0, M, N, K, 2, torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, 'gemm')
     torch.cuda.synchronize()
@@ -85,7 +85,7 @@ def test_pw_gemm_balanced_pieces_cover_everything(env):
         w = torch.randn(N, K, device=dev) * 0.1
         a_s, w_s = split(a), split(w)
         buf = torch.full((M + 3, N + 8), float('nan'), device=dev)
-        rc = lib.epos_pwconv_gemm(a_s.data_ptr(), K, a_s.stride(0), w_s.data_ptr(), None, 0, None, 0,
+        rc = lib.epos_pwconv_gemm(a_s.data_ptr(), K, a_s.stride(0), w_s.data_ptr(), K, None, 0, None, 0,
                                   buf.data_ptr(), N + 8, None, 0, 0, M, N, K, 0, torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, 'gemm')
         torch.cuda.synchronize()
@@ -104,7 +104,7 @@ def test_pw_gemm_grouped_bias_and_slices(env):
     bias = torch.randn(G, N, device=dev)
     buf = torch.zeros(M, 304, device=dev)
     a_s, w_s = split(a), split(w)
-    rc = lib.epos_pwconv_gemm(a_s.data_ptr(), K, a_s.stride(0), w_s.data_ptr(), bias.data_ptr(), M // G, None, 0,
+    rc = lib.epos_pwconv_gemm(a_s.data_ptr(), K, a_s.stride(0), w_s.data_ptr(), K, bias.data_ptr(), M // G, None, 0,
                               buf[:, 256:].data_ptr(), 304, None, 0, 0, M, N, K, 1,
                               torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, 'gemm')
@@ -182,7 +182,7 @@ def test_conv3x3_gemm(env, B, H, W, C, N, rate, mode):
     rd = torch.from_numpy(res).to(dev).view(B * H * W, N) if res is not None else None
     d = torch.full((B * H * W, N), float('nan'), device=dev) if mode != 'split' else None
     ds = torch.zeros((2, B * H * W, N), dtype=torch.bfloat16, device=dev) if mode == 'split' else None
-    rc = lib.epos_conv3x3_gemm(xs.data_ptr(), C, xs.stride(0), ws.data_ptr(), bd.data_ptr(), _lib.ptr(rd), N,
+    rc = lib.epos_conv3x3_gemm(xs.data_ptr(), C, xs.stride(0), ws.data_ptr(), 9 * C, bd.data_ptr(), _lib.ptr(rd), N,
                                _lib.ptr(d), N, _lib.ptr(ds), N, 0 if ds is None else ds.stride(0), B, H, W, C, N, rate,
                                int(mode != 'plain'), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, 'conv3x3_gemm')
