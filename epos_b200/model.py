@@ -208,14 +208,16 @@ class EposNet:
         return y
 
     def gemm(self, a_split, g, M, relu, residual=None, out_f32=True, out_split=False, d_f32=None, ldd=None,
-             d_split=None, ldd_split=None, bias=None, bias_group_rows=0, a_f32=None):
+             d_split=None, ldd_split=None, bias=None, bias_group_rows=0, a_f32=None, pad_f32=True):
         """a_split [2,M,lda] bf16.  Returns (d_f32 or None, d_split or None)."""
         lda = a_split.shape[2]
         N, K = g.N, g.K
         bias_t = g.bias if bias is None else bias
         if out_f32 and d_f32 is None:
-            d_f32 = torch.empty((M, N), dtype=torch.float32, device=self.dev)
-            ldd = N
+            # f32 activations with 128-byte aligned rows (728 -> 736 channels of pitch): the depthwise kernel's TMA boxes
+            # (128 B of one pixel) then never straddle a line.  Only the 728-channel layers are affected.
+            ldd = (N + 31) // 32 * 32 if (pad_f32 and N >= 64) else N
+            d_f32 = torch.empty((M, ldd), dtype=torch.float32, device=self.dev)
         if out_split and d_split is None:
             d_split = torch.empty((2, M, N), dtype=torch.bfloat16, device=self.dev)
             ldd_split = N
@@ -283,7 +285,7 @@ class EposNet:
                 _lib.check(self.lib.epos_subsample_f32(x32.data_ptr(), cin, shortcut.data_ptr(), B, H, W, cin, stride,
                                                        self._s()), 'epos_subsample_f32')
         else:
-            xsc = xs if stride == 1 else self.split(x32, B, H, W, cin, cin, subsample=stride)
+            xsc = xs if stride == 1 else self.split(x32, B, H, W, cin, x32.shape[1], subsample=stride)
             shortcut, _ = self.gemm(xsc, p[base + '/shortcut'], Mo, relu=False)
         _, r1 = self.gemm(xs, p[base + '/conv1'], M, relu=True, out_f32=False, out_split=True)
         if stride == 1:
@@ -348,13 +350,13 @@ class EposNet:
         r, c, h, w = x, cin, H, W
         for i in range(3):
             s = stride if i == 2 else 1
-            a, ho, wo = self.dwconv(r, B, h, w, c, c, self.p['%s/dw%d' % (base, i)], s, rate,
+            a, ho, wo = self.dwconv(r, B, h, w, c, r.shape[1], self.p['%s/dw%d' % (base, i)], s, rate,
                                     relu_in=not relu_inside, relu_out=relu_inside)
             M = B * ho * wo
             g = self.p['%s/pw%d' % (base, i)]
             res = None
             if i == 2 and skip == 'conv':
-                xs = self.split(x, B, H, W, cin, cin, subsample=stride)
+                xs = self.split(x, B, H, W, cin, x.shape[1], subsample=stride)
                 res, _ = self.gemm(xs, self.p[base + '/shortcut'], M, relu=False)
             elif i == 2 and skip == 'sum':
                 res = x
@@ -408,7 +410,7 @@ class EposNet:
             xs = self.split(x, B, h, w, c, c)
         self.gemm(xs, p['aspp0'], M, relu=True, out_f32=False, d_split=cat, ldd_split=256 * nb)
         for i, r_ in enumerate(self.opts.atrous_rates, 1):
-            a, _, _ = self.dwconv(x, B, h, w, c, c, p['aspp%d_dw' % i], 1, r_, relu_in=False, relu_out=True)
+            a, _, _ = self.dwconv(x, B, h, w, c, x.shape[1], p['aspp%d_dw' % i], 1, r_, relu_in=False, relu_out=True)
             self.gemm(a, p['aspp%d_pw' % i], M, relu=True, out_f32=False, d_split=cat[:, :, 256 * i:],
                       ldd_split=256 * nb)
         aspp, _ = self.gemm(cat, p['concat_proj'], M, relu=True, bias=cp_bias, bias_group_rows=h * w)
@@ -421,12 +423,12 @@ class EposNet:
         if (sh, sw) != (dh_, dw_):
             raise NotImplementedError('skip feature %dx%d != decoder size %dx%d' % (sh, sw, dh_, dw_))
         Md = B * dh_ * dw_
-        dcat = torch.empty((Md, 304), dtype=torch.float32, device=self.dev)
-        ss = self.split(skip, B, sh, sw, sc, sc)
-        self.gemm(ss, p['feature_projection0'], Md, relu=True, d_f32=dcat[:, 256:], ldd=304)
-        _lib.check(lib.epos_resize_bilinear(aspp.data_ptr(), dcat.data_ptr(), 304, B, h, w, dh_, dw_, 256, self._s()),
+        dcat = torch.empty((Md, 320), dtype=torch.float32, device=self.dev)       # 304 channels, 128-byte aligned rows
+        ss = self.split(skip, B, sh, sw, sc, skip.shape[1])
+        self.gemm(ss, p['feature_projection0'], Md, relu=True, d_f32=dcat[:, 256:], ldd=320)
+        _lib.check(lib.epos_resize_bilinear(aspp.data_ptr(), dcat.data_ptr(), 320, B, h, w, dh_, dw_, 256, self._s()),
                    'epos_resize_bilinear')
-        a, _, _ = self.dwconv(dcat, B, dh_, dw_, 304, 304, p['decoder_conv0_dw'], 1, 1, False, True)
+        a, _, _ = self.dwconv(dcat, B, dh_, dw_, 304, 320, p['decoder_conv0_dw'], 1, 1, False, True)
         y0, _ = self.gemm(a, p['decoder_conv0_pw'], Md, relu=True)
         a, _, _ = self.dwconv(y0, B, dh_, dw_, 256, 256, p['decoder_conv1_dw'], 1, 1, False, True)
         y1, y1s = self.gemm(a, p['decoder_conv1_pw'], Md, relu=True, out_f32=self.keep_f32, out_split=True)
@@ -437,10 +439,10 @@ class EposNet:
         """Logit heads + softmax/argmax in materialising mode (model.py:448-456, 676-685)."""
         M = B * h * w
         O, F = self.O, self.F
-        obj, _ = self.gemm(feat_split, self.p['logits/' + PRED_OBJ_CONF], M, relu=False)
+        obj, _ = self.gemm(feat_split, self.p['logits/' + PRED_OBJ_CONF], M, relu=False, pad_f32=False)
         fused = F % 64 == 0 and self.impl == 'tcgen05'      # softmax over F in the GEMM epilogue (relu = 2)
-        fc, _ = self.gemm(feat_split, self.p['logits/' + PRED_FRAG_CONF], M, relu=2 if fused else False)
-        fl, _ = self.gemm(feat_split, self.p['logits/' + PRED_FRAG_LOC], M, relu=False)
+        fc, _ = self.gemm(feat_split, self.p['logits/' + PRED_FRAG_CONF], M, relu=2 if fused else False, pad_f32=False)
+        fl, _ = self.gemm(feat_split, self.p['logits/' + PRED_FRAG_LOC], M, relu=False, pad_f32=False)
         labels = torch.empty((M,), dtype=torch.int64, device=self.dev)
         _lib.check(self.lib.epos_softmax_rows(obj.data_ptr(), labels.data_ptr(), M, O + 1, self._s()), 'epos_softmax_rows')
         if not fused:
