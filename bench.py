@@ -241,6 +241,9 @@ def run_ours(args, kind):
         from epos_b200 import synthetic
         store = synthetic.model_store(O, F)
         K = synthetic.default_K()
+    # the per-batch all-gather of pose records runs on the engine's side stream: give it its own communicator so that it
+    # never interleaves with the main-stream collectives (barrier, timing all-reduce) of the default group
+    side_group = dist.new_group(backend='nccl') if world > 1 else None
     from epos_b200 import model as emodel
     opts = emodel.ModelOptions(Wt.head_channels(O, F), model_variant=args.backbone)
     fit_params = None
@@ -251,7 +254,7 @@ def run_ours(args, kind):
     eng = engine.Engine(w, O, F, dev, stages=engine.STAGES_FULL if kind == 'full' else engine.STAGES_CNN,
                         model_store=store, K=K, seed=1234 + rank, max_correspondences=MAX_CORR, model_options=opts,
                         fit_params=fit_params, pipelined=not args.serial,
-                        post_fit=(lambda poses: edist.all_gather_poses(poses, world)) if world > 1 else None)
+                        post_fit=(lambda poses: edist.all_gather_poses(poses, world, group=side_group)) if world > 1 else None)
 
     # inputs: NROT distinct batches (> L2 in total) rotated between steps, both pinned-host and device copies
     NROT = 5
@@ -260,6 +263,9 @@ def run_ours(args, kind):
     torch.cuda.synchronize()
 
     def barrier():
+        # drain BOTH streams first: the pose all-gathers run on the engine's side stream, and NCCL operations of one rank
+        # must not be in flight on two streams in an order that can differ between ranks
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -285,6 +291,7 @@ def run_ours(args, kind):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = world * B * args.steps / (ms * 1e-3)
+    torch.cuda.synchronize()
 
     # ---- end-to-end through the public host API ("e2e") ----
     res0 = eng.result_tensor(out)
@@ -315,10 +322,11 @@ def run_ours(args, kind):
         eng.net.gemm_events = []
         nat = max(1, min(args.steps, 5))
         was_pipelined, eng.pipelined = eng.pipelined, False       # kernel timed alone: no pose-fitting CTAs beside it
+        post_fit, eng.post_fit = eng.post_fit, None               # rank 0 only: no collective in this pass
         for i in range(nat):
             eng.run_device(dev_batches[i % NROT])
         torch.cuda.synchronize()
-        eng.pipelined = was_pipelined
+        eng.pipelined, eng.post_fit = was_pipelined, post_fit
         evs, eng.net.gemm_events = eng.net.gemm_events, None
         gemm_ms = sum(a.elapsed_time(b) for a, b, _, _, _ in evs)
         gemm_flop = sum(2.0 * m * n * k for _, _, m, n, k in evs)

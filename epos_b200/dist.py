@@ -65,10 +65,10 @@ def broadcast_weights(weights, num_objs, num_frags, device, world, rank, src=0, 
     return unpack_weights(t.cpu().numpy(), num_objs, num_frags, model_variant)
 
 
-def all_gather_poses(poses, world):
+def all_gather_poses(poses, world, group=None):
     """poses [b, O, 16] f64 on this rank -> [world*b, O, 16] (rank-major, i.e. global image order)."""
     if world == 1:
         return poses
     out = torch.empty((world * poses.shape[0],) + tuple(poses.shape[1:]), dtype=poses.dtype, device=poses.device)
-    dist.all_gather_into_tensor(out, poses.contiguous())
+    dist.all_gather_into_tensor(out, poses.contiguous(), group=group)
     return out
