@@ -28,10 +28,11 @@ __global__ void __launch_bounds__(DT_THREADS) dwconv3x3_tile_kernel(
   extern __shared__ __align__(128) uint8_t dt_smem[];
   float4* tile = reinterpret_cast<float4*>(dt_smem + ((128u - (smem_u32(dt_smem) & 127u)) & 127u));
   __shared__ uint64_t bar;
-  const int x0 = blockIdx.x * DT_TW;
-  const int y0 = (blockIdx.y % tiles_y) * TH;
-  const int b = blockIdx.y / tiles_y;
-  const int slab = blockIdx.z;
+  // slab is the fastest grid index: CTAs that run together read adjacent 128-byte chunks of the same pixels
+  const int slab = blockIdx.x;
+  const int x0 = blockIdx.y * DT_TW;
+  const int y0 = (blockIdx.z % tiles_y) * TH;
+  const int b = blockIdx.z / tiles_y;
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -99,6 +100,100 @@ __global__ void __launch_bounds__(DT_THREADS) dwconv3x3_tile_kernel(
   }
 }
 
+// Large dilation rates (ASPP: 12 / 24 / 36 on a 60 x 80 map).  With rate r the rows y = ry (mod r) form an independent
+// problem: a tap of such a row lies in a row of the same class, r pixels to the side.  A CTA therefore owns one row class
+// of one image and one 32-channel slab: every input value is read from HBM exactly once (the register-strip kernel
+// re-reads each value up to 9 times from L2), taps come from shared memory, padding is an index test.
+__global__ void __launch_bounds__(DT_THREADS) dwconv3x3_rows_kernel(
+    const float* __restrict__ x, int ldx, const float* __restrict__ w, const float* __restrict__ bias,
+    float* __restrict__ y_f32, uint16_t* __restrict__ y_split, int ldy_split, long long plane_stride, int H, int W, int C,
+    int rate, int relu_in, int relu_out) {
+  extern __shared__ __align__(128) uint8_t dt_smem[];
+  float4* tile = reinterpret_cast<float4*>(dt_smem);
+  // slab is the fastest grid index: CTAs that run together read adjacent 128-byte chunks of the same pixels
+  const int slab = blockIdx.x, ry = blockIdx.y, b = blockIdx.z;
+  const int Hs = (H - ry + rate - 1) / rate;          // rows ry, ry + r, ... of this class
+  const int cg = threadIdx.x & 7;
+  const int c = slab * DT_SLAB + cg * 4;
+  const bool c_ok = c < C;
+  const float in_floor = relu_in ? 0.f : -INFINITY;
+  const float out_floor = relu_out ? 0.f : -INFINITY;
+  const int n = Hs * W * 8;
+  // eight independent loads per thread in flight (the loop body has no other work to hide the latency behind)
+  for (int base = threadIdx.x; base < n; base += 8 * DT_THREADS) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * DT_THREADS;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < n && c_ok) {
+        const int px = idx >> 3, i = px / W, xx = px - i * W;
+        v[u] = __ldg(reinterpret_cast<const float4*>(x + (((long long)b * H + ry + i * rate) * W + xx) * ldx + c));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * DT_THREADS;
+      if (idx < n) {
+        v[u].x = fmaxf(v[u].x, in_floor); v[u].y = fmaxf(v[u].y, in_floor);
+        v[u].z = fmaxf(v[u].z, in_floor); v[u].w = fmaxf(v[u].w, in_floor);
+        tile[idx] = c_ok ? v[u] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  float4 wk[9];
+  float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int t = 0; t < 9; ++t) wk[t] = c_ok ? __ldg(reinterpret_cast<const float4*>(w + (size_t)t * C + c)) : bb;
+  if (c_ok) bb = __ldg(reinterpret_cast<const float4*>(bias + c));
+  __syncthreads();
+  if (!c_ok) return;
+  for (int idx = threadIdx.x; idx < n; idx += DT_THREADS) {
+    const int px = idx >> 3, i = px / W, xx = px - i * W;
+    float4 acc = bb;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int ii = i + ky - 1;
+      if (ii < 0 || ii >= Hs) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xs = xx + (kx - 1) * rate;
+        if (xs < 0 || xs >= W) continue;
+        const float4 v = tile[(ii * W + xs) * 8 + cg];
+        const float4 ww = wk[ky * 3 + kx];
+        acc.x = fmaf(v.x, ww.x, acc.x); acc.y = fmaf(v.y, ww.y, acc.y);
+        acc.z = fmaf(v.z, ww.z, acc.z); acc.w = fmaf(v.w, ww.w, acc.w);
+      }
+    }
+    acc.x = fmaxf(acc.x, out_floor); acc.y = fmaxf(acc.y, out_floor); acc.z = fmaxf(acc.z, out_floor); acc.w = fmaxf(acc.w, out_floor);
+    const long long pix = ((long long)b * H + ry + i * rate) * W + xx;
+    if (y_f32) *reinterpret_cast<float4*>(y_f32 + pix * C + c) = acc;
+    if (y_split) {
+      uint2 hi, lo;
+      split_bf16x2(acc.x, acc.y, hi.x, lo.x);
+      split_bf16x2(acc.z, acc.w, hi.y, lo.y);
+      *reinterpret_cast<uint2*>(y_split + pix * ldy_split + c) = hi;
+      *reinterpret_cast<uint2*>(y_split + plane_stride + pix * ldy_split + c) = lo;
+    }
+  }
+}
+
+static int launch_dw_rows(const float* x, int ldx, const float* w, const float* bias, float* y_f32, uint16_t* y_split,
+                          int ldy_split, int B, int H, int W, int C, int rate, int relu_in, int relu_out, cudaStream_t stream) {
+  const int hs_max = ceil_div(H, rate);
+  const int smem = hs_max * W * DT_SLAB * 4;
+  static int attr = 0;
+  if (smem > attr) {
+    EPOS_CUDA(cudaFuncSetAttribute(dwconv3x3_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = smem;
+  }
+  dim3 grid(ceil_div(C, DT_SLAB), rate < H ? rate : H, B);
+  dwconv3x3_rows_kernel<<<grid, DT_THREADS, smem, stream>>>(x, ldx, w, bias, y_f32, y_split, ldy_split,
+                                                            (long long)B * H * W * ldy_split, H, W, C, rate, relu_in, relu_out);
+  EPOS_LAUNCH_CHECK();
+  return EPOS_OK;
+}
+
 // f32 NHWC [B][H][W][ldx] viewed as {C, W, H, B}; box {32, 16+2r, TH+2r, 1}, no swizzle, zero fill outside.
 static int make_dw_map(CUtensorMap* map, const float* x, int ldx, int B, int H, int W, int C, int TH, int R) {
   PFN_encodeTiled enc = get_encode();
@@ -127,7 +222,7 @@ static int launch_dw_tile(const CUtensorMap& map, const float* w, const float* b
     attr = smem;
   }
   const int tiles_y = ceil_div(H, TH), slabs = ceil_div(C, DT_SLAB);
-  dim3 grid(ceil_div(W, DT_TW), tiles_y * B, slabs);
+  dim3 grid(slabs, ceil_div(W, DT_TW), tiles_y * B);
   dwconv3x3_tile_kernel<R><<<grid, DT_THREADS, smem, stream>>>(map, w, bias, y_f32, y_split, ldy_split, (long long)B * H * W * ldy_split, H,
                                                               W, C, TH, tiles_y, slabs, relu_in, relu_out);
   EPOS_LAUNCH_CHECK();
@@ -138,15 +233,20 @@ static int launch_dw_tile(const CUtensorMap& map, const float* w, const float* b
 // then uses the register-strip kernel in cnn_kernels.cu.
 int dwconv3x3_tiled(const float* x, int ldx, const float* w, const float* bias, float* y_f32, uint16_t* y_split,
                     int ldy_split, int B, int H, int W, int C, int rate, int relu_in, int relu_out, cudaStream_t stream) {
-  if (!(rate == 1 || rate == 2 || rate == 4)) return EPOS_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || (ldx % 4) != 0 || (C % 4) != 0) return EPOS_ERR_UNSUPPORTED;
+  if (!(rate == 1 || rate == 2 || rate == 4)) {
+    // large rates: one row class per CTA if it fits in shared memory (<= 96 KB keeps two CTAs per SM)
+    if (rate >= 6 && (long long)ceil_div(H, rate) * W * DT_SLAB * 4 <= 96 * 1024 && B <= 65535)
+      return launch_dw_rows(x, ldx, w, bias, y_f32, y_split, ldy_split, B, H, W, C, rate, relu_in, relu_out, stream);
+    return EPOS_ERR_UNSUPPORTED;
+  }
   // tile height: a multiple of 4 in [8, 24] with the least padded rows (ties: the taller tile)
   int TH = 8, best = 1 << 30;
   for (int t = 8; t <= 24; t += 4) {
     const int waste = ceil_div(H, t) * t - H;
     if (waste <= best) { best = waste; TH = t; }
   }
-  if ((long long)ceil_div(H, TH) * B > 65535 || ceil_div(C, DT_SLAB) > 65535) return EPOS_ERR_UNSUPPORTED;
+  if ((long long)ceil_div(H, TH) * B > 65535 || ceil_div(W, DT_TW) > 65535) return EPOS_ERR_UNSUPPORTED;
   CUtensorMap map;
   int rc = make_dw_map(&map, x, ldx, B, H, W, C, TH, rate);
   if (rc) return rc;
