@@ -34,6 +34,7 @@ _SIGS = {
     'epos_conv3x3_dense': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     'epos_dwconv3x3': (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     'epos_pwconv_gemm': (i32, [vp, i32, sz, vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, sz, i32, i32, i32, i32, vp]),
+    'epos_gemm_pieces': (i32, [i32, i32, i32, i32, i32, vp, i32]),
     'epos_pwconv_simt': (i32, [vp, i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp]),
     'epos_split_bf16': (i32, [vp, i32, vp, i32, sz, i32, i32, i32, i32, i32, i32, vp]),
     'epos_global_mean': (i32, [vp, vp, i32, i32, i32, vp]),

@@ -136,7 +136,7 @@ constexpr int CONV_TW = 16, CONV_TH = 8;
 struct PieceMap {
   int n_tiles, bulk_end, block_n, unit, bpr, g0, num_pieces, tile_m;
   // m_tiles row-tiles of tile_m rows (128, or 256 for a CTA pair); G = CTAs (or CTA pairs) sharing the work
-  __device__ PieceMap(int m_tiles, int N, int block_n_, int tile_m_, int G) {
+  __host__ __device__ PieceMap(int m_tiles, int N, int block_n_, int tile_m_, int G) {
     block_n = block_n_; tile_m = tile_m_;
     n_tiles = (N + block_n - 1) / block_n;
     const int num_tiles = m_tiles * n_tiles;
@@ -150,7 +150,7 @@ struct PieceMap {
     num_pieces = bulk_end + (m_tiles * bpr - g0);
   }
   // rows [m0, m0+tile_m) x columns [n0, n0+n_cols) (n_cols may run past N: mask with N)
-  __device__ void decode(int id, int& m0, int& n0, int& n_cols) const {
+  __host__ __device__ void decode(int id, int& m0, int& n0, int& n_cols) const {
     if (id < bulk_end) {
       m0 = (id / n_tiles) * tile_m; n0 = (id % n_tiles) * block_n; n_cols = block_n;
     } else {
@@ -840,4 +840,15 @@ extern "C" int epos_conv3x3_gemm(const uint16_t* x_split, int ldx, size_t x_plan
   cg.rate = rate; cg.cpb = C / GEMM_BK;
   return run_gemm(ma, w_split, ldw, bias, 0, residual, ldr, d_f32, ldd, d_split, ldd_split, d_plane_stride, cg, B * H * W, N,
                   9 * C, relu, (cudaStream_t)stream);
+}
+
+// Host view of the work distribution of the GEMM kernel (the same PieceMap code the device runs): piece i covers rows
+// [out[3i], out[3i] + tile_m) x columns [out[3i+1], out[3i+1] + out[3i+2]).  Returns the number of pieces (writes at
+// most `cap`).  Used by the CPU tests to check that every output element is produced exactly once.
+extern "C" int epos_gemm_pieces(int m_tiles, int N, int block_n, int tile_m, int num_ctas, int32_t* out, int cap) {
+  EPOS_CHECK_ARG(m_tiles > 0 && N > 0 && num_ctas > 0 && (tile_m == 128 || tile_m == 256));
+  EPOS_CHECK_ARG(block_n == 32 || block_n == 64 || block_n == 128 || block_n == 256);
+  const PieceMap pm(m_tiles, N, block_n, tile_m, num_ctas);
+  for (int i = 0; i < pm.num_pieces && i < cap && out; ++i) pm.decode(i, out[3 * i], out[3 * i + 1], out[3 * i + 2]);
+  return pm.num_pieces;
 }

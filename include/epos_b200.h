@@ -108,6 +108,12 @@ int epos_conv3x3_gemm(const uint16_t* x_split, int ldx, size_t x_plane_stride, c
                       uint16_t* d_split, int ldd_split, size_t d_plane_stride,
                       int B, int H, int W, int C, int N, int rate, int relu, void* stream);
 
+/* Host-side view of the GEMM kernel's work distribution (no GPU needed): pieces of tile_m rows x n_cols
+ * columns, full 128 x block_n tiles first, then -- when the tile count leaves at most half a wave over
+ * num_ctas CTAs (CTA pairs for tile_m = 256) -- the remainder cut into 64-column blocks.  out [cap][3] =
+ * (m0, n0, n_cols); returns the number of pieces, negative on error. */
+int epos_gemm_pieces(int m_tiles, int N, int block_n, int tile_m, int num_ctas, int32_t* out, int cap);
+
 /* Same contract computed by an fp32 SIMT kernel from f32 operands (validation / tiny shapes):
  * a [M][lda] f32, w [N][K] f32. */
 int epos_pwconv_simt(const float* a, int lda, const float* w, const float* bias, int bias_group_rows,
