@@ -30,7 +30,7 @@ constexpr int MAXNB = 8;            // storage stride of neighbour lists
 constexpr int MAX_TRIALS = 20;
 constexpr int THREADS = MAX_TRIALS * 32;      // fit kernel: 20 warps = one warp per LO trial
 constexpr int WARPS = THREADS / 32;
-constexpr int PT = 512;                       // prep kernel threads
+constexpr int PT = 1024;                      // prep kernel threads
 constexpr int TRIAL_THREADS = THREADS;
 constexpr int PER_THREAD = (NMAX + THREADS - 1) / THREADS;   // contiguous points per thread in ordered compactions
 constexpr int DIST_INF = 0x7fffffff;
