@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument('--num_frags', type=int, default=64)
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--head_std', type=float, default=300.0, help='logit initialiser stddev of the random-init heads')
+    ap.add_argument('--model_variant', default='xception_65', choices=['xception_65', 'resnet_v1_50_beta'],
+                    help='common.py:117-119 flag of the reference (backbone)')
     return ap.parse_args()
 
 
@@ -73,7 +75,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from epos_b200 import dist as edist, engine, posefit, synthetic, weights as W
+    from epos_b200 import dist as edist, engine, model, posefit, synthetic, weights as W
     if args.required_ransac_confidence != 1.0:
         raise SystemExit('required_ransac_confidence must be 1.0 in this build')
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -86,8 +88,9 @@ def main():
     O, F = args.num_objs, args.num_frags
     w = None
     if rank == 0:
-        w = W.load_npz(args.weights) if args.weights else W.random_init(O, F, seed=args.seed, logits_std=args.head_std)
-    w = edist.broadcast_weights(w, O, F, dev, world, rank)
+        w = W.load_npz(args.weights) if args.weights else W.random_init(O, F, seed=args.seed, logits_std=args.head_std,
+                                                                        model_variant=args.model_variant)
+    w = edist.broadcast_weights(w, O, F, dev, world, rank, model_variant=args.model_variant)
     store = synthetic.model_store(O, F)
     K = synthetic.default_K()
     params = posefit.default_params(threshold=args.inlier_thresh, neighborhood_ball_radius=args.neighbour_max_dist,
@@ -97,7 +100,8 @@ def main():
                                     max_iters=args.max_fitting_iterations)
     eng = engine.Engine(w, O, F, dev, stages=engine.STAGES_FULL, model_store=store, K=K, fit_params=params,
                         max_correspondences=args.max_correspondences, seed=args.seed,
-                        min_obj_conf=args.corr_min_obj_conf, min_frag_rel_conf=args.corr_min_frag_rel_conf)
+                        min_obj_conf=args.corr_min_obj_conf, min_frag_rel_conf=args.corr_min_frag_rel_conf,
+                        model_options=model.ModelOptions(W.head_channels(O, F), model_variant=args.model_variant))
     lo, hi = edist.shard_range(args.num_images, world, rank)
     results = []
     ids = store.dp_model['obj_ids']
