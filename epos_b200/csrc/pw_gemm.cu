@@ -9,12 +9,12 @@
 // operands are error-compensated bf16 pairs (x = hi + lo): D = Ahi*Whi + Ahi*Wlo + Alo*Whi, three
 // kind::f16 MMAs per product with fp32 accumulation in TMEM (~2^-17 relative operand error).
 //
-// Structure (one CTA per SM, 192 threads):
+// Structure (one CTA per SM, 320 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor.3d loads of the {64 x 128 x 2} A box and the
 //               {64 x BLOCK_N x 2} W box (both planes in one copy) into a STAGES-deep smem ring (128B swizzle)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit frees smem slots and
 //               publishes the accumulator
-//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp), bias / ReLU / residual, fp32 and/or
+//   warps 2..9  epilogue (two per TMEM lane quarter, alternate 32-column chunks): tcgen05.ld, bias / ReLU / residual, fp32 and/or
 //               split-bf16 stores; double-buffered accumulators (2 x BLOCK_N TMEM columns) overlap the
 //               epilogue of tile i with the main loop of tile i+1
 #include <cuda.h>
@@ -27,7 +27,8 @@ namespace epos {
 constexpr int BLOCK_M = 128;
 constexpr int UMMA_K = 16;
 constexpr int GEMM_BK = 64;        // K block (bf16 elements): rows of 128 B, 128-byte swizzle
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;          // two epilogue warps per TMEM lane quarter, each taking alternate column chunks
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 
 struct GemmEpilogue {
   const float* bias;
@@ -171,9 +172,10 @@ struct GemmCfg {
   static constexpr int B_BOX_ROWS = PAIR ? 32 : (BLOCK_N < 64 ? BLOCK_N : 64);   // small W box (rows per plane) for partial pieces
   static constexpr int B_BOX_BYTES = B_BOX_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES < 2 ? 2 : ((200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES);
+  static constexpr int STAGING_BYTES = EPI_WARPS * 32 * 32 * 4;    // epilogue transpose buffers, one per warp
+  static constexpr int RING_BUDGET = 227 * 1024 - 1024 - 512 - STAGING_BYTES;
+  static constexpr int STAGES = RING_BUDGET / STAGE_BYTES < 2 ? 2 : (RING_BUDGET / STAGE_BYTES > 8 ? 8 : RING_BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
-  static constexpr int STAGING_BYTES = 4 * 32 * 32 * 4;            // epilogue transpose buffers, one per warp
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers, piece queue*/ + STAGING_BYTES;
 };
 
@@ -215,11 +217,11 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w64) : "memory");
-    // full: one arrive.expect_tx per producer; tmem_empty: 4 epilogue warps per CTA; sched_empty: every consumer of the
-    // piece queue (single CTA: MMA + 4 epilogue warps; pair: + the peer's producer and its 4 epilogue warps)
+    // full: one arrive.expect_tx per producer; tmem_empty: the epilogue warps of each CTA; sched_empty: every consumer of
+    // the piece queue (single CTA: MMA + epilogue warps; pair: + the peer's producer and its epilogue warps)
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], NCTA); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4 * NCTA); }
-    for (int i = 0; i < SCHED_DEPTH; ++i) { mbar_init(&sched_full[i], 1); mbar_init(&sched_empty[i], 5 * NCTA); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_WARPS * NCTA); }
+    for (int i = 0; i < SCHED_DEPTH; ++i) { mbar_init(&sched_full[i], 1); mbar_init(&sched_empty[i], (1 + EPI_WARPS) * NCTA); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if constexpr (PAIR) cluster_sync_all();            // both CTAs' barriers exist before anything remote touches them
@@ -402,7 +404,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -420,6 +422,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ways): tcgen05.ld hands a lane one ROW, but coalesced global access wants 8 consecutive lanes on 128 contiguous
     // bytes of a row.  After the transpose lane (rsub, jj) owns columns 4*jj..4*jj+3 of rows rsub, rsub+4, ...
     float4* stg = reinterpret_cast<float4*>(staging + (warp - 2) * 1024);
+    const int half = (warp - 2) >> 2;                // which of the two warps of this quarter: alternate column chunks
     const int rsub = lane >> 3, jj = lane & 7;
     const float relu_floor = ep.relu ? 0.f : -INFINITY;
     const PieceMap pm(PAIR ? (m_tiles + 1) / 2 : m_tiles, N, BLOCK_N, PAIR ? 2 * BLOCK_M : BLOCK_M,
@@ -465,7 +468,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // Fused softmax over groups of 64 columns (tf.nn.softmax over the fragment axis, model.py:676-678): a lane owns
         // one row, so the 64 logits of a group are 2 x 32 registers and max / sum need no cross-lane traffic.
 #pragma unroll 1
-        for (int c0 = 0; c0 < n_valid; c0 += 64) {
+        for (int c0 = half * 64; c0 < n_valid; c0 += 128) {
           uint32_t r0[32], r1[32];
           __syncwarp();
           tmem_ld32_issue(tacc + (uint32_t)c0, r0);
@@ -525,7 +528,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         const bool two_groups = boundary < row_base + 32 && boundary < M;
 #pragma unroll 1
-        for (int c0 = 0; c0 < n_valid; c0 += 32) {
+        for (int c0 = half * 32; c0 < n_valid; c0 += 64) {
           const int col = n0 + c0 + jj * 4;
           const bool col_ok = col < N;
           uint32_t r[32];
@@ -588,7 +591,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         const float* brow = ep.bias ? ep.bias + (ep.bias_group_rows > 0 && m >= 0 ? (m / ep.bias_group_rows) * N : 0) : nullptr;
 #pragma unroll 1
-        for (int c0 = 0; c0 < n_valid; c0 += 32) {
+        for (int c0 = half * 32; c0 < n_valid; c0 += 64) {
           uint32_t r[32];
           __syncwarp();
           tmem_ld32_issue(tacc + (uint32_t)c0, r);
