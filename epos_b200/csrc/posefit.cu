@@ -180,7 +180,6 @@ prep_kernel(Workspace ws, const double* __restrict__ c2d, const double* __restri
   float* q = reinterpret_cast<float*>(smem_raw);                         // [5][NMAX] f32 neighbourhood coordinates
   unsigned long long* table = reinterpret_cast<unsigned long long*>(smem_raw + 5 * NMAX * 4);   // 8192 hash slots
   int* scan_sh = reinterpret_cast<int*>(smem_raw + 5 * NMAX * 4 + 8192 * 8);
-  const float sc = (float)0;  (void)sc;
   for (int i = tid; i < 8192; i += PT) table[i] = ~0ULL;
   __syncthreads();
   for (int i = tid; i < N; i += PT) {

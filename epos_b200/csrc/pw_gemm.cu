@@ -1,9 +1,11 @@
-// Pointwise (1x1) convolution as a persistent, warp-specialised tcgen05 GEMM for sm_100a.
+// Pointwise (1x1) and dense 3x3 (atrous) convolutions as a persistent, warp-specialised tcgen05 GEMM for sm_100a.
 //
-//   D[m][n] = act( sum_k A[m][k] W[n][k] + bias[g(m)][n] ) (+ residual[m][n])
+//   D[m][n] = act( sum_k A[m][k] W[n][k] + bias[g(m)][n] + residual[m][n] )      act = identity | ReLU | softmax-64
 //
 // Replaces slim.conv2d(1x1)+BatchNorm(+ReLU)(+residual add) of the reference
-// (/root/reference/epos_lib/net_xception.py:178-182,297-313; model.py:90-97,223-258,350-352,448-456).
+// (/root/reference/epos_lib/net_xception.py:178-182,297-313; model.py:90-97,223-258,350-352,448-456;
+// net_resnet_v1_beta.py:72-88) and, in conv mode (K = 9 taps x C, A boxes fetched by 5-D TMA with zero fill),
+// resnet_utils.conv2d_same at stride 1 (external/slim/nets/resnet_utils.py:77-122).
 //
 // Precision: the reference computes in fp32.  To hold the 1e-3 parity bound through ~75 stacked GEMMs the
 // operands are error-compensated bf16 pairs (x = hi + lo): D = Ahi*Whi + Ahi*Wlo + Alo*Whi, three
@@ -15,8 +17,10 @@
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit frees smem slots and
 //               publishes the accumulator
 //   warps 2..9  epilogue (two per TMEM lane quarter, alternate 32-column chunks): tcgen05.ld, bias / ReLU / residual, fp32 and/or
-//               split-bf16 stores; double-buffered accumulators (2 x BLOCK_N TMEM columns) overlap the
-//               epilogue of tile i with the main loop of tile i+1
+//               split-bf16 stores through a per-warp smem transpose (coalesced); double-buffered accumulators
+//               (2 x BLOCK_N TMEM columns) overlap the epilogue of tile i with the main loop of tile i+1
+// Work is handed out dynamically (PieceMap + a global counter); PAIR = true runs the same roles on a cluster of two
+// CTAs with tcgen05.mma.cta_group::2 (M = 256, each CTA holds half of the W tile).
 #include <cuda.h>
 #include <stdlib.h>
 #include "common.cuh"
