@@ -440,7 +440,9 @@ class EposNet:
         M = B * h * w
         O, F = self.O, self.F
         obj, _ = self.gemm(feat_split, self.p['logits/' + PRED_OBJ_CONF], M, relu=False, pad_f32=False)
-        fused = F % 64 == 0 and self.impl == 'tcgen05'      # softmax over F in the GEMM epilogue (relu = 2)
+        # softmax over F in the GEMM epilogue (relu = 2) when a fragment group is exactly one 64-column group;
+        # other F (e.g. config 5's 256) use the row-softmax kernel
+        fused = F == 64 and self.impl == 'tcgen05'
         fc, _ = self.gemm(feat_split, self.p['logits/' + PRED_FRAG_CONF], M, relu=2 if fused else False, pad_f32=False)
         fl, _ = self.gemm(feat_split, self.p['logits/' + PRED_FRAG_LOC], M, relu=False, pad_f32=False)
         labels = torch.empty((M,), dtype=torch.int64, device=self.dev)

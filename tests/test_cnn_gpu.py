@@ -305,6 +305,14 @@ def test_network_small():
     _net_parity(2, 96, 128, 3, 8, seed=11, check_simt=True)
 
 
+def test_network_fragment_counts_around_the_fused_softmax_width():
+    """F = 64 takes the softmax fused into the GEMM epilogue; F = 128 (a multiple of 64, like config 5's 256) and F = 32 must
+    take the row-softmax kernel (softmax over ALL fragments of an object)."""
+    _net_parity(1, 64, 96, 2, 128, seed=31)
+    _net_parity(1, 64, 96, 2, 64, seed=32)
+    _net_parity(1, 64, 96, 3, 32, seed=33)
+
+
 def test_network_odd_size():
     _net_parity(1, 81, 113, 1, 4, seed=12)
 
