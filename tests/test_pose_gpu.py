@@ -212,12 +212,13 @@ def test_batch_fitter_matches_oracle_pipeline():
     assert found >= 6
 
 
-def test_engine_full_path_postprocessing_matches_oracle_on_its_own_maps():
+@pytest.mark.parametrize('F', [16, 128])
+def test_engine_full_path_postprocessing_matches_oracle_on_its_own_maps(F):
     """Engine = model.predict -> corresp -> fit on the device; the oracle post-processes the SAME maps (copied to the
     host), so the comparison is exact although the CNN itself only matches the f32 oracle to 1e-3."""
     from epos_b200 import engine, model, synthetic, weights as W
     from oracle import pipeline
-    O, F, B = 3, 16, 2
+    O, B = 3, 2
     w = W.random_init(O, F, seed=2, bn='random', logits_std=0.5)
     store = synthetic.model_store(O, F)
     K = synthetic.default_K()
