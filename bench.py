@@ -66,6 +66,10 @@ def parse_args():
     ap.add_argument('--cpu-images', type=int, default=3, help='images in the cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--serial', action='store_true', help='no CNN / pose-fitting overlap (single stream)')
+    ap.add_argument('--secondary', dest='secondary', action='store_true', default=None,
+                    help='also time BASELINE configs[3] (ResNet-50-beta, 8/GPU) and configs[4] (30x256, 2000 iterations, '
+                         '16/GPU) for a few steps each (default: on when no workload flag is given)')
+    ap.add_argument('--no-secondary', dest='secondary', action='store_false')
     return ap.parse_args()
 
 
@@ -213,48 +217,46 @@ def run_reference(args, kind):
 # ------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------
-def run_ours(args, kind):
-    import numpy as np
+class Cfg:
+    """One measured workload (a BASELINE.json config at its per-GPU shape)."""
+
+    def __init__(self, kind, batch, objs, frags, backbone, max_iters, steps, warmup):
+        self.kind, self.batch, self.objs, self.frags = kind, batch, objs, frags
+        self.backbone, self.max_iters, self.steps, self.warmup = backbone, max_iters, steps, warmup
+
+
+def measure(cfg, ctx, serial=False, want_roofline=True):
+    """Builds the engine for `cfg`, times `value` (device-resident inputs) and `e2e` (host buffers) over exactly
+    cfg.steps steps after cfg.warmup warm-up steps, max over ranks; rank 0 also measures the rooflines of the two
+    dominant kernels (tcgen05 GEMM: tensor; fit_kernel: HBM on algorithmic bytes).  Returns a dict (rank 0) / None."""
     import torch
     import torch.distributed as dist
     from epos_b200 import _lib, engine, weights as Wt
-
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    if not torch.cuda.is_available():
-        raise SystemExit('bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU path)')
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-    lib = _lib.lib()
-    B, O, F = args.batch, args.objs, args.frags
+    from epos_b200 import dist as edist
+    from epos_b200 import model as emodel
+    world, rank, local, dev, lib, side_group = (ctx[k] for k in ('world', 'rank', 'local', 'dev', 'lib', 'side_group'))
+    kind, B, O, F = cfg.kind, cfg.batch, cfg.objs, cfg.frags
 
     # weights: generated on rank 0 and broadcast once over NCCL (SURVEY.md 8e)
-    from epos_b200 import dist as edist
-    w = edist.broadcast_weights(Wt.random_init(O, F, seed=0, logits_std=head_std(kind, args.backbone),
-                                               model_variant=args.backbone)
-                                if rank == 0 else None, O, F, dev, world, rank, model_variant=args.backbone)
+    w = edist.broadcast_weights(Wt.random_init(O, F, seed=0, logits_std=head_std(kind, cfg.backbone),
+                                               model_variant=cfg.backbone)
+                                if rank == 0 else None, O, F, dev, world, rank, model_variant=cfg.backbone)
     store = K = None
     if kind == 'full':
         from epos_b200 import synthetic
         store = synthetic.model_store(O, F)
         K = synthetic.default_K()
-    # the per-batch all-gather of pose records runs on the engine's side stream: give it its own communicator so that it
-    # never interleaves with the main-stream collectives (barrier, timing all-reduce) of the default group
-    side_group = dist.new_group(backend='nccl') if world > 1 else None
-    from epos_b200 import model as emodel
-    opts = emodel.ModelOptions(Wt.head_channels(O, F), model_variant=args.backbone)
+    opts = emodel.ModelOptions(Wt.head_channels(O, F), model_variant=cfg.backbone)
     fit_params = None
-    if kind == 'full' and args.max_iters != 400:
+    if kind == 'full' and cfg.max_iters != 400:
         from epos_b200 import posefit
         fit_params = posefit.default_params()
-        fit_params.max_iters = args.max_iters
+        fit_params.max_iters = cfg.max_iters
     eng = engine.Engine(w, O, F, dev, stages=engine.STAGES_FULL if kind == 'full' else engine.STAGES_CNN,
                         model_store=store, K=K, seed=1234 + rank, max_correspondences=MAX_CORR, model_options=opts,
-                        fit_params=fit_params, pipelined=not args.serial,
+                        fit_params=fit_params, pipelined=not serial,
                         post_fit=(lambda poses: edist.all_gather_poses(poses, world, group=side_group)) if world > 1 else None)
+    del w
 
     # inputs: NROT distinct batches (> L2 in total) rotated between steps, both pinned-host and device copies
     NROT = 5
@@ -270,72 +272,83 @@ def run_ours(args, kind):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # ---- device-resident timing ("value") ----
-    for i in range(args.warmup):
+    for i in range(cfg.warmup):
         out = eng.run_device(dev_batches[i % NROT])
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = lib.epos_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
+    for i in range(cfg.steps):
         out = eng.run_device(dev_batches[i % NROT])
     eng.join()                         # the timed region ends when the last batch's pose records (and all-gather) are done
     e1.record()
     barrier()
-    ms = e0.elapsed_time(e1)
     launches = int(lib.epos_launch_count() - l0)
     clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    value = world * B * args.steps / (ms * 1e-3)
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    value = world * B * cfg.steps / (ms * 1e-3)
     torch.cuda.synchronize()
 
     # ---- end-to-end through the public host API ("e2e") ----
     res0 = eng.result_tensor(out)
     res_pinned = torch.empty(res0.shape, dtype=res0.dtype).pin_memory()
     res_pinned2 = torch.empty(res0.shape, dtype=res0.dtype).pin_memory()     # pipelined: batch i lands while i+1 runs
-    for i in range(args.warmup):
+    for i in range(cfg.warmup):
         eng.run_host(host_batches[i % NROT], res_pinned if i % 2 == 0 else res_pinned2)
     eng.flush()
     barrier()
     e0.record()
-    for i in range(args.steps):
+    for i in range(cfg.steps):
         eng.run_host(host_batches[i % NROT], res_pinned if i % 2 == 0 else res_pinned2)
     eng.flush()                        # host holds the last batch's result
     e1.record()
     barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
-    e2e = {'value': world * B * args.steps / (e2e_ms * 1e-3), 'unit': 'images/s',
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e = {'value': world * B * cfg.steps / (e2e_ms * 1e-3), 'unit': 'images/s',
            'h2d_bytes_per_step': int(host_batches[0].numel() * host_batches[0].element_size()),
            'd2h_bytes_per_step': int(res_pinned.numel() * res_pinned.element_size()),
-           'ms_per_step': e2e_ms / args.steps}
+           'ms_per_step': e2e_ms / cfg.steps}
 
-    # ---- roofline of the dominant kernel: per-launch CUDA events around every tcgen05 GEMM ----
-    roof = None
-    if rank == 0:
-        eng.net.gemm_events = []
-        nat = max(1, min(args.steps, 5))
-        was_pipelined, eng.pipelined = eng.pipelined, False       # kernel timed alone: no pose-fitting CTAs beside it
-        post_fit, eng.post_fit = eng.post_fit, None               # rank 0 only: no collective in this pass
-        for i in range(nat):
-            eng.run_device(dev_batches[i % NROT])
-        torch.cuda.synchronize()
-        eng.pipelined, eng.post_fit = was_pipelined, post_fit
-        evs, eng.net.gemm_events = eng.net.gemm_events, None
-        gemm_ms = sum(a.elapsed_time(b) for a, b, _, _, _ in evs)
-        gemm_flop = sum(2.0 * m * n * k for _, _, m, n, k in evs)
+    # ---- rooflines of the dominant kernels: per-launch CUDA events, engine serial (each kernel alone on the GPU) ----
+    roof = roof_ransac = None
+    if rank == 0 and want_roofline:
+        import ctypes as C
         peaks = {}
         try:
             with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
                 peaks = json.load(f)
         except Exception:
             pass
+        eng.net.gemm_events = []
+        nat = max(1, min(cfg.steps, 5))
+        was_pipelined, eng.pipelined = eng.pipelined, False       # kernel timed alone: no pose-fitting CTAs beside it
+        post_fit, eng.post_fit = eng.post_fit, None               # rank 0 only: no collective in this pass
+        fit_ms = fit_bytes = prep_ms = 0.0
+        if kind == 'full':
+            _lib.check(lib.epos_fit_enable_timing(1), 'epos_fit_enable_timing')
+        for i in range(nat):
+            eng.run_device(dev_batches[i % NROT])
+            if kind == 'full':
+                a, b = C.c_float(0), C.c_float(0)
+                _lib.check(lib.epos_fit_last_kernel_ms(C.byref(a), C.byref(b)), 'epos_fit_last_kernel_ms')
+                prep_ms += a.value
+                fit_ms += b.value
+                fit_bytes += eng._fitter._fitter.algorithmic_bytes(B * eng._fitter.J)
+        torch.cuda.synchronize()
+        if kind == 'full':
+            _lib.check(lib.epos_fit_enable_timing(0), 'epos_fit_enable_timing')
+        eng.pipelined, eng.post_fit = was_pipelined, post_fit
+        evs, eng.net.gemm_events = eng.net.gemm_events, None
+        gemm_ms = sum(a.elapsed_time(b) for a, b, _, _, _ in evs)
+        gemm_flop = sum(2.0 * m * n * k for _, _, m, n, k in evs)
         peak = peaks.get('bf16_tflops_sustained') or 1400.0
         traffic = None
         try:
@@ -353,7 +366,87 @@ def run_ours(args, kind):
                 'mma_issue_frac': 3.0 * achieved / peak,
                 'note': 'achieved = algorithmic fp32-equivalent FLOPs (2MNK per launch, SURVEY 8d) / summed per-launch '
                         'event time; each product costs 3 bf16 MMAs (error-compensated split), mma_issue_frac = 3x',
-                'gemm_ms_per_step': gemm_ms / nat, 'share_of_step': (gemm_ms / nat) / (ms / args.steps)}
+                'gemm_ms_per_step': gemm_ms / nat, 'share_of_step': (gemm_ms / nat) / (ms / cfg.steps)}
+        if kind == 'full' and fit_ms > 0:
+            hbm = peaks.get('hbm_gbs') or 6500.0
+            ach = fit_bytes / (fit_ms * 1e-3) / 1e9
+            traffic_r = None
+            try:
+                with open(os.path.join(ROOT, 'profiles', 'ransac_traffic.json')) as f:
+                    traffic_r = json.load(f)
+            except Exception:
+                pass
+            roof_ransac = {
+                'bound': 'hbm', 'kernel': 'fit_kernel (persistent CTA per (image, object) problem: GC-RANSAC main loop, '
+                                          'graph-cut LO, final LSQ/LM), 1 launch/step',
+                'achieved': ach, 'peak': hbm, 'unit': 'GB/s', 'frac': ach / hbm,
+                'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback', 'traffic': traffic_r,
+                'algorithmic_mb_per_launch': fit_bytes / nat / 1e6, 'fit_ms_per_launch': fit_ms / nat,
+                'prep_ms_per_launch': prep_ms / nat,
+                'note': 'SURVEY 8d: every model scored over a problem\'s N points costs N x 40 B (u_n, v_n, x, y, z f64) '
+                        '+ N x 8 B (pixel id); models counted on the device (epos_fit_debug_state cols 16-18: main loop '
+                        'hypotheses, LO trials, final re-scorings).  The point set is shared-memory resident, so DRAM '
+                        'traffic is far below the algorithmic bytes; the kernel is FP64-issue / latency bound.'}
+
+    res = None
+    if rank == 0:
+        flop_img = TRUNK_FLOP[cfg.backbone] + head_flop(O, F)
+        res = {'value': value, 'ms_per_step': ms / cfg.steps, 'steps': cfg.steps, 'warmup': cfg.warmup, 'e2e': e2e,
+               'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'roofline_ransac': roof_ransac,
+               'model_tflops_algorithmic': value * flop_img / 1e12 / world,
+               'config': {'workload': workload_name(kind, B, O, F, cfg.backbone), 'images_per_gpu_per_step': B,
+                          'global_batch': B * world,
+                          'l2': 'inputs rotate over %d distinct batches (%.0f MB) and per-layer activations (>=112 MB at '
+                                'B=8) exceed the 126 MB L2' % (NROT, NROT * host_batches[0].numel() * 4 / 1e6),
+                          'algorithmic_gflop_per_image': flop_img / 1e9,
+                          'heads': 'random-init; logit initialiser stddev %s' % (head_std(kind, cfg.backbone) or 0.01),
+                          'ransac_max_iters': cfg.max_iters if kind == 'full' else None,
+                          'max_correspondences': MAX_CORR if kind == 'full' else None,
+                          'parallelism': 'image-sharded dp%d' % world,
+                          'pipeline': 'pose fitting of batch i on a side stream under the CNN of batch i+1'
+                                      if eng.pipelined else 'serial',
+                          'parity_pin': 'pose: reference golden vectors (pnp16 / pose6dscene / tless / cv2 / BK max-flow); '
+                                        'CNN: Slim conv2d_same / atrous vectors only (the reference holds no network-level '
+                                        'vector; TF-1.12 not installable)'}}
+    del eng, dev_batches, host_batches, out
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_ours(args, kind):
+    import torch
+    import torch.distributed as dist
+    from epos_b200 import _lib
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU path)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    # the per-batch all-gather of pose records runs on the engine's side stream: give it its own communicator so that it
+    # never interleaves with the main-stream collectives (barrier, timing all-reduce) of the default group
+    side_group = dist.new_group(backend='nccl') if world > 1 else None
+    ctx = {'world': world, 'rank': rank, 'local': local, 'dev': dev, 'lib': _lib.lib(), 'side_group': side_group}
+    B, O, F = args.batch, args.objs, args.frags
+    primary = measure(Cfg(kind, B, O, F, args.backbone, args.max_iters, args.steps, args.warmup), ctx, serial=args.serial)
+
+    # ---- the other multi-GPU configs of BASELINE.json at their per-GPU shapes (short runs, same timing rules) ----
+    secondary = None
+    if args.secondary and kind == 'full':
+        sw, ss = max(3, min(args.warmup, 3)), max(3, min(args.steps, 6))
+        secondary = {}
+        for name, cfg in (('configs[3]', Cfg('full', 8, 21, 64, 'resnet_v1_50_beta', 400, ss, sw)),
+                          ('configs[4]', Cfg('full', 16, 30, 256, 'xception_65', 2000, ss, sw))):
+            r = measure(cfg, ctx, serial=args.serial)
+            if rank == 0:
+                r['metric'], r['unit'], r['n_gpus'] = 'images/sec', 'images/s', world
+                secondary[name] = r
 
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None
@@ -366,24 +459,15 @@ def run_ours(args, kind):
                          % (args.cpu_images, json.dumps({k: round(v, 4) for k, v in stages.items()}))}
 
     if rank == 0:
-        flop_img = TRUNK_FLOP[args.backbone] + head_flop(O, F)
         line = {
-            'metric': 'images/sec (640x480, Xception-65 f64 + PnP-RANSAC)', 'value': value, 'unit': 'images/s',
-            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (split-bf16 x3 MMA, f32 accumulate; pose f64)',
-            'data': 'synthetic',
-            'config': {'workload': workload_name(kind, B, O, F, args.backbone), 'images_per_gpu_per_step': B, 'global_batch': B * world,
-                       'l2': 'inputs rotate over %d distinct batches (%.0f MB) and per-layer activations (>=112 MB at B=8) '
-                             'exceed the 126 MB L2' % (NROT, NROT * host_batches[0].numel() * 4 / 1e6),
-                       'algorithmic_gflop_per_image': flop_img / 1e9,
-                       'heads': 'random-init; logit initialiser stddev %s' % (head_std(kind, args.backbone) or 0.01),
-                       'ransac_max_iters': args.max_iters if kind == 'full' else None,
-                       'max_correspondences': MAX_CORR if kind == 'full' else None,
-                       'parallelism': 'image-sharded dp%d' % world,
-                       'pipeline': 'pose fitting of batch i on a side stream under the CNN of batch i+1' if eng.pipelined
-                                   else 'serial'},
-            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu,
-            'model_tflops_algorithmic': value * flop_img / 1e12 / world,
+            'metric': 'images/sec (640x480, Xception-65 f64 + PnP-RANSAC)', 'value': primary['value'], 'unit': 'images/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': primary['ms_per_step'],
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32 (split-bf16 x3 MMA, f32 accumulate; pose f64)', 'data': 'synthetic',
+            'config': primary['config'], 'clocks': primary['clocks'], 'e2e': primary['e2e'],
+            'gpu_launches': primary['gpu_launches'], 'roofline': primary['roofline'],
+            'roofline_ransac': primary['roofline_ransac'], 'cpu_baseline': cpu,
+            'model_tflops_algorithmic': primary['model_tflops_algorithmic'], 'secondary': secondary,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -393,6 +477,9 @@ def run_ours(args, kind):
 def main():
     args = parse_args()
     kind = args.workload or default_workload()
+    if args.secondary is None:          # the plain driver invocation measures every multi-GPU config of BASELINE.json
+        args.secondary = (args.workload is None and args.batch == 8 and args.objs == 21 and args.frags == 64 and
+                          args.backbone == 'xception_65' and args.max_iters == 400)
     if args.impl == 'reference':
         run_reference(args, kind)
     else:

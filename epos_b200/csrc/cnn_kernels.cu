@@ -234,52 +234,6 @@ __global__ void __launch_bounds__(256, 3) dwconv3x3_kernel(const float* __restri
   }
 }
 
-// Variant A (flat): one thread = one output pixel x 4 channels, grid-stride; consecutive threads walk the channel axis.
-__global__ void __launch_bounds__(256) dwconv3x3_flat_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w,
-                                                        const float* __restrict__ bias, float* __restrict__ y_f32,
-                                                        uint16_t* __restrict__ y_split, int ldy_split, long long plane_stride,
-                                                        int B, int H, int W, int C, int Ho, int Wo, int stride, int rate,
-                                                        int relu_in, int relu_out) {
-  const int G = C >> 2;
-  const long long total = (long long)B * Ho * Wo * G;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % G);
-    long long p = idx / G;
-    const int ox = (int)(p % Wo);
-    long long q = p / Wo;
-    const int oy = (int)(q % Ho);
-    const int b = (int)(q / Ho);
-    float4 acc = __ldg(reinterpret_cast<const float4*>(bias) + g);
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int iy = oy * stride - rate + ky * rate;
-      if (iy < 0 || iy >= H) continue;
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int ix = ox * stride - rate + kx * rate;
-        if (ix < 0 || ix >= W) continue;
-        float4 v = __ldg(reinterpret_cast<const float4*>(x + (((long long)b * H + iy) * W + ix) * ldx) + g);
-        if (relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-        const float4 ww = __ldg(reinterpret_cast<const float4*>(w + (ky * 3 + kx) * C) + g);
-        acc.x = fmaf(v.x, ww.x, acc.x); acc.y = fmaf(v.y, ww.y, acc.y);
-        acc.z = fmaf(v.z, ww.z, acc.z); acc.w = fmaf(v.w, ww.w, acc.w);
-      }
-    }
-    if (relu_out) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
-    if (y_f32) *(reinterpret_cast<float4*>(y_f32 + p * C) + g) = acc;
-    if (y_split) {
-      __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-      split_bf16(acc.x, h0, l0); split_bf16(acc.y, h1, l1); split_bf16(acc.z, h2, l2); split_bf16(acc.w, h3, l3);
-      uint2 hi = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
-      uint2 lo = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
-      *(reinterpret_cast<uint2*>(y_split + p * C) + g) = hi;
-      *(reinterpret_cast<uint2*>(y_split + plane_stride + p * C) + g) = lo;
-    }
-  }
-}
-
-
 // slim.max_pool2d(3, stride 2, 'SAME') (net_resnet_v1_beta.py:187): TF pads total = max((ceil(n/2)-1)*2+3-n, 0), before =
 // floor(total/2) (0/1 for even n, 1/1 for odd n); padded taps never win the max.
 __global__ void __launch_bounds__(256) maxpool3x3_s2_kernel(const float* __restrict__ x, float* __restrict__ y_f32,
@@ -588,10 +542,11 @@ int epos_conv3x3_dense(const float* x, const float* w, const float* bias, float*
     return EPOS_ERR_UNSUPPORTED;
   }
   constexpr int smem = (18 * 18 * 33 + 9 * 32 * 64) * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<int> attr_set[EPOS_MAX_DEVICES];
+  const int dslot = device_slot();
+  if (!attr_set[dslot].load(std::memory_order_acquire)) {
     EPOS_CUDA(cudaFuncSetAttribute(conv3x3_dense_kernel<32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    attr_set[dslot].store(1, std::memory_order_release);
   }
   dim3 grid(ceil_div(W, 16), ceil_div(H, 16), B);
   conv3x3_dense_kernel<32, 64><<<grid, 256, smem, (cudaStream_t)stream>>>(x, w, bias, y, H, W);
@@ -617,16 +572,9 @@ int epos_dwconv3x3(const float* x, int ldx, const float* w, const float* bias, f
     const int rc = dwconv3x3_tiled(x, ldx, w, bias, y_f32, y_split, ldy_split, B, H, W, C, rate, relu_in, relu_out, (cudaStream_t)stream);
     if (rc != EPOS_ERR_UNSUPPORTED) return rc;
   }
-  if (variant != 2) {
-    dwconv3x3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, w, bias, y_f32, y_split, ldy_split,
-                                                             (long long)B * Ho * Wo * ldy_split, B, H, W, C, Ho, Wo,
-                                                             stride, rate, relu_in, relu_out);
-  } else {
-    const long long total = (long long)B * Ho * Wo * (C / 4);
-    dwconv3x3_flat_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, ldx, w, bias, y_f32, y_split, ldy_split,
-                                                                             (long long)B * Ho * Wo * ldy_split, B, H, W, C, Ho, Wo,
-                                                                             stride, rate, relu_in, relu_out);
-  }
+  dwconv3x3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, w, bias, y_f32, y_split, ldy_split,
+                                                           (long long)B * Ho * Wo * ldy_split, B, H, W, C, Ho, Wo,
+                                                           stride, rate, relu_in, relu_out);
   EPOS_LAUNCH_CHECK();
   return EPOS_OK;
 }

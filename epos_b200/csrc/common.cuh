@@ -44,6 +44,15 @@ int dwconv3x3_tiled(const float* x, int ldx, const float* w, const float* bias, 
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute applies to the device that is current at the time of the call, so one-time set-up is tracked
+// PER DEVICE (a process may drive several GPUs).  Index of the current device into such a table.
+constexpr int EPOS_MAX_DEVICES = 64;
+inline int device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= EPOS_MAX_DEVICES) return 0;
+  return dev;
+}
+
 // fp32 -> (hi, lo) bf16 pair with hi + lo ~= x to 16-17 significant bits.
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);

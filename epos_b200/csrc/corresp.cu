@@ -326,10 +326,11 @@ int epos_corresp(const float* obj_conf, const float* frag_conf, const float* fra
   a.counts = counts; a.totals = totals;
   a.ws = reinterpret_cast<unsigned int*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
   const size_t smem = 2048 * 4 + (size_t)SORT_MAX * 12;
-  static bool attr = false;
-  if (!attr) {
+  static std::atomic<int> attr[EPOS_MAX_DEVICES];
+  const int dslot = device_slot();
+  if (!attr[dslot].load(std::memory_order_acquire)) {
     EPOS_CUDA(cudaFuncSetAttribute(corresp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
+    attr[dslot].store(1, std::memory_order_release);
   }
   corresp_kernel<<<B * J, CT, smem, (cudaStream_t)stream>>>(a);
   EPOS_LAUNCH_CHECK();

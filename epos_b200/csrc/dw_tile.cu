@@ -182,10 +182,11 @@ static int launch_dw_rows(const float* x, int ldx, const float* w, const float* 
                           int ldy_split, int B, int H, int W, int C, int rate, int relu_in, int relu_out, cudaStream_t stream) {
   const int hs_max = ceil_div(H, rate);
   const int smem = hs_max * W * DT_SLAB * 4;
-  static int attr = 0;
-  if (smem > attr) {
+  static std::atomic<int> attr[EPOS_MAX_DEVICES];
+  const int dslot = device_slot();
+  if (smem > attr[dslot].load(std::memory_order_acquire)) {
     EPOS_CUDA(cudaFuncSetAttribute(dwconv3x3_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = smem;
+    attr[dslot].store(smem, std::memory_order_release);
   }
   dim3 grid(ceil_div(C, DT_SLAB), rate < H ? rate : H, B);
   dwconv3x3_rows_kernel<<<grid, DT_THREADS, smem, stream>>>(x, ldx, w, bias, y_f32, y_split, ldy_split,
@@ -216,10 +217,11 @@ template <int R>
 static int launch_dw_tile(const CUtensorMap& map, const float* w, const float* bias, float* y_f32, uint16_t* y_split,
                           int ldy_split, int B, int H, int W, int C, int TH, int relu_in, int relu_out, cudaStream_t stream) {
   const int smem = (TH + 2 * R) * (DT_TW + 2 * R) * DT_SLAB * 4 + 128;
-  static int attr = 0;
-  if (smem > attr) {
+  static std::atomic<int> attr[EPOS_MAX_DEVICES];
+  const int dslot = device_slot();
+  if (smem > attr[dslot].load(std::memory_order_acquire)) {
     EPOS_CUDA(cudaFuncSetAttribute(dwconv3x3_tile_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = smem;
+    attr[dslot].store(smem, std::memory_order_release);
   }
   const int tiles_y = ceil_div(H, TH), slabs = ceil_div(C, DT_SLAB);
   dim3 grid(slabs, ceil_div(W, DT_TW), tiles_y * B);

@@ -52,6 +52,8 @@ struct ProbState {
   int chunk_base, chunk_n;
   long long t_sample, t_score, t_replay, t_total;   // main_kernel clock64() accumulators (profiling aid)
   long long t_cut, t_trials, t_final, t_fit;        // other kernels; t_fit = non-minimal fits inside trials (warp 0)
+  long long n_scored_main, n_scored_lo, n_scored_final;   // models scored over all N points (roofline accounting)
+  long long pad2;
 };
 
 struct PassRecord;
@@ -161,6 +163,7 @@ prep_kernel(Workspace ws, const double* __restrict__ c2d, const double* __restri
     st->lo_value = 0; st->lo_inl = 0; st->used_pixels = 0; st->chunk_base = 0; st->chunk_n = 0;
     st->t_sample = st->t_score = st->t_replay = st->t_total = 0;
     st->t_cut = st->t_trials = st->t_final = st->t_fit = 0;
+    st->n_scored_main = st->n_scored_lo = st->n_scored_final = 0;
     st->seed = seeds[p];
     st->max_iteration = iteration_bound(1.0 /* set below */, 1, N > 0 ? N : 1);
     for (int i = 0; i < 12; ++i) { st->best_model[i] = 0.0; st->lo_model[i] = 0.0; }
@@ -512,7 +515,7 @@ __device__ __noinline__ void phase_main(const Workspace& ws, const epos_fit_para
   if (tid < 12) best_model[tid] = st->best_model[tid];
   __syncthreads();
   bool ended = false, to_lo = false;
-  long long t_sample = 0, t_score = 0, t_replay = 0;
+  long long t_sample = 0, t_score = 0, t_replay = 0, n_scored = 0;
   const long long t_begin = clock64();
   while (true) {
     long long t0 = clock64();
@@ -556,6 +559,7 @@ __device__ __noinline__ void phase_main(const Workspace& ws, const epos_fit_para
         }
       }
       __syncthreads();
+      if (tid == 0) { int sc = 0; for (int k = 0; k < CHUNK; ++k) sc += recs[k].nm; n_scored += sc; }
       t_score += clock64() - t0; t0 = clock64();
     }
     // ---- in-order replay (every thread runs the same scalar code on the same records) ----
@@ -596,6 +600,7 @@ __device__ __noinline__ void phase_main(const Workspace& ws, const epos_fit_para
   }
   if (tid == 0) {
     st->t_sample += t_sample; st->t_score += t_score; st->t_replay += t_replay; st->t_total += clock64() - t_begin;
+    st->n_scored_main += n_scored;
     st->iter = iter; st->max_iteration = max_iteration; st->pass = pass; st->best_value = best_value;
     st->best_inl = best_inl; st->coverage = coverage; st->chunk_base = chunk_base; st->chunk_n = chunk_n;
     for (int i = 0; i < 12; ++i) st->best_model[i] = best_model[i];
@@ -846,6 +851,7 @@ __device__ __noinline__ void phase_trials(const Workspace& ws, const epos_fit_pa
   __syncthreads();
   if (tid == 0) {
     st->t_fit += t_fit;
+    for (int t = 0; t < n_eval; ++t) st->n_scored_lo += recs[t].ok ? 1 : 0;
     bool updated = false;
     int mv = st->lo_value, mi = st->lo_inl;
     if (sample_size < ni) {
@@ -963,6 +969,7 @@ __device__ __noinline__ void phase_final(const Workspace& ws, const epos_fit_par
   for (int i = 0; i < 12; ++i) best_model[i] = st->best_model[i];
   const int best_value = st->best_value;
   int nA, pxA;
+  int n_scored = 1;
   score_cta(sp, N, best_model, sq_trunc, bits, scan_sh, listA, &nA, &pxA, &red_sh);      // GCRANSAC.h:470-478
   PointView pv;
   pv.un = sp.un; pv.vn = sp.vn; pv.x = sp.x; pv.y = sp.y; pv.z = sp.z;
@@ -978,6 +985,7 @@ __device__ __noinline__ void phase_final(const Workspace& ws, const epos_fit_par
       if (!fit_list(listB, nB, m2)) break;
       int nC, pxC;
       score_cta(sp, N, m2, sq_trunc, bits, scan_sh, listC, &nC, &pxC, &red_sh);
+      ++n_scored;
       if (nC < 3) break;
       if (nC <= nB) break;
       for (int i = 0; i < 12; ++i) cur[i] = m2[i];
@@ -988,6 +996,7 @@ __device__ __noinline__ void phase_final(const Workspace& ws, const epos_fit_par
     if (iterations > 1) {
       int nC, pxC;
       score_cta(sp, N, cur, sq_trunc, bits, scan_sh, listC, &nC, &pxC, &red_sh);
+      ++n_scored;
       if (best_value < pxC) {
         refit_applied = true;
         for (int i = 0; i < 12; ++i) best_model[i] = cur[i];
@@ -1036,7 +1045,7 @@ __device__ __noinline__ void phase_final(const Workspace& ws, const epos_fit_par
   if (tid < 12) rec[tid] = best_model[tid];
   if (tid == 0) {
     rec[12] = (double)nA; rec[13] = (double)st->iter; rec[14] = 1.0; rec[15] = (double)st->gc_count;
-    st->found = 1; st->phase = PH_DONE; st->t_final += clock64() - t_begin;
+    st->found = 1; st->phase = PH_DONE; st->t_final += clock64() - t_begin; st->n_scored_final += n_scored;
   }
   const int off = offsets[p];
   for (int i = tid; i < nA; i += THREADS) labeling[off + listA[i]] = 1;
@@ -1119,8 +1128,9 @@ void epos_fit_params_default(epos_fit_params* p) {
 int epos_fit_max_points(void) { return NMAX; }
 
 // Profiling / debugging aid: copies per-problem counters out of a workspace after epos_fit_poses (synchronises).
-// out [P][16] i64: N, used_pixels, iterations, passes, graph_cuts, lo_runs, phase, best_inliers,
-//                  main-kernel clocks: sample+P3P, scoring, replay, total.
+// out [P][EPOS_FIT_DEBUG_COLS] i64: N, used_pixels, iterations, passes, graph_cuts, lo_runs, phase, best_inliers,
+//                  clocks (sample+P3P, scoring, replay, main total, cut, trials, final, trial fits),
+//                  models scored over all N points in main / LO trials / final, reserved.
 int epos_fit_debug_state(const void* workspace, int P, long long* out) {
   EPOS_CHECK_ARG(workspace && out && P > 0);
   Workspace ws;
@@ -1130,11 +1140,12 @@ int epos_fit_debug_state(const void* workspace, int P, long long* out) {
   cudaError_t e = cudaMemcpy(h, ws.st, (size_t)P * sizeof(ProbState), cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) { free(h); set_error("epos_fit_debug_state: %s", cudaGetErrorString(e)); return EPOS_ERR_CUDA; }
   for (int i = 0; i < P; ++i) {
-    long long* o = out + (size_t)i * 16;
+    long long* o = out + (size_t)i * EPOS_FIT_DEBUG_COLS;
     o[0] = h[i].N; o[1] = h[i].used_pixels; o[2] = (long long)h[i].iter; o[3] = h[i].pass; o[4] = h[i].gc_count;
     o[5] = h[i].lo_runs; o[6] = h[i].phase; o[7] = h[i].best_inl; o[8] = h[i].t_sample; o[9] = h[i].t_score;
     o[10] = h[i].t_replay; o[11] = h[i].t_total; o[12] = h[i].t_cut; o[13] = h[i].t_trials; o[14] = h[i].t_final;
     o[15] = h[i].t_fit;
+    o[16] = h[i].n_scored_main; o[17] = h[i].n_scored_lo; o[18] = h[i].n_scored_final; o[19] = 0;
   }
   free(h);
   return EPOS_OK;
@@ -1147,11 +1158,32 @@ size_t epos_fit_workspace_bytes(int P, int max_points, const epos_fit_params* pa
 }
 
 static int set_smem_attrs() {
-  static bool done = false;
-  if (done) return EPOS_OK;
+  static std::atomic<int> done[EPOS_MAX_DEVICES];
+  const int dslot = device_slot();
+  if (done[dslot].load(std::memory_order_acquire)) return EPOS_OK;
   EPOS_CUDA(cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PREP));
   EPOS_CUDA(cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FIT));
-  done = true;
+  done[dslot].store(1, std::memory_order_release);
+  return EPOS_OK;
+}
+
+// Optional per-launch timing of the two kernels with CUDA events on the launch stream (bench.py's RANSAC roofline).
+static bool g_fit_timing = false;
+static cudaEvent_t g_fit_ev[3] = {nullptr, nullptr, nullptr};
+
+int epos_fit_enable_timing(int on) {
+  g_fit_timing = on != 0;
+  if (g_fit_timing && !g_fit_ev[0])
+    for (int i = 0; i < 3; ++i) EPOS_CUDA(cudaEventCreate(&g_fit_ev[i]));
+  return EPOS_OK;
+}
+
+int epos_fit_last_kernel_ms(float* prep_ms, float* fit_ms) {
+  EPOS_CHECK_ARG(prep_ms && fit_ms);
+  if (!g_fit_ev[0]) { set_error("epos_fit_last_kernel_ms: timing was never enabled"); return EPOS_ERR_INVALID_ARG; }
+  EPOS_CUDA(cudaEventSynchronize(g_fit_ev[2]));
+  EPOS_CUDA(cudaEventElapsedTime(prep_ms, g_fit_ev[0], g_fit_ev[1]));
+  EPOS_CUDA(cudaEventElapsedTime(fit_ms, g_fit_ev[1], g_fit_ev[2]));
   return EPOS_OK;
 }
 
@@ -1173,11 +1205,14 @@ int epos_fit_poses(const double* coord_2d, const double* coord_3d, const int32_t
   Workspace ws;
   workspace_layout(P, workspace, &ws);
   cudaStream_t s = (cudaStream_t)stream;
+  if (g_fit_timing) EPOS_CUDA(cudaEventRecord(g_fit_ev[0], s));
   prep_kernel<<<P, PT, SMEM_PREP, s>>>(ws, coord_2d, coord_3d, offsets, counts, K,
                                             reinterpret_cast<const unsigned long long*>(seeds), *params, labeling, poses);
   EPOS_LAUNCH_CHECK();
+  if (g_fit_timing) EPOS_CUDA(cudaEventRecord(g_fit_ev[1], s));
   fit_kernel<<<P, THREADS, SMEM_FIT, s>>>(ws, *params, offsets, poses, labeling);
   EPOS_LAUNCH_CHECK();
+  if (g_fit_timing) EPOS_CUDA(cudaEventRecord(g_fit_ev[2], s));
   return EPOS_OK;
 }
 

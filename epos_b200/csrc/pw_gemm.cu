@@ -703,10 +703,12 @@ template <int BLOCK_N, int BLOCK_K, bool PAIR>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mw64, const GemmEpilogue& ep,
                        const ConvGeom& cg, int M, int N, int K, cudaStream_t stream, int dbg) {
   using Cfg = GemmCfg<BLOCK_N, BLOCK_K, PAIR>;
-  static bool attr = false;
-  static int max_pairs = 0;
+  static std::atomic<int> attr[EPOS_MAX_DEVICES];
+  static int max_pairs_dev[EPOS_MAX_DEVICES];
+  const int dslot = device_slot();
+  int& max_pairs = max_pairs_dev[dslot];
   auto kern = pw_gemm_kernel<BLOCK_N, BLOCK_K, PAIR>;
-  if (!attr) {
+  if (!attr[dslot].load(std::memory_order_acquire)) {
     EPOS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     if (PAIR) {
       cudaLaunchConfig_t q = {};
@@ -719,7 +721,7 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const CUten
       if (getenv("EPOS_GEMM_VERBOSE")) fprintf(stderr, "[epos] pw_gemm pair: max active clusters %d (SMs %d)\n", max_pairs, num_sms());
       if (max_pairs <= 0) { set_error("pw_gemm: no CTA pair fits (cudaOccupancyMaxActiveClusters = %d)", max_pairs); return EPOS_ERR_CUDA; }
     }
-    attr = true;
+    attr[dslot].store(1, std::memory_order_release);
   }
   // one CTA (or CTA pair) per SM (TPC); with less than a wave of tiles PieceMap spreads 64-column blocks
   const long long m_tiles = cg.enabled ? (long long)(M / (cg.H * cg.W)) * cg.tiles_x * cg.tiles_y : ceil_div(M, BLOCK_M);

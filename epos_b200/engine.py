@@ -46,20 +46,22 @@ class Engine:
                                                max_correspondences, seed, min_obj_conf=min_obj_conf,
                                                min_frag_rel_conf=min_frag_rel_conf)
 
-    def _fit(self, out, after_extract=None):
-        poses = self._fitter.fit(out, after_extract).clone()      # the fitter's record buffer is reused by the next batch
+    def _fit(self, out, after_extract=None, K=None):
+        poses = self._fitter.fit(out, after_extract, K).clone()      # the fitter's record buffer is reused by the next batch
         out['poses'] = poses
         if self.post_fit is not None:
             out['poses_all'] = self.post_fit(poses)
 
-    def run_device(self, images_dev):
-        """images_dev [B,H,W,3] f32 CUDA.  Returns a dict of CUDA tensors: model.predict's outputs for 'cnn',
-        plus 'poses' [B,O,16] f64 pose records for the full path (pipelined: valid after join() / out['ready'])."""
+    def run_device(self, images_dev, K=None):
+        """images_dev [B,H,W,3] f32 CUDA; K = this batch's camera intrinsics, [3,3] or [B,3,3] (default: the K given
+        at construction -- the reference reads K per image, scripts/infer.py:376-377).  Returns a dict of CUDA tensors:
+        model.predict's outputs for 'cnn', plus 'poses' [B,O,16] f64 pose records for the full path (pipelined: valid
+        after join() / out['ready'])."""
         out = self.net.predict(images_dev)
         if self._fitter is None:
             return out
         if not self.pipelined:
-            self._fit(out)
+            self._fit(out, K=K)
             return out
         main = torch.cuda.current_stream(self.dev)
         done_cnn = torch.cuda.Event()
@@ -74,7 +76,7 @@ class Engine:
             for t in maps:
                 t.record_stream(self._side)
             ev_maps = torch.cuda.Event()
-            self._fit(out, after_extract=lambda: ev_maps.record(self._side))
+            self._fit(out, after_extract=lambda: ev_maps.record(self._side), K=K)
             ev = torch.cuda.Event()
             ev.record(self._side)
         self._inflight.append((maps, ev_maps))
@@ -91,7 +93,7 @@ class Engine:
         """The tensor a caller reads back per batch: pose records (full path) or the object label map."""
         return out['poses'] if 'poses' in out else out[model.PRED_OBJ_LABEL]
 
-    def run_host(self, images_pinned, result_pinned=None):
+    def run_host(self, images_pinned, result_pinned=None, K=None):
         """End-to-end call with HOST buffers: H2D of the batch, the hot path, D2H of the result.
         Serial engine: returns this batch's result.  Pipelined engine: the D2H of this batch is queued behind its pose
         fitting on the side stream and the call returns the PREVIOUS batch's result (None on the first call); flush()
@@ -107,7 +109,7 @@ class Engine:
             x.record_stream(main)
         else:
             x = images_pinned.to(self.dev, non_blocking=True)
-        out = self.run_device(x)
+        out = self.run_device(x, K=K)
         r = self.result_tensor(out)
         if not self.pipelined:
             if result_pinned is None:

@@ -458,6 +458,7 @@ class EposNet:
 
 
 _NETS = {}
+_NETS_MAX = 2
 
 
 def predict(images, model_options=None, upsample_logits=False, image_pyramid=None, num_objs=None, num_frags=None,
@@ -467,8 +468,14 @@ def predict(images, model_options=None, upsample_logits=False, image_pyramid=Non
     if upsample_logits or image_pyramid or frag_cls_agnostic or frag_loc_agnostic:
         raise NotImplementedError('only the default inference configuration of scripts/infer.py is built')
     if net is None:
-        key = id(weights)
-        if key not in _NETS:
-            _NETS[key] = EposNet(weights, num_objs, num_frags, images.device, model_options)
-        net = _NETS[key]
+        # the cache entry holds a reference to the weights dict, so its id cannot be recycled while the entry lives;
+        # one network per (weights, head shape, options, device), at most _NETS_MAX kept (oldest evicted)
+        key = (id(weights), num_objs, num_frags, model_options, str(images.device))
+        hit = _NETS.get(key)
+        if hit is None or hit[0] is not weights:
+            hit = (weights, EposNet(weights, num_objs, num_frags, images.device, model_options))
+            _NETS[key] = hit
+            while len(_NETS) > _NETS_MAX:
+                _NETS.pop(next(iter(_NETS)))
+        net = hit[1]
     return net.predict(images)

@@ -48,6 +48,19 @@ class PoseFitter:
                                            _lib.stream_ptr()), 'epos_fit_poses')
         return poses, labeling
 
+    def debug_state(self, P):
+        """Per-problem counters of the last fit (synchronises): [P, EPOS_FIT_DEBUG_COLS] i64, columns as in
+        include/epos_b200.h."""
+        out = np.zeros((P, 20), np.int64)
+        _lib.check(self.lib.epos_fit_debug_state(self._ws_ptr, P, out.ctypes.data), 'epos_fit_debug_state')
+        return out
+
+    def algorithmic_bytes(self, P):
+        """SURVEY.md 8d RANSAC figure for the last fit: every model scored over a problem's N points reads
+        N x 40 B (u_n, v_n, x, y, z in f64) + N x 8 B (pixel id)."""
+        d = self.debug_state(P)
+        return float((d[:, 0] * (d[:, 16] + d[:, 17] + d[:, 18])).sum()) * 48.0
+
 
 class BatchFitter:
     """model.predict outputs -> correspondences -> poses for a whole batch: [B, J, 16] pose records on the device
@@ -66,31 +79,47 @@ class BatchFitter:
                                                  min_frag_rel_conf=min_frag_rel_conf, cap=max_correspondences,
                                                  max_correspondences=max_correspondences)
         self.J = len(self.extract.obj_ids_list)
-        self.K = np.asarray(K, np.float64)
+        self.K = None if K is None else np.asarray(K, np.float64)     # default intrinsics; a call may pass its own
         self.seed = int(seed)
         self._fitter = None
         self._Kdev = None
-        self._seeds = None
+        self._Khost = None
+        self._P = 0
         self.batch_index = 0
 
-    def _prepare(self, B):
+    def _prepare(self, B, K=None):
+        """Buffers for B images and the intrinsics of this batch.  The reference reads K per image
+        (samples[common.K][0], scripts/infer.py:376-377; BOP sets such as T-LESS have per-image intrinsics), so K is
+        [3,3] (all images) or [B,3,3]; the device copy is refreshed only when the values change."""
         P = B * self.J
         if self._fitter is None or self._fitter.P < P:
             self._fitter = PoseFitter(self.dev, P, self.params)
-        if self._Kdev is None or self._Kdev.shape[0] != P:
-            K = self.K if self.K.ndim == 3 else np.broadcast_to(self.K, (B, 3, 3))
-            self._Kdev = torch.from_numpy(np.ascontiguousarray(np.repeat(K, self.J, axis=0))).to(self.dev)
+        if self._P != P:
+            self._P = P
+            self._Kdev = torch.empty((P, 9), dtype=torch.float64, device=self.dev)
+            self._Khost = None
             self._poses = torch.empty((P, 16), dtype=torch.float64, device=self.dev)
             self._labeling = torch.empty((P * self.extract.cap,), dtype=torch.int32, device=self.dev)
             self._base = torch.arange(P, dtype=torch.int64, device=self.dev)
+        K = self.K if K is None else np.asarray(K, np.float64)
+        if K is None:
+            raise ValueError('camera intrinsics K are required ([3,3] or [B,3,3])')
+        if K.shape == (3, 3):
+            K = np.broadcast_to(K, (B, 3, 3))
+        if K.shape != (B, 3, 3):
+            raise ValueError('K should be [3,3] or [%d,3,3], got %s' % (B, K.shape))
+        if self._Khost is None or not np.array_equal(self._Khost, K):
+            self._Khost = np.array(K, np.float64)
+            rows = np.ascontiguousarray(np.repeat(self._Khost.reshape(B, 9), self.J, axis=0))
+            self._Kdev.copy_(torch.from_numpy(rows), non_blocking=False)
 
     def seeds_for(self, B):
         """Stream key of problem (image b, slot j) in batch n: seed * 2^32 + n * P + b * J + j."""
         return self._base + (self.seed << 32) + self.batch_index * (B * self.J)
 
-    def fit_maps(self, obj_conf, frag_conf, frag_loc, after_extract=None):
+    def fit_maps(self, obj_conf, frag_conf, frag_loc, after_extract=None, K=None):
         B = obj_conf.shape[0]
-        self._prepare(B)
+        self._prepare(B, K)
         bc = self.extract(obj_conf, frag_conf, frag_loc)
         self.corr = bc
         if after_extract is not None:
@@ -101,10 +130,10 @@ class BatchFitter:
                                       self._Kdev, seeds, self._poses, self._labeling)
         return poses.view(B, self.J, 16)
 
-    def fit(self, predictions, after_extract=None):
+    def fit(self, predictions, after_extract=None, K=None):
         from . import model
         return self.fit_maps(predictions[model.PRED_OBJ_CONF], predictions[model.PRED_FRAG_CONF],
-                             predictions[model.PRED_FRAG_LOC], after_extract)
+                             predictions[model.PRED_FRAG_LOC], after_extract, K)
 
 
 def find6DPoses(x1y1, x2y2z2, K, threshold=4.0, max_model_number=-1, conf=0.5, proposal_engine_conf=1.0,

@@ -205,9 +205,19 @@ size_t epos_fit_workspace_bytes(int P, int max_points, const epos_fit_params* pa
 /* Largest number of correspondences per problem (shared-memory resident point set): 4096. */
 int epos_fit_max_points(void);
 /* Profiling aid (synchronous): per-problem counters of the last epos_fit_poses on `workspace`.
- * out [P][16] i64 (host): N, used_pixels, iterations, passes, graph_cuts, lo_runs, phase, best_inliers, then clock64()
- * totals: main kernel sampling+P3P, scoring, replay, whole; cut, trials, final kernels; fits inside trials (warp 0). */
+ * out [P][EPOS_FIT_DEBUG_COLS] i64 (host): N, used_pixels, iterations, passes, graph_cuts, lo_runs, phase, best_inliers,
+ * then clock64() totals: main phase sampling+P3P, scoring, replay, whole; cut, trials, final phases; fits inside trials
+ * (warp 0); then the number of models scored over all N points in the main loop / the LO trials / the final phase
+ * (the "hypotheses" of SURVEY.md 8d's algorithmic-bytes figure: each costs N x 40 B of points + N x 8 B of pixel ids),
+ * one reserved column. */
+#define EPOS_FIT_DEBUG_COLS 20
 int epos_fit_debug_state(const void* workspace, int P, long long* out);
+
+/* Measurement aid: when enabled, epos_fit_poses records CUDA events on its stream around the set-up kernel and the
+ * persistent fitting kernel; epos_fit_last_kernel_ms waits for the last launch and returns both durations (the
+ * RANSAC roofline line of bench.py divides SURVEY.md 8d's algorithmic bytes by fit_ms). */
+int epos_fit_enable_timing(int on);
+int epos_fit_last_kernel_ms(float* prep_ms, float* fit_ms);
 
 #ifdef __cplusplus
 }

@@ -742,6 +742,65 @@ static void build_neighbors(Problem& pb, double radius, double scaling, int max_
   }
   const float r2 = (float)radius * (float)radius;
   pb.nbr.assign(N, std::vector<int>());
+  if (N == 0) return;
+  // Uniform grid over (u, v) with cells at least one radius wide: a point within the 5-D radius is within the radius
+  // in (u, v), hence in the 3 x 3 block of cells around the query.  The candidate SET is the one an all-pairs scan
+  // finds and (distance, index) pairs are ordered the same way, so the lists are identical to the O(N^2) search
+  // (the reference builds a KD-tree, flann_neighborhood_graph.h:86-125: sub-quadratic as well).
+  float mnu = q[0], mxu = q[0], mnv = q[1], mxv = q[1];
+  bool finite = true;
+  for (int i = 0; i < N; ++i) {
+    mnu = std::min(mnu, q[5 * i]); mxu = std::max(mxu, q[5 * i]);
+    mnv = std::min(mnv, q[5 * i + 1]); mxv = std::max(mxv, q[5 * i + 1]);
+    finite = finite && std::isfinite(q[5 * i]) && std::isfinite(q[5 * i + 1]);
+  }
+  float cs = (float)radius * 1.0001f + 1e-6f;
+  long long gw = 1, gh = 1;
+  if (finite) {
+    for (;;) {
+      gw = (long long)std::floor((mxu - mnu) / cs) + 1;
+      gh = (long long)std::floor((mxv - mnv) / cs) + 1;
+      if (gw * gh <= (1 << 22)) break;
+      cs *= 2.0f;
+    }
+  }
+  auto cell = [&](int i, long long* cx, long long* cy) {
+    if (!finite) { *cx = *cy = 0; return; }
+    long long x = (long long)std::floor((q[5 * i] - mnu) / cs), y = (long long)std::floor((q[5 * i + 1] - mnv) / cs);
+    *cx = std::min(std::max(x, 0LL), gw - 1); *cy = std::min(std::max(y, 0LL), gh - 1);
+  };
+  std::vector<std::vector<int>> cells((size_t)(gw * gh));
+  for (int i = 0; i < N; ++i) { long long cx, cy; cell(i, &cx, &cy); cells[(size_t)(cy * gw + cx)].push_back(i); }
+  std::vector<std::pair<float, int>> cand;
+  for (int i = 0; i < N; ++i) {
+    cand.clear();
+    long long cx, cy;
+    cell(i, &cx, &cy);
+    for (long long yy = std::max(cy - 1, 0LL); yy <= std::min(cy + 1, gh - 1); ++yy)
+      for (long long xx = std::max(cx - 1, 0LL); xx <= std::min(cx + 1, gw - 1); ++xx)
+        for (int j : cells[(size_t)(yy * gw + xx)]) {
+          if (j == i) continue;
+          float d = 0.f;
+          for (int k = 0; k < 5; ++k) { float e = q[5 * i + k] - q[5 * j + k]; d = std::fmaf(e, e, d); }
+          if (d <= r2) cand.emplace_back(d, j);
+        }
+    size_t keep = std::min(cand.size(), (size_t)max_nbr);
+    std::partial_sort(cand.begin(), cand.begin() + keep, cand.end());
+    for (size_t k = 0; k < keep; ++k) pb.nbr[i].push_back(cand[k].second);
+  }
+}
+
+// All-pairs form of the same search (tests/test_oracle_pose.py checks the two agree).
+static void build_neighbors_bruteforce(Problem& pb, double radius, double scaling, int max_nbr) {
+  const int N = pb.N;
+  std::vector<float> q((size_t)5 * N);
+  for (int i = 0; i < N; ++i) {
+    const double* r = &pb.pts[(size_t)7 * i];
+    q[5 * i] = (float)r[5]; q[5 * i + 1] = (float)r[6];
+    q[5 * i + 2] = (float)(r[2] * scaling); q[5 * i + 3] = (float)(r[3] * scaling); q[5 * i + 4] = (float)(r[4] * scaling);
+  }
+  const float r2 = (float)radius * (float)radius;
+  pb.nbr.assign(N, std::vector<int>());
   std::vector<std::pair<float, int>> cand;
   for (int i = 0; i < N; ++i) {
     cand.clear();
@@ -1138,6 +1197,15 @@ int ora_neighbors(int N, const double* x2d, const double* x3d, const double* K, 
   ora::Problem pb;
   ora::make_problem(N, x2d, x3d, K, *P, pb);
   ora::build_neighbors(pb, P->neighborhood_ball_radius, P->scaling_from_millimeters, P->max_neighbors);
+  for (int i = 0; i < N; ++i)
+    for (int k = 0; k < P->max_neighbors; ++k) out[i * P->max_neighbors + k] = k < (int)pb.nbr[i].size() ? pb.nbr[i][k] : -1;
+  return 0;
+}
+
+int ora_neighbors_bruteforce(int N, const double* x2d, const double* x3d, const double* K, const ora_params* P, int* out) {
+  ora::Problem pb;
+  ora::make_problem(N, x2d, x3d, K, *P, pb);
+  ora::build_neighbors_bruteforce(pb, P->neighborhood_ball_radius, P->scaling_from_millimeters, P->max_neighbors);
   for (int i = 0; i < N; ++i)
     for (int k = 0; k < P->max_neighbors; ++k) out[i * P->max_neighbors + k] = k < (int)pb.nbr[i].size() ? pb.nbr[i][k] : -1;
   return 0;

@@ -136,6 +136,16 @@ def neighbors(x2d, x3d, K, params=None):
     return out
 
 
+def neighbors_bruteforce(x2d, x3d, K, params=None):
+    """All-pairs form of neighbors() (same lists; kept to test the grid-binned search)."""
+    params = params or default_params()
+    x2d, x3d, K = _d(x2d), _d(x3d), _d(K)
+    n = x2d.shape[0]
+    out = np.zeros((n, params.max_neighbors), np.int32)
+    lib().ora_neighbors_bruteforce(n, _p(x2d), _p(x3d), _p(K), C.byref(params), _p(out, C.c_int))
+    return out
+
+
 def _csr(nbr):
     """[-1 padded N x k] or list of lists -> (offsets, index)."""
     lists = [[int(j) for j in row if j >= 0] for row in nbr]

@@ -36,11 +36,11 @@ c = bc.counts.cpu().numpy().reshape(B, O); t = bc.totals.cpu().numpy().reshape(B
 print('counts img0', c[0].tolist()); print('totals img0', t[0].tolist())
 r = poses.cpu().numpy().reshape(B, O, 16)
 print('valid', int((r[..., 14] == 1).sum()), 'of', B * O, 'iterations mean', r[..., 13].mean(), 'graph cuts mean', r[..., 15].mean())
-dbg = np.zeros((B * O, 16), np.int64)
+dbg = np.zeros((B * O, 20), np.int64)
 _lib.check(_lib.lib().epos_fit_debug_state(bf._fitter._ws_ptr, B * O, dbg.ctypes.data), 'dbg')
 tot_c = dbg[:, 11] + dbg[:, 12] + dbg[:, 13] + dbg[:, 14]
 order = np.argsort(-tot_c)[:10]
 print('slowest problems: [N, used_px, iters, passes, gcuts, lo_runs, phase, best_inl] | Mcycles main(sample, score, replay, total) cut trials final fit-in-trials')
 for i in order:
-    print(i, dbg[i, :8].tolist(), (dbg[i, 8:] / 1e6).round(2).tolist())
+    print(i, dbg[i, :8].tolist(), (dbg[i, 8:16] / 1e6).round(2).tolist())
 print('sum over problems (Mcycles): main %.1f cut %.1f trials %.1f final %.1f' % tuple(dbg[:, k].sum() / 1e6 for k in (11, 12, 13, 14)))

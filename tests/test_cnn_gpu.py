@@ -327,6 +327,12 @@ def test_network_full_size_ycbv_heads():
     _net_parity(2, 480, 640, 21, 64, seed=14)
 
 
+def test_network_full_size_config5_heads():
+    """BASELINE configs[4] head shape: 30 objects x 256 fragments at 640x480 (N = 7 680 conf + 23 040 loc columns,
+    2.36 GB of head maps per image, row-softmax path for F = 256)."""
+    _net_parity(1, 480, 640, 30, 256, seed=15)
+
+
 # The variance-scaling initialiser with perturbed BN statistics leaves decoder features of magnitude ~1e3-1e4; the logit
 # stddev is scaled down so that the logits stay O(1-10) and the softmax outputs are a meaningful comparison.
 def test_resnet50_beta_small():

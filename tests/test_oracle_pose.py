@@ -232,6 +232,23 @@ def test_neighbors_are_nearest_within_radius(golden):
         assert np.allclose(sorted(d2[i, got]), sorted(d2[i, exp]), rtol=1e-5)
 
 
+def test_grid_binned_neighbour_search_equals_all_pairs(golden):
+    """The oracle's neighbour graph is built with a uniform (u, v) grid (sub-quadratic, like the reference's KD-tree);
+    the lists must be identical to the all-pairs scan on dense, sparse and degenerate point sets."""
+    g = golden('tless.json')
+    c, K = np.array(g['corrs']), np.array(g['K'])
+    rng = np.random.default_rng(0)
+    cases = [(c[:, :2], c[:, 2:])]
+    cases.append((4.0 * (rng.integers(0, 160, (3000, 2)) + 0.5), rng.uniform(-100, 100, (3000, 3))))     # dense pixel grid
+    cases.append((rng.uniform(0, 640, (50, 2)), rng.uniform(-5, 5, (50, 3))))                             # sparse
+    cases.append((np.tile([[100.0, 100.0]], (40, 1)), np.tile([[1.0, 2.0, 3.0]], (40, 1))))               # all identical
+    cases.append((np.stack([np.linspace(0, 1e5, 300), np.zeros(300)], 1), rng.uniform(-5, 5, (300, 3))))  # huge extent
+    for uv, X in cases:
+        for k in (5, 8):
+            p = pf.default_params(max_neighbors=k)
+            assert np.array_equal(pf.neighbors(uv, X, K, p), pf.neighbors_bruteforce(uv, X, K, p))
+
+
 def test_find6dposes_argument_checks():
     K = np.eye(3)
     with pytest.raises(ValueError):
