@@ -45,6 +45,7 @@ _SIGS = {
     'epos_corresp_workspace_bytes': (sz, [i32, i32, i32, i32]),
     'epos_fit_max_points': (i32, []),
     'epos_fit_debug_state': (i32, [vp, i32, vp]),
+    'epos_fit_debug_trace': (i32, [vp, i32, i32, vp]),
     'epos_fit_enable_timing': (i32, [i32]),
     'epos_fit_last_kernel_ms': (i32, [C.POINTER(f32), C.POINTER(f32)]),
     'epos_fit_params_default': (None, [C.POINTER(FitParams)]),

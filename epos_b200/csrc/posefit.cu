@@ -35,6 +35,11 @@ constexpr int TRIAL_THREADS = THREADS;
 constexpr int PER_THREAD = (NMAX + THREADS - 1) / THREADS;   // contiguous points per thread in ordered compactions
 constexpr int DIST_INF = 0x7fffffff;
 constexpr size_t SMEM_CUT_DYN = 222 * 1024;
+// Residual capacities below CUT_EPS count as saturated when the SINK segment is determined (capacities are O(lambda) =
+// O(0.1)): exact-arithmetic ties (an outlier whose terminal capacity equals the total capacity of its arcs) are then
+// resolved the same way by every max-flow algorithm, the oracle's Dinic included (oracle/posefit.cpp).
+constexpr double CUT_EPS = 1e-9;
+constexpr int TRACE_ROUNDS = 16, TRACE_COLS = 72;   // debugging aid (epos_fit_debug_trace)
 
 enum Phase { PH_MAIN = 0, PH_LO = 1, PH_FINAL = 2, PH_DONE = 3 };
 
@@ -75,6 +80,7 @@ struct Workspace {
   int* lstart;              // [P][NMAX+2]  BFS level boundaries
   unsigned short* order;    // [P][NMAX]    BFS queue
   PassRecord* recs;         // [P][CHUNK]   hypotheses of the current chunk of RANSAC passes
+  int* trace;               // [P][TRACE_ROUNDS][TRACE_COLS] LO rounds: gc, ni, updated, lo_value, lo_inl, (ok, inl, pix) x 20
 };
 
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
@@ -99,6 +105,7 @@ static size_t workspace_layout(int P, void* base, Workspace* w) {
   p = take((size_t)P * (NMAX + 2) * 4); if (w) w->lstart = (int*)p;
   p = take((size_t)P * NMAX * 2); if (w) w->order = (unsigned short*)p;
   p = take((size_t)P * 80 * 432); if (w) w->recs = (PassRecord*)p;
+  p = take((size_t)P * TRACE_ROUNDS * TRACE_COLS * 4); if (w) w->trace = (int*)p;
   return off;
 }
 
@@ -702,7 +709,7 @@ __device__ __noinline__ void phase_cut(const Workspace& ws, const epos_fit_param
     if (tid == 0) { s_qn = 0; s_any = 0; }
     __syncthreads();
     for (int i = tid; i < N; i += THREADS) {
-      const bool root = exc[i] < 0.0;
+      const bool root = exc[i] < -CUT_EPS;
       dist[i] = root ? 0 : DIST_INF;
       if (root) order[atomicAdd(&s_qn, 1)] = (unsigned short)i;
     }
@@ -715,7 +722,7 @@ __device__ __noinline__ void phase_cut(const Workspace& ws, const epos_fit_param
         for (int k = 0; k < KN; ++k)                                 // edges owned by v: arc u -> v has residual lambda + flow
           if (owned[(size_t)v * MAXNB + k]) {
             const int u = nbr[(size_t)v * MAXNB + k];
-            if (dist[u] == DIST_INF && lambda + flow[(size_t)v * KN + k] > 0.0 &&
+            if (dist[u] == DIST_INF && lambda + flow[(size_t)v * KN + k] > CUT_EPS &&
                 atomicCAS(&dist[u], DIST_INF, level + 1) == DIST_INF) {
               order[atomicAdd(&s_qn, 1)] = (unsigned short)u;
               if (exc[u] > 0.0) s_any = 1;
@@ -725,7 +732,7 @@ __device__ __noinline__ void phase_cut(const Workspace& ws, const epos_fit_param
           const int e0 = rev_idx[a];
           const int u = e0 / MAXNB;
           const size_t e = (size_t)u * KN + (e0 % MAXNB);
-          if (dist[u] == DIST_INF && capf[e] - flow[e] > 0.0 && atomicCAS(&dist[u], DIST_INF, level + 1) == DIST_INF) {
+          if (dist[u] == DIST_INF && capf[e] - flow[e] > CUT_EPS && atomicCAS(&dist[u], DIST_INF, level + 1) == DIST_INF) {
             order[atomicAdd(&s_qn, 1)] = (unsigned short)u;
             if (exc[u] > 0.0) s_any = 1;
           }
@@ -871,6 +878,15 @@ __device__ __noinline__ void phase_trials(const Workspace& ws, const epos_fit_pa
       }
     }
     st->lo_value = mv; st->lo_inl = mi;
+    if (gc >= 1 && gc <= TRACE_ROUNDS) {
+      int* tr = ws.trace + ((size_t)p * TRACE_ROUNDS + (gc - 1)) * TRACE_COLS;
+      tr[0] = gc; tr[1] = ni; tr[2] = updated ? 1 : 0; tr[3] = mv; tr[4] = mi;
+      for (int t = 0; t < MAX_TRIALS; ++t) {
+        const bool have = t < n_eval;
+        tr[5 + 3 * t] = have ? recs[t].ok : -1; tr[6 + 3 * t] = have && recs[t].ok ? recs[t].inl : 0;
+        tr[7 + 3 * t] = have && recs[t].ok ? recs[t].pix : 0;
+      }
+    }
     if (updated) st->lo_stage = 0;                                  // another labeling round (GCRANSAC.h:794-796)
     else finalize_lo(st, prm);
     st->t_trials += clock64() - t_begin;
@@ -1148,6 +1164,18 @@ int epos_fit_debug_state(const void* workspace, int P, long long* out) {
     o[16] = h[i].n_scored_main; o[17] = h[i].n_scored_lo; o[18] = h[i].n_scored_final; o[19] = 0;
   }
   free(h);
+  return EPOS_OK;
+}
+
+// Debugging aid (synchronous): the local-optimisation rounds of problem p of the last epos_fit_poses:
+// out [16][72] i32 rows (graph-cut number, labelled inliers, updated, lo value, lo inliers, then (ok, inliers, pixels)
+// of the 20 inner fits; ok = -1: trial not evaluated).  Rows of rounds that did not run keep stale data.
+int epos_fit_debug_trace(const void* workspace, int P, int p, int32_t* out) {
+  EPOS_CHECK_ARG(workspace && out && P > 0 && p >= 0 && p < P);
+  Workspace ws;
+  workspace_layout(P, const_cast<void*>(workspace), &ws);
+  EPOS_CUDA(cudaMemcpy(out, ws.trace + (size_t)p * TRACE_ROUNDS * TRACE_COLS, (size_t)TRACE_ROUNDS * TRACE_COLS * 4,
+                       cudaMemcpyDeviceToHost));
   return EPOS_OK;
 }
 

@@ -213,6 +213,11 @@ int epos_fit_max_points(void);
 #define EPOS_FIT_DEBUG_COLS 20
 int epos_fit_debug_state(const void* workspace, int P, long long* out);
 
+/* Debugging aid (synchronous): local-optimisation rounds of problem p of the last epos_fit_poses.
+ * out [16][72] i32: graph-cut number, labelled inliers, updated, LO value, LO inliers, then (ok, inliers, pixels) of
+ * the 20 inner fits (ok = -1: not evaluated). */
+int epos_fit_debug_trace(const void* workspace, int P, int p, int32_t* out);
+
 /* Measurement aid: when enabled, epos_fit_poses records CUDA events on its stream around the set-up kernel and the
  * persistent fitting kernel; epos_fit_last_kernel_ms waits for the last launch and returns both durations (the
  * RANSAC roofline line of bench.py divides SURVEY.md 8d's algorithmic bytes by fit_ms). */

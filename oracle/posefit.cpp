@@ -819,6 +819,8 @@ static void build_neighbors_bruteforce(Problem& pb, double radius, double scalin
 // ---------------------------------------------------------------------------------------------------
 // graph-cut labeling (GCRANSAC.h:812-920, energy.h:204-253): returns the SINK segment (inliers)
 // ---------------------------------------------------------------------------------------------------
+constexpr double CUT_EPS = 1e-9;     // capacities are O(lambda) = O(0.1)
+
 struct Dinic {
   struct Arc { int to; double cap; };
   std::vector<Arc> arcs;
@@ -918,7 +920,11 @@ static void labeling(const Problem& pb, const double* model, double lambda, std:
   }
   for (size_t e = 0; e < g.ex.size(); ++e) dn.add(g.ex[e], g.ey[e], g.cxy[e], g.cyx[e]);
   dn.run(S, Tn);
-  // SINK segment = nodes that can still reach the sink through residual arcs
+  // SINK segment = nodes that can still reach the sink through residual arcs.  A residual capacity below CUT_EPS
+  // counts as saturated: when an outlier's terminal capacity equals the total capacity of its arcs in exact arithmetic
+  // (e.g. exactly (1-lambda)/lambda incident edges towards inliers) both labelings have the same energy and the
+  // answer of ANY floating-point max-flow (the reference's BK included) hinges on the rounding of its own sequence of
+  // subtractions; the tolerance makes the answer the exact-arithmetic one (saturated -> SOURCE) for every algorithm.
   std::vector<char> in_t(N + 2, 0);
   std::queue<int> q;
   in_t[Tn] = 1; q.push(Tn);
@@ -926,7 +932,7 @@ static void labeling(const Problem& pb, const double* model, double lambda, std:
     int v = q.front(); q.pop();
     for (int a : dn.adj[v]) {
       int u = dn.arcs[a].to;                                            // arc a: v->u ; its pair a^1: u->v
-      if (!in_t[u] && dn.arcs[a ^ 1].cap > 0) { in_t[u] = 1; q.push(u); }
+      if (!in_t[u] && dn.arcs[a ^ 1].cap > CUT_EPS) { in_t[u] = 1; q.push(u); }
     }
   }
   inliers.clear();
@@ -971,6 +977,9 @@ static int generate_models(const Problem& pb, const Params& P, u64 seed, int pas
   return nm;
 }
 
+// debugging aid: rows of 72 ints per LO round, same layout as the CUDA library's epos_fit_debug_trace
+static std::vector<int> g_trace;
+
 static void local_optimization(const Problem& pb, const Params& P, u64 seed, Stats& st, double* best_model,
                                Score& best_score) {
   Score max_score = best_score;
@@ -983,8 +992,11 @@ static void local_optimization(const Problem& pb, const Params& P, u64 seed, Sta
     labeling(pb, lo_model, P.spatial_coherence_weight, inliers);
     const int ni = (int)inliers.size();
     const int sample_size = std::min(21, ni);
+    std::vector<int> row(72, 0);
+    for (int t = 0; t < 20; ++t) row[5 + 3 * t] = -1;
     for (int trial = 0; trial < P.max_lo_trials; ++trial) {
       double model[12];
+      if (trial < 20) row[5 + 3 * trial] = 0;
       if (sample_size < ni) {
         int sel[21], idx[21];
         unique_set(seed, 1, (u64)st.graph_cuts, (u64)trial, ni, sample_size, sel);
@@ -996,12 +1008,18 @@ static void local_optimization(const Problem& pb, const Params& P, u64 seed, Sta
         break;
       }
       Score s = get_score(pb, model, max_score.inliers, nullptr);
+      if (trial < 20) {
+        Score raw = get_score(pb, model, 0, nullptr);
+        row[5 + 3 * trial] = 1; row[6 + 3 * trial] = (int)raw.inliers; row[7 + 3 * trial] = (int)raw.value;
+      }
       if (max_score.value < s.value) {
         updated = true;
         max_score = s;
         std::memcpy(lo_model, model, sizeof(lo_model));
       }
     }
+    row[0] = st.graph_cuts; row[1] = ni; row[2] = updated ? 1 : 0; row[3] = (int)max_score.value; row[4] = (int)max_score.inliers;
+    g_trace.insert(g_trace.end(), row.begin(), row.end());
     if (!updated) break;
   }
   if (best_score.value < max_score.value) {
@@ -1266,11 +1284,19 @@ int ora_cut_graph(int N, const double* x2d, const double* x3d, const double* K, 
   return E;
 }
 
+// LO trace of the last ora_find6dposes call: returns the number of rounds, copies up to cap rows of 72 ints
+int ora_last_trace(int* out, int cap) {
+  int rounds = (int)(ora::g_trace.size() / 72);
+  for (int r = 0; r < rounds && r < cap; ++r) std::memcpy(out + 72 * r, ora::g_trace.data() + 72 * r, 72 * sizeof(int));
+  return rounds;
+}
+
 // find6DPoses, single-instance branch.  stats: {iterations, graph_cuts, lo_runs, passes, found}
 int ora_find6dposes(int N, const double* x2d, const double* x3d, const double* K, const ora_params* P,
                     unsigned long long seed, const int* nbr_offsets, const int* nbr_index, double* pose,
                     int* labeling_out, int* stats) {
   ora::Stats st;
+  ora::g_trace.clear();
   int r = ora::find6dposes(N, x2d, x3d, K, *P, seed, nbr_offsets, nbr_index, pose, labeling_out, st);
   if (stats) { stats[0] = st.iterations; stats[1] = st.graph_cuts; stats[2] = st.lo_runs; stats[3] = st.passes; stats[4] = st.found; }
   return r;

@@ -119,7 +119,34 @@ def cv2_solvepnp():
     dump('cv2_solvepnp.json', {'cv2_version': cv2.__version__, 'cases': cases, 'rodrigues': rod})
 
 
+def tie_case():
+    """case_b2_o2.npz: problem (image 2, object 2) of the planted 8 x 21 batch of tests/test_pose_gpu.py, the first scene
+    on which a graph-cut TIE showed (an outlier node with exactly (1-lambda)/lambda = 9 incident edges): correspondences,
+    K, the model that is labelled (best P3P hypothesis of the first 11 passes) and the RANSAC stream key."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from epos_b200 import synthetic
+    from oracle import pipeline, posefit as pf
+    O, F, B = 21, 64, 8
+    store, K = synthetic.model_store(O, F), synthetic.default_K()
+    oc, fc, fl, _ = synthetic.planted_maps(B, O, F, store, K, seed=21, objs_per_image=5)
+    pp = pipeline.PostProcess(O, F, seed=9, model_store=store, K=K, max_correspondences=2048)
+    d = pp.corresp({'pred_obj_conf': oc, 'pred_frag_conf': fc, 'pred_frag_loc': fl}, 2)[2]
+    seed = (9 << 32) + 2 * 21 + 1
+    p = pf.default_params()
+    best, bv, bi = None, 0, 0
+    for ps in range(11):
+        models, _, _ = pf.generate_models(d['coord_2d'], d['coord_3d'], K, seed, ps, p)
+        for m in models:
+            sc = pf.score(d['coord_2d'], d['coord_3d'], K, m, p, best_inl=bi)
+            if bv < sc['value']:
+                bv, bi, best = sc['value'], sc['inliers'], m.copy()
+    np.savez_compressed(os.path.join(OUT, "case_b2_o2.npz"), c2=d['coord_2d'], c3=d['coord_3d'], K=K, model=best,
+                        seed=np.int64(seed))
+
+
 if __name__ == '__main__':
+    tie_case()
     slim()
     pnp16()
     scenes()

@@ -2,6 +2,8 @@
 (SURVEY.md section 4 / 8c): the 16-correspondence notebook answer, the pose6dscene and T-LESS fixtures, outputs of
 cv2.solvePnP(ITERATIVE)/cv2.Rodrigues recorded from the cv2 wheel, and the reference's own BK max-flow
 (oracle/_ref, built from /root/reference when present) for the graph-cut labeling."""
+import os
+
 import numpy as np
 import pytest
 
@@ -172,10 +174,31 @@ def test_tless_fixture(golden):
     assert sum(hits) >= 4, hits
 
 
+def _cut_energy(g, lam, labels):
+    """Energy of a labeling under the terms handed to add_term1 / add_term2 (GCRANSAC.h:843-907)."""
+    e = float(np.where(labels == 1, g['u1'], g['u0']).sum())
+    a, b = labels[g['ex']], labels[g['ey']]
+    return e + float(np.where((a == 0) & (b == 0), g['e00'], np.where(a != b, lam, 0.0)).sum())
+
+
+def _assert_same_cut(lab, ref, g, lam):
+    """Identical labelings, except on exact-arithmetic TIES: when the terminal capacity of a group of nodes equals the
+    total capacity of its arcs, both labels are optimal and the reference's BK answer depends on the rounding of its own
+    subtraction sequence.  The oracle (and the CUDA kernel) resolve ties as exact arithmetic does (saturated ->
+    SOURCE); a mismatch is accepted only if both labelings are minimum cuts of the same energy."""
+    if np.array_equal(lab, ref):
+        return 0
+    ea, eb = _cut_energy(g, lam, lab), _cut_energy(g, lam, ref)
+    assert abs(ea - eb) < 1e-9 * max(1.0, abs(eb)), (ea, eb)
+    assert (lab != ref).sum() <= 8 and (lab <= ref).all()       # ties resolve towards SOURCE (outlier)
+    return int((lab != ref).sum())
+
+
 def test_labeling_matches_reference_bk_maxflow(golden):
     """oracle labeling (Dinic + reverse BFS) == the reference's own BK max-flow + what_segment on the same energy."""
     if pf.ref_lib() is None:
         pytest.skip('oracle/_ref not built (reference tree absent)')
+    ties = 0
     g = golden('tless.json')
     c, K, gts = np.array(g['corrs']), np.array(g['K']), np.array(g['gt_poses'])
     rng = np.random.default_rng(3)
@@ -190,8 +213,8 @@ def test_labeling_matches_reference_bk_maxflow(golden):
         for lam in (0.1, 0.3):
             p = pf.default_params(spatial_coherence_weight=lam)
             lab = pf.labeling(c[:, :2], c[:, 2:], K, model, nbr=nbr, params=p)
-            ref = pf.ref_bk_labeling(pf.cut_graph(c[:, :2], c[:, 2:], K, model, nbr, params=p), lam)
-            assert np.array_equal(lab, ref), (trial, lam, int((lab != ref).sum()))
+            gr = pf.cut_graph(c[:, :2], c[:, 2:], K, model, nbr, params=p)
+            ties += _assert_same_cut(lab, pf.ref_bk_labeling(gr, lam), gr, lam)
             checked += 1
             thr = pf.score(c[:, :2], c[:, 2:], K, model)['mask']
             if trial == 0 and lam == 0.1:
@@ -213,8 +236,17 @@ def test_labeling_matches_reference_bk_maxflow(golden):
         for lam in ((0.23, 0.3) if dense else (0.1, 0.3)):
             p = pf.default_params(spatial_coherence_weight=lam)
             lab = pf.labeling(uv, X, K2, model, nbr=nb, params=p)
-            ref = pf.ref_bk_labeling(pf.cut_graph(uv, X, K2, model, nb, params=p), lam)
-            assert np.array_equal(lab, ref)
+            gr = pf.cut_graph(uv, X, K2, model, nb, params=p)
+            ties += _assert_same_cut(lab, pf.ref_bk_labeling(gr, lam), gr, lam)
+    assert ties <= 12                                            # a handful of tie nodes over 48 graphs
+    # the planted scene on which the tie first showed (an outlier with 9 incident edges at lambda = 0.1): here the
+    # reference's BK lands on the exact-arithmetic answer as well
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'case_b2_o2.npz'))
+    p = pf.default_params()
+    nbr = pf.neighbors(d['c2'], d['c3'], d['K'], p)
+    lab = pf.labeling(d['c2'], d['c3'], d['K'], d['model'], nbr=nbr, params=p)
+    gr = pf.cut_graph(d['c2'], d['c3'], d['K'], d['model'], nbr, params=p)
+    assert np.array_equal(lab, pf.ref_bk_labeling(gr, 0.1)) and lab.sum() == 1336
 
 
 def test_neighbors_are_nearest_within_radius(golden):
