@@ -43,6 +43,8 @@ _SIGS = {
     'epos_corresp': (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, f64, f32, f32, i32, i32,
                            vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     'epos_corresp_workspace_bytes': (sz, [i32, i32, i32, i32]),
+    'epos_corresp_lazy_loc': (i32, [vp, vp, vp, i32, sz, i32, vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, f64, f32,
+                                    f32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     'epos_fit_max_points': (i32, []),
     'epos_fit_debug_state': (i32, [vp, i32, vp]),
     'epos_fit_debug_trace': (i32, [vp, i32, i32, vp]),

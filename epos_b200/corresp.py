@@ -46,8 +46,10 @@ class CorrespExtractor:
         self.max_corr = 0 if max_correspondences is None else int(max_correspondences)
         self._out = None
 
-    def __call__(self, obj_conf, frag_conf, frag_loc, out=None):
-        """obj_conf [B,h,w,O+1], frag_conf [B,h,w,O,F], frag_loc [B,h,w,O,F,3] f32 CUDA -> BatchCorresp."""
+    def __call__(self, obj_conf, frag_conf, frag_loc, out=None, lazy_loc=None):
+        """obj_conf [B,h,w,O+1], frag_conf [B,h,w,O,F], frag_loc [B,h,w,O,F,3] f32 CUDA -> BatchCorresp.
+        frag_loc = None with lazy_loc = (feat_split [2,B*h*w,ld] bf16, w_loc [O*F*3,C] f32, b_loc [O*F*3] f32 or None):
+        the localisation head is evaluated only at the surviving rows (epos_corresp_lazy_loc)."""
         B, h, w = obj_conf.shape[:3]
         J = len(self.obj_ids_list)
         if out is None:
@@ -55,6 +57,21 @@ class CorrespExtractor:
             if o is None or (o.B, o.J, o.cap, o.h, o.w) != (B, J, self.cap, h, w):
                 o = self._out = BatchCorresp(self.dev, B, J, self.cap, h, w)
             out = o
+        if frag_loc is None:
+            feat, w_loc, b_loc = lazy_loc
+            for t in (obj_conf, frag_conf, w_loc):
+                assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+            assert feat.dtype == torch.bfloat16 and feat.dim() == 3 and feat.shape[1] == B * h * w and feat.stride(2) == 1
+            _lib.check(self.lib.epos_corresp_lazy_loc(
+                obj_conf.data_ptr(), frag_conf.data_ptr(), feat.data_ptr(), feat.stride(1), feat.stride(0), w_loc.shape[1],
+                w_loc.data_ptr(), _lib.ptr(b_loc), B, h, w, self.O, self.F,
+                self.obj_ids.data_ptr(), J, self.centers.data_ptr(), self.sizes.data_ptr(), float(self.output_scale),
+                float(self.min_obj_conf), float(self.min_frag_rel_conf), self.cap, self.max_corr,
+                out.coord_2d.data_ptr(), out.coord_3d.data_ptr(), out.conf.data_ptr(), out.conf_obj.data_ptr(),
+                out.conf_frag.data_ptr(), out.px.data_ptr(), out.frag.data_ptr(), out.counts.data_ptr(),
+                out.totals.data_ptr(), out.workspace.data_ptr(), out.workspace.numel(), _lib.stream_ptr()),
+                'epos_corresp_lazy_loc')
+            return out
         for t in (obj_conf, frag_conf, frag_loc):
             assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
         _lib.check(self.lib.epos_corresp(

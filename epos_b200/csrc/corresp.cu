@@ -28,6 +28,10 @@ struct CorrArgs {
   int cap, max_corr;
   double* c2d; double* c3d; float* conf; float* conf_obj; float* conf_frag; int* px; int* frag; int* counts; int* totals;
   unsigned int* ws;                // workspace [B*J][4][HW+1]: masked-pixel list, obj_conf, row max, emission offsets
+  // lazy localisation head (frag_loc == NULL): pred_frag_loc is never materialised; the three local coordinates of a
+  // surviving (pixel, object, fragment) row are computed here from the decoder features and the logit weights
+  const uint16_t* feat; int ldf; long long feat_plane;     // split-bf16 decoder features [2][B*h*w][ldf], C = feat_c
+  const float* w_loc; const float* b_loc; int feat_c;      // logits/pred_frag_loc weights [O*F*3][feat_c] f32, bias
 };
 
 __device__ inline int block_scan_excl(int v, int* sh, int* total) {
@@ -107,19 +111,63 @@ __device__ inline void write_row(const CorrArgs& a, int b, int obj_id, size_t ds
   a.c2d[2 * dst] = a.inv_scale * ((double)x + 0.5);
   a.c2d[2 * dst + 1] = a.inv_scale * ((double)y + 0.5);
   const int HW = a.h * a.w;
-  const float* loc = a.frag_loc + ((((size_t)b * HW + p) * a.O + (obj_id - 1)) * a.F + f) * 3;
-  const double* cen = a.centers + ((size_t)(obj_id - 1) * a.F + f) * 3;
-  const double sz = a.sizes[(size_t)(obj_id - 1) * a.F + f];
+  if (a.frag_loc) {
+    const float* loc = a.frag_loc + ((((size_t)b * HW + p) * a.O + (obj_id - 1)) * a.F + f) * 3;
+    const double* cen = a.centers + ((size_t)(obj_id - 1) * a.F + f) * 3;
+    const double sz = a.sizes[(size_t)(obj_id - 1) * a.F + f];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const float l32 = (float)((double)__ldg(loc + k) * sz);      // numpy: f32 array *= f64 array -> computed in f64, cast to f32
-    a.c3d[3 * dst + k] = cen[k] + (double)l32;
+    for (int k = 0; k < 3; ++k) {
+      const float l32 = (float)((double)__ldg(loc + k) * sz);      // numpy: f32 array *= f64 array -> computed in f64, cast to f32
+      a.c3d[3 * dst + k] = cen[k] + (double)l32;
+    }
   }
   a.conf[dst] = __fmul_rn(vobj, vfrag);
   a.conf_obj[dst] = vobj;
   a.conf_frag[dst] = vfrag;
   a.px[dst] = p;
   a.frag[dst] = f;
+}
+
+// Lazy localisation head: rows [0, n) of the segment already carry px / frag; one warp per row computes
+//   loc[k] = b_loc[c] + sum_i feat[p][i] * w_loc[c][i],  c = ((obj_id-1) F + f) 3 + k      (model.py:448-456, 1x1 conv + bias)
+// in fp32 (feat = hi + lo is exact in fp32; lanes own interleaved 4-element groups of the channel axis, partial sums are
+// combined by a butterfly), then coord_3d as in write_row.  Replaces the dense 3 O F-column GEMM whose output is read at
+// <= max_corr rows per (image, object).
+__device__ inline void lazy_loc_rows(const CorrArgs& a, int b, int obj_id, size_t seg_base, int n) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int HW = a.h * a.w;
+  for (int i = warp; i < n; i += CW) {
+    const size_t dst = seg_base + i;
+    const int p = a.px[dst], f = a.frag[dst];
+    const uint16_t* fh = a.feat + ((size_t)b * HW + p) * a.ldf;
+    const uint16_t* fl = fh + a.feat_plane;
+    const size_t c0 = ((size_t)(obj_id - 1) * a.F + f) * 3;
+    const float* w0 = a.w_loc + c0 * a.feat_c;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int k = lane * 4; k < a.feat_c; k += 128) {
+      const uint2 h = __ldg(reinterpret_cast<const uint2*>(fh + k)), l = __ldg(reinterpret_cast<const uint2*>(fl + k));
+      const float x0 = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+      const float x1 = __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
+      const float x2 = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+      const float x3 = __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
+      const float4 wa = __ldg(reinterpret_cast<const float4*>(w0 + k));
+      const float4 wb = __ldg(reinterpret_cast<const float4*>(w0 + a.feat_c + k));
+      const float4 wc = __ldg(reinterpret_cast<const float4*>(w0 + 2 * a.feat_c + k));
+      s0 = fmaf(x0, wa.x, fmaf(x1, wa.y, fmaf(x2, wa.z, fmaf(x3, wa.w, s0))));
+      s1 = fmaf(x0, wb.x, fmaf(x1, wb.y, fmaf(x2, wb.z, fmaf(x3, wb.w, s1))));
+      s2 = fmaf(x0, wc.x, fmaf(x1, wc.y, fmaf(x2, wc.z, fmaf(x3, wc.w, s2))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane < 3) {
+      const float loc = (lane == 0 ? s0 : (lane == 1 ? s1 : s2)) + (a.b_loc ? __ldg(a.b_loc + c0 + lane) : 0.f);
+      const double sz = a.sizes[(size_t)(obj_id - 1) * a.F + f];
+      const float l32 = (float)((double)loc * sz);
+      a.c3d[3 * dst + lane] = a.centers[((size_t)(obj_id - 1) * a.F + f) * 3 + lane] + (double)l32;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(CT, 1) corresp_kernel(CorrArgs a) {
@@ -205,6 +253,7 @@ __global__ void __launch_bounds__(CT, 1) corresp_kernel(CorrArgs a) {
     for_each_candidate(a, b, obj_id, L, [&](int p, int f, unsigned int e, float vo, float vf) {
       if ((int)e < a.cap) write_row(a, b, obj_id, seg_base + e, p, f, vo, vf);
     });
+    if (!a.frag_loc) { __syncthreads(); lazy_loc_rows(a, b, obj_id, seg_base, n); }
     return;
   }
   // ---- phase 2: radix select of the K largest 64-bit keys ----
@@ -292,6 +341,7 @@ __global__ void __launch_bounds__(CT, 1) corresp_kernel(CorrArgs a) {
     const float vf = __ldg(a.frag_conf + (((size_t)b * HW + p) * a.O + (obj_id - 1)) * a.F + f);
     write_row(a, b, obj_id, seg_base + i, p, f, vo, vf);
   }
+  if (!a.frag_loc) { __syncthreads(); lazy_loc_rows(a, b, obj_id, seg_base, n); }
 }
 
 }  // namespace epos
@@ -305,12 +355,17 @@ size_t epos_corresp_workspace_bytes(int B, int J, int h, int w) {
   return (size_t)B * J * ((size_t)h * w + 1) * 16 + 256;
 }
 
-int epos_corresp(const float* obj_conf, const float* frag_conf, const float* frag_loc, int B, int h, int w, int num_objs,
-                 int num_frags, const int32_t* obj_ids, int J, const double* frag_centers, const double* frag_sizes,
-                 double output_scale, float min_obj_conf, float min_frag_rel_conf, int cap, int max_corr, double* coord_2d,
-                 double* coord_3d, float* conf, float* conf_obj, float* conf_frag, int32_t* px, int32_t* frag,
-                 int32_t* counts, int32_t* totals, void* workspace, size_t workspace_bytes, void* stream) {
-  EPOS_CHECK_ARG(obj_conf && frag_conf && frag_loc && obj_ids && frag_centers && frag_sizes);
+static int corresp_launch(const float* obj_conf, const float* frag_conf, const float* frag_loc, const uint16_t* feat, int ldf,
+                          size_t feat_plane, int feat_c, const float* w_loc, const float* b_loc, int B, int h, int w,
+                          int num_objs, int num_frags, const int32_t* obj_ids, int J, const double* frag_centers,
+                          const double* frag_sizes, double output_scale, float min_obj_conf, float min_frag_rel_conf,
+                          int cap, int max_corr, double* coord_2d, double* coord_3d, float* conf, float* conf_obj,
+                          float* conf_frag, int32_t* px, int32_t* frag, int32_t* counts, int32_t* totals, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  EPOS_CHECK_ARG(obj_conf && frag_conf && obj_ids && frag_centers && frag_sizes);
+  EPOS_CHECK_ARG(frag_loc || (feat && w_loc && feat_c > 0 && (feat_c % 4) == 0 && ldf >= feat_c && (ldf % 4) == 0 &&
+                              (feat_plane % 4) == 0 && (reinterpret_cast<uintptr_t>(feat) & 7) == 0 &&
+                              (reinterpret_cast<uintptr_t>(w_loc) & 15) == 0));
   EPOS_CHECK_ARG(coord_2d && coord_3d && conf && conf_obj && conf_frag && px && frag && counts && workspace);
   EPOS_CHECK_ARG(B > 0 && h > 0 && w > 0 && num_objs > 0 && num_frags > 0 && J > 0 && cap > 0 && output_scale > 0);
   EPOS_CHECK_ARG((size_t)h * w < (1u << 23));
@@ -324,6 +379,7 @@ int epos_corresp(const float* obj_conf, const float* frag_conf, const float* fra
   a.min_obj_conf = min_obj_conf; a.min_rel = min_frag_rel_conf; a.cap = cap; a.max_corr = max_corr;
   a.c2d = coord_2d; a.c3d = coord_3d; a.conf = conf; a.conf_obj = conf_obj; a.conf_frag = conf_frag; a.px = px; a.frag = frag;
   a.counts = counts; a.totals = totals;
+  a.feat = feat; a.ldf = ldf; a.feat_plane = (long long)feat_plane; a.w_loc = w_loc; a.b_loc = b_loc; a.feat_c = feat_c;
   a.ws = reinterpret_cast<unsigned int*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
   const size_t smem = 2048 * 4 + (size_t)SORT_MAX * 12;
   static std::atomic<int> attr[EPOS_MAX_DEVICES];
@@ -335,6 +391,32 @@ int epos_corresp(const float* obj_conf, const float* frag_conf, const float* fra
   corresp_kernel<<<B * J, CT, smem, (cudaStream_t)stream>>>(a);
   EPOS_LAUNCH_CHECK();
   return EPOS_OK;
+}
+
+int epos_corresp(const float* obj_conf, const float* frag_conf, const float* frag_loc, int B, int h, int w, int num_objs,
+                 int num_frags, const int32_t* obj_ids, int J, const double* frag_centers, const double* frag_sizes,
+                 double output_scale, float min_obj_conf, float min_frag_rel_conf, int cap, int max_corr, double* coord_2d,
+                 double* coord_3d, float* conf, float* conf_obj, float* conf_frag, int32_t* px, int32_t* frag,
+                 int32_t* counts, int32_t* totals, void* workspace, size_t workspace_bytes, void* stream) {
+  EPOS_CHECK_ARG(frag_loc);
+  return corresp_launch(obj_conf, frag_conf, frag_loc, nullptr, 0, 0, 0, nullptr, nullptr, B, h, w, num_objs, num_frags,
+                        obj_ids, J, frag_centers, frag_sizes, output_scale, min_obj_conf, min_frag_rel_conf, cap, max_corr,
+                        coord_2d, coord_3d, conf, conf_obj, conf_frag, px, frag, counts, totals, workspace, workspace_bytes,
+                        stream);
+}
+
+int epos_corresp_lazy_loc(const float* obj_conf, const float* frag_conf, const uint16_t* feat_split, int ldf,
+                          size_t feat_plane_stride, int feat_channels, const float* w_loc, const float* b_loc, int B, int h,
+                          int w, int num_objs, int num_frags, const int32_t* obj_ids, int J, const double* frag_centers,
+                          const double* frag_sizes, double output_scale, float min_obj_conf, float min_frag_rel_conf,
+                          int cap, int max_corr, double* coord_2d, double* coord_3d, float* conf, float* conf_obj,
+                          float* conf_frag, int32_t* px, int32_t* frag, int32_t* counts, int32_t* totals, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  EPOS_CHECK_ARG(feat_split && w_loc);
+  return corresp_launch(obj_conf, frag_conf, nullptr, feat_split, ldf, feat_plane_stride, feat_channels, w_loc, b_loc, B, h, w,
+                        num_objs, num_frags, obj_ids, J, frag_centers, frag_sizes, output_scale, min_obj_conf,
+                        min_frag_rel_conf, cap, max_corr, coord_2d, coord_3d, conf, conf_obj, conf_frag, px, frag, counts,
+                        totals, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -22,7 +22,7 @@ class Engine:
 
     def __init__(self, weights, num_objs, num_frags, device, stages=STAGES_CNN, model_store=None, K=None,
                  fit_params=None, max_correspondences=4096, seed=0, min_obj_conf=0.1, min_frag_rel_conf=0.5,
-                 model_options=None, pipelined=False, post_fit=None):
+                 model_options=None, pipelined=False, post_fit=None, lazy_loc=True):
         self.dev = torch.device(device)
         self.net = model.EposNet(weights, num_objs, num_frags, self.dev, model_options=model_options)
         self.O, self.F = num_objs, num_frags
@@ -34,6 +34,9 @@ class Engine:
         self.seed = seed
         self._fitter = None
         self.post_fit = post_fit                 # e.g. the NCCL all-gather of pose records (epos_b200/dist.py)
+        # full path: pred_frag_loc is evaluated only at the surviving correspondences (model.EposNet.heads); the CNN-only
+        # stage keeps the materialising mode = the output contract of model.predict
+        self.lazy_loc = bool(lazy_loc) and stages == STAGES_FULL
         self.pipelined = bool(pipelined) and stages == STAGES_FULL
         self._side = torch.cuda.Stream(device=self.dev) if self.pipelined else None
         self._copy = torch.cuda.Stream(device=self.dev) if self.pipelined else None    # H2D of the next batch
@@ -57,7 +60,7 @@ class Engine:
         at construction -- the reference reads K per image, scripts/infer.py:376-377).  Returns a dict of CUDA tensors:
         model.predict's outputs for 'cnn', plus 'poses' [B,O,16] f64 pose records for the full path (pipelined: valid
         after join() / out['ready'])."""
-        out = self.net.predict(images_dev)
+        out = self.net.predict(images_dev, lazy_loc=self.lazy_loc)
         if self._fitter is None:
             return out
         if not self.pipelined:
@@ -72,7 +75,9 @@ class Engine:
             ev.synchronize()
         with torch.cuda.stream(self._side):
             self._side.wait_event(done_cnn)
-            maps = [out[k] for k in (model.PRED_OBJ_CONF, model.PRED_FRAG_CONF, model.PRED_FRAG_LOC)]
+            maps = [out[k] for k in (model.PRED_OBJ_CONF, model.PRED_FRAG_CONF, model.PRED_FRAG_LOC) if k in out]
+            if model.LAZY_FRAG_LOC in out:
+                maps.append(out[model.LAZY_FRAG_LOC][0])           # decoder features read by the lazy localisation head
             for t in maps:
                 t.record_stream(self._side)
             ev_maps = torch.cuda.Event()

@@ -25,6 +25,7 @@ PRED_OBJ_CONF = 'pred_obj_conf'        # common.py:24-27
 PRED_OBJ_LABEL = 'pred_obj_label'
 PRED_FRAG_CONF = 'pred_frag_conf'
 PRED_FRAG_LOC = 'pred_frag_loc'
+LAZY_FRAG_LOC = 'lazy_frag_loc'        # engine path: (decoder features, f32 logit weights, bias) instead of pred_frag_loc
 
 EPS_BACKBONE = 1e-3                    # feature.py:304
 EPS_HEAD = 1e-5                        # model.py:197,310
@@ -182,7 +183,8 @@ class EposNet:
             p['decoder_conv%d_pw' % i] = self._pw(w, 'decoder/decoder_conv%d_pointwise' % i, EPS_HEAD)
         for name in (PRED_OBJ_CONF, PRED_FRAG_CONF, PRED_FRAG_LOC):
             k = np.asarray(w['logits/%s/weights' % name], np.float64)[0, 0].T
-            p['logits/' + name] = Gemm(k, w['logits/%s/biases' % name], self.dev, self.keep_f32)
+            # the localisation head keeps its f32 weights: the lazy head (engine path) evaluates it row by row in fp32
+            p['logits/' + name] = Gemm(k, w['logits/%s/biases' % name], self.dev, self.keep_f32 or name == PRED_FRAG_LOC)
 
     # -- op wrappers ----------------------------------------------------------------------------------
     def _s(self):
@@ -435,8 +437,12 @@ class EposNet:
         self.end_points['decoder'] = (y1, dh_, dw_, 256)
         return y1s, B, dh_, dw_
 
-    def heads(self, feat_split, B, h, w):
-        """Logit heads + softmax/argmax in materialising mode (model.py:448-456, 676-685)."""
+    def heads(self, feat_split, B, h, w, lazy_loc=False):
+        """Logit heads + softmax/argmax (model.py:448-456, 676-685).  Materialising mode (the drop-in contract of
+        model.predict) writes all four maps.  lazy_loc=True (engine path) skips the pred_frag_loc GEMM -- 3 O F columns,
+        2.4 GB per image at O = 30 / F = 256, read back at <= max_correspondences rows per object -- and returns the
+        decoder features and the f32 logit weights instead; corresp.CorrespExtractor evaluates the head at the
+        surviving rows only."""
         M = B * h * w
         O, F = self.O, self.F
         obj, _ = self.gemm(feat_split, self.p['logits/' + PRED_OBJ_CONF], M, relu=False, pad_f32=False)
@@ -444,17 +450,23 @@ class EposNet:
         # other F (e.g. config 5's 256) use the row-softmax kernel
         fused = F == 64 and self.impl == 'tcgen05'
         fc, _ = self.gemm(feat_split, self.p['logits/' + PRED_FRAG_CONF], M, relu=2 if fused else False, pad_f32=False)
-        fl, _ = self.gemm(feat_split, self.p['logits/' + PRED_FRAG_LOC], M, relu=False, pad_f32=False)
         labels = torch.empty((M,), dtype=torch.int64, device=self.dev)
         _lib.check(self.lib.epos_softmax_rows(obj.data_ptr(), labels.data_ptr(), M, O + 1, self._s()), 'epos_softmax_rows')
         if not fused:
             _lib.check(self.lib.epos_softmax_rows(fc.data_ptr(), None, M * O, F, self._s()), 'epos_softmax_rows')
-        return {PRED_OBJ_CONF: obj.view(B, h, w, O + 1), PRED_OBJ_LABEL: labels.view(B, h, w),
-                PRED_FRAG_CONF: fc.view(B, h, w, O, F), PRED_FRAG_LOC: fl.view(B, h, w, O, F, 3)}
+        out = {PRED_OBJ_CONF: obj.view(B, h, w, O + 1), PRED_OBJ_LABEL: labels.view(B, h, w),
+               PRED_FRAG_CONF: fc.view(B, h, w, O, F)}
+        g = self.p['logits/' + PRED_FRAG_LOC]
+        if lazy_loc:
+            out[LAZY_FRAG_LOC] = (feat_split, g.w_f32, g.bias)
+        else:
+            fl, _ = self.gemm(feat_split, g, M, relu=False, pad_f32=False)
+            out[PRED_FRAG_LOC] = fl.view(B, h, w, O, F, 3)
+        return out
 
-    def predict(self, images):
+    def predict(self, images, lazy_loc=False):
         feat, B, h, w = self.forward_features(images)
-        return self.heads(feat, B, h, w)
+        return self.heads(feat, B, h, w, lazy_loc)
 
 
 _NETS = {}

@@ -117,10 +117,10 @@ class BatchFitter:
         """Stream key of problem (image b, slot j) in batch n: seed * 2^32 + n * P + b * J + j."""
         return self._base + (self.seed << 32) + self.batch_index * (B * self.J)
 
-    def fit_maps(self, obj_conf, frag_conf, frag_loc, after_extract=None, K=None):
+    def fit_maps(self, obj_conf, frag_conf, frag_loc, after_extract=None, K=None, lazy_loc=None):
         B = obj_conf.shape[0]
         self._prepare(B, K)
-        bc = self.extract(obj_conf, frag_conf, frag_loc)
+        bc = self.extract(obj_conf, frag_conf, frag_loc, lazy_loc=lazy_loc)
         self.corr = bc
         if after_extract is not None:
             after_extract()                       # the head maps are no longer needed from here on
@@ -133,7 +133,8 @@ class BatchFitter:
     def fit(self, predictions, after_extract=None, K=None):
         from . import model
         return self.fit_maps(predictions[model.PRED_OBJ_CONF], predictions[model.PRED_FRAG_CONF],
-                             predictions[model.PRED_FRAG_LOC], after_extract, K)
+                             predictions.get(model.PRED_FRAG_LOC), after_extract, K,
+                             lazy_loc=predictions.get(model.LAZY_FRAG_LOC))
 
 
 def find6DPoses(x1y1, x2y2z2, K, threshold=4.0, max_model_number=-1, conf=0.5, proposal_engine_conf=1.0,

@@ -162,6 +162,26 @@ int epos_corresp(const float* obj_conf, const float* frag_conf, const float* fra
                  void* workspace, size_t workspace_bytes, void* stream);
 size_t epos_corresp_workspace_bytes(int B, int J, int h, int w);
 
+/* Same contract with a LAZY localisation head: pred_frag_loc [B,h,w,O,F,3] (model.py:448-456; 2.4 GB per image at
+ * O = 30, F = 256) is never materialised.  The three local coordinates of each surviving (pixel, object, fragment) row
+ * (at most max_corr per segment) are computed in place from the decoder features -- feat_split [2][B*h*w][ldf] bf16
+ * (hi, lo planes `feat_plane_stride` elements apart, feat_channels = 256 used) -- and the 1x1 logit weights
+ * w_loc [O*F*3][feat_channels] f32 (row c = (o*F+f)*3+k, the channel order of model.py:133-147) + bias b_loc [O*F*3]
+ * (may be NULL), in fp32.  px / frag / coord_2d / conf* are bit-identical to epos_corresp on the materialised maps;
+ * coord_3d agrees to fp32 rounding of the 256-term dot product (the dense head computes the same sum on the tensor
+ * cores in a different order). */
+int epos_corresp_lazy_loc(const float* obj_conf, const float* frag_conf,
+                          const uint16_t* feat_split, int ldf, size_t feat_plane_stride, int feat_channels,
+                          const float* w_loc, const float* b_loc,
+                          int B, int h, int w, int num_objs, int num_frags,
+                          const int32_t* obj_ids, int J,
+                          const double* frag_centers, const double* frag_sizes,
+                          double output_scale, float min_obj_conf, float min_frag_rel_conf,
+                          int cap, int max_corr,
+                          double* coord_2d, double* coord_3d, float* conf, float* conf_obj, float* conf_frag,
+                          int32_t* px, int32_t* frag, int32_t* counts, int32_t* totals,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- pose fitting: replaces pyprogressivex.find6DPoses
  * (external/progressive-x/src/pyprogressivex/src/bindings.cpp:9-118, progressivex_python.cpp:36-336),
  * single-instance branch (GC-RANSAC + final LM), batched over P independent problems. --------------- */

@@ -20,11 +20,11 @@ from epos_b200 import model
 for it in range(n):
     e = [ev() for _ in range(4)]
     e[0].record()
-    out = eng.net.predict(imgs[it % 3])
+    out = eng.net.predict(imgs[it % 3], lazy_loc=eng.lazy_loc)
     e[1].record()
     bf = eng._fitter
     bf._prepare(B)
-    bc = bf.extract(out[model.PRED_OBJ_CONF], out[model.PRED_FRAG_CONF], out[model.PRED_FRAG_LOC])
+    bc = bf.extract(out[model.PRED_OBJ_CONF], out[model.PRED_FRAG_CONF], out.get(model.PRED_FRAG_LOC), lazy_loc=out.get(model.LAZY_FRAG_LOC))
     e[2].record()
     seeds = bf.seeds_for(B); bf.batch_index += 1
     poses, lab = bf._fitter.fit(bc.coord_2d.view(-1, 2), bc.coord_3d.view(-1, 3), bc.offsets, bc.counts, bf._Kdev, seeds, bf._poses, bf._labeling)

@@ -86,6 +86,47 @@ def test_corresp_planted_maps_with_ties_and_empty_objects():
     assert _check_corresp(oc, fc, fl, store, O, F, 4096) > 0
 
 
+@pytest.mark.parametrize('O,F,h,w,max_corr', [(3, 64, 60, 80, 0), (3, 64, 60, 80, 500), (2, 256, 30, 40, 1024)])
+def test_corresp_lazy_localisation_head(O, F, h, w, max_corr):
+    """epos_corresp_lazy_loc never sees pred_frag_loc: it evaluates the 1x1 localisation head (model.py:448-456) at the
+    surviving rows from the decoder features.  Against epos_corresp on the MATERIALISED head (features x weights in f64):
+    row sets, order, 2D coordinates and confidences bit-identical; 3D coordinates to fp32 rounding of the dot product."""
+    from epos_b200 import corresp, synthetic
+    rng = np.random.default_rng(7 + F)
+    B, C = 2, 256
+    store = synthetic.model_store(O, F)
+    oc, fc, _ = _random_maps(rng, B, h, w, O, F)
+    feat = torch.from_numpy(rng.standard_normal((B * h * w, C)).astype(np.float32)).to(DEV)
+    hi = feat.to(torch.bfloat16)
+    lo = (feat - hi.float()).to(torch.bfloat16)
+    fs = torch.stack([hi, lo]).contiguous()                              # split-bf16 [2, M, C]
+    w_loc = torch.from_numpy((rng.standard_normal((O * F * 3, C)) * 0.05).astype(np.float32)).to(DEV)
+    b_loc = torch.from_numpy(rng.standard_normal(O * F * 3).astype(np.float32)).to(DEV)
+    a64 = hi.double() + lo.double()
+    fl = (a64 @ w_loc.double().T + b_loc.double()).float().view(B, h, w, O, F, 3).contiguous()
+    cap = h * w * F if not max_corr else max_corr
+    kw = dict(cap=cap, max_correspondences=max_corr, min_obj_conf=0.2)
+    ocd, fcd = torch.from_numpy(oc).to(DEV), torch.from_numpy(fc).to(DEV)
+    ref = corresp.CorrespExtractor(DEV, O, F, store, **kw)(ocd, fcd, fl)
+    got = corresp.CorrespExtractor(DEV, O, F, store, **kw)(ocd, fcd, None, lazy_loc=(fs, w_loc, b_loc))
+    torch.cuda.synchronize()
+    counts = ref.counts.cpu().numpy()
+    assert np.array_equal(counts, got.counts.cpu().numpy()) and np.array_equal(ref.totals.cpu().numpy(), got.totals.cpu().numpy())
+    assert counts.sum() > 1000
+    for s_, n in enumerate(counts):
+        for k in ('px', 'frag', 'coord_2d', 'conf', 'conf_obj', 'conf_frag'):
+            assert torch.equal(getattr(ref, k)[s_, :n], getattr(got, k)[s_, :n]), (s_, k)
+        a, b = ref.coord_3d[s_, :n], got.coord_3d[s_, :n]
+        if n:
+            assert float((a - b).abs().max()) < 1e-4 * max(1.0, float(a.abs().max()))     # mm; fp32 dot of 256 terms
+    # without a bias
+    got2 = corresp.CorrespExtractor(DEV, O, F, store, **kw)(ocd, fcd, None, lazy_loc=(fs, w_loc, None))
+    fl2 = (a64 @ w_loc.double().T).float().view(B, h, w, O, F, 3).contiguous()
+    ref2 = corresp.CorrespExtractor(DEV, O, F, store, **kw)(ocd, fcd, fl2)
+    n0 = int(counts[0])
+    assert float((ref2.coord_3d[0, :n0] - got2.coord_3d[0, :n0]).abs().max()) < 1e-4 * float(ref2.coord_3d[0, :n0].abs().max())
+
+
 def test_establish_many_to_many_dropin():
     from epos_b200 import corresp, synthetic
     from oracle import corresp as ocorr
@@ -255,7 +296,8 @@ def test_engine_full_path_postprocessing_matches_oracle_on_its_own_maps(F):
     w = W.random_init(O, F, seed=2, bn='random', logits_std=0.5)
     store = synthetic.model_store(O, F)
     K = synthetic.default_K()
-    eng = engine.Engine(w, O, F, DEV, stages=engine.STAGES_FULL, model_store=store, K=K, max_correspondences=1024, seed=4)
+    eng = engine.Engine(w, O, F, DEV, stages=engine.STAGES_FULL, model_store=store, K=K, max_correspondences=1024, seed=4,
+                        lazy_loc=False)
     img = torch.from_numpy(W.synthetic_images(B, seed=6, height=160, width=224)).to(DEV)
     out = eng.run_device(img)
     torch.cuda.synchronize()
@@ -276,6 +318,48 @@ def test_engine_full_path_postprocessing_matches_oracle_on_its_own_maps(F):
     # second batch uses the next stream keys
     out2 = eng.run_device(img)
     assert eng._fitter.batch_index == 2
+
+
+def test_lazy_engine_matches_materialising_engine_and_oracle_fit():
+    """The engine's default path never materialises pred_frag_loc.  Its correspondences must be those of the
+    materialising engine (rows / order / confidences identical, 3D coordinates to fp32 rounding), and its pose records
+    must equal the oracle's fit of the engine's OWN correspondences (identical inliers / iterations / graph cuts)."""
+    from epos_b200 import engine, model, synthetic, weights as W
+    from oracle import posefit as opf
+    O, F, B = 3, 64, 2
+    w = W.random_init(O, F, seed=2, bn='random', logits_std=0.5)
+    store = synthetic.model_store(O, F)
+    K = synthetic.default_K()
+    img = torch.from_numpy(W.synthetic_images(B, seed=6, height=160, width=224)).to(DEV)
+    res = {}
+    for lazy in (False, True):
+        eng = engine.Engine(w, O, F, DEV, stages=engine.STAGES_FULL, model_store=store, K=K, max_correspondences=1024, seed=4,
+                            lazy_loc=lazy)
+        out = eng.run_device(img)
+        torch.cuda.synchronize()
+        assert (model.PRED_FRAG_LOC in out) == (not lazy) and (model.LAZY_FRAG_LOC in out) == lazy
+        bc = eng._fitter.corr
+        res[lazy] = (out['poses'].cpu().numpy(), bc.counts.cpu().numpy(), bc.px.cpu().numpy(), bc.frag.cpu().numpy(),
+                     bc.conf.cpu().numpy(), bc.coord_2d.cpu().numpy(), bc.coord_3d.cpu().numpy())
+    a, b = res[False], res[True]
+    assert np.array_equal(a[1], b[1]) and a[1].sum() > 100
+    nprob = 0
+    for s_, n in enumerate(a[1]):
+        for k in (2, 3, 4, 5):
+            assert np.array_equal(a[k][s_, :n], b[k][s_, :n])
+        if n:
+            assert np.abs(a[6][s_, :n] - b[6][s_, :n]).max() < 1e-4 * max(1.0, np.abs(a[6][s_, :n]).max())
+        if n >= 6:
+            bi, j = divmod(s_, O)
+            op, ol, _, st = opf.find6DPoses(b[5][s_, :n], b[6][s_, :n], K, max_model_number=1, seed=(4 << 32) + bi * O + j,
+                                            return_stats=True, threshold=4.0, min_triangle_area=0.0)
+            g = b[0][bi, j]
+            assert int(g[13]) == st['iterations'] and int(g[15]) == st['graph_cuts'] and int(g[14]) == st['found']
+            if st['found']:
+                assert int(g[12]) == int(ol.sum())
+                assert np.abs(g[:12].reshape(3, 4) - op).max() < 1e-4 * max(1.0, np.abs(op).max())
+            nprob += 1
+    assert nprob >= 2
 
 
 def test_pipelined_engine_equals_serial_engine():
