@@ -698,9 +698,15 @@ static inline double sq_residual(const double* row, const double* m) {
   return std::fma(du, du, dv * dv);
 }
 
-struct Score { long long value = 0, inliers = 0; };
+// Score::value is a double as in the reference (scoring_function.h:44-66): the pixel count in the single-instance
+// path, pixel count minus (shared support)^2 when a compound model is present (Progressive-X).
+struct Score { double value = 0; long long inliers = 0; };
 
 struct Problem {
+  // Progressive-X proposal engine only: preference vector of the compound model (NULL = plain EPOS score) and the
+  // random-stream pair of this proposal (streams stream_base / stream_base + 1: main sampler / LO sampler)
+  const double* cpref = nullptr;
+  u64 stream_base = 0;
   int N = 0;
   std::vector<double> pts;          // N x 7
   std::vector<int> pixel_id;        // dense rank of ((int)u, (int)v)
@@ -725,7 +731,29 @@ static Score get_score(const Problem& pb, const double* model, long long best_in
     }
   }
   if (s.inliers + 1 < best_inl) { if (inliers) inliers->clear(); return Score(); }
-  s.value = pixels;
+  s.value = (double)pixels;
+  if (pb.cpref) {
+    // EPOSScoringFunctionWithCompoundModel::getScore (scoring_function_with_compound_model.h:216-263): the support
+    // shared with the compound model, sum_i min(compound_pref_i, pref_i) with pref_i = max(0, 1 - r_i^2 / T) for inliers,
+    // squared (exponent_of_shared_score is an int set to 2, progressive_x.h:196,663), is subtracted from the pixel count.
+    // Summation order (the reference adds sequentially; the CUDA warp cannot): point i goes to partial sum i mod 32 in
+    // ascending order, the 32 partial sums are combined by a butterfly (offsets 16, 8, 4, 2, 1).
+    double part[32] = {0};
+    for (int i = 0; i < pb.N; ++i) {
+      double r2 = sq_residual(&pb.pts[(size_t)7 * i], model);
+      if (r2 < pb.sq_trunc) {
+        double pref = 1.0 - r2 / pb.sq_trunc;
+        if (pref < 0.0) pref = 0.0;
+        part[i & 31] += std::min(pb.cpref[i], pref);
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      double t[32];
+      for (int l = 0; l < 32; ++l) t[l] = part[l] + part[l ^ o];
+      std::memcpy(part, t, sizeof(t));
+    }
+    s.value -= part[0] * part[0];
+  }
   return s;
 }
 
@@ -968,7 +996,7 @@ static int generate_models(const Problem& pb, const Params& P, u64 seed, int pas
   int fails = -1, nm = 0;
   while (++fails < P.max_unsuccessful) {
     int s[3];
-    if (!unique_set(seed, 0, (u64)pass, (u64)fails, pb.N, 3, s)) continue;
+    if (!unique_set(seed, pb.stream_base, (u64)pass, (u64)fails, pb.N, 3, s)) continue;
     if (!valid_sample(pb, s, P.min_triangle_area)) continue;
     nm = p3p(pb.pts.data(), s, models);
     if (nm > 0) { if (sample_out) { sample_out[0] = s[0]; sample_out[1] = s[1]; sample_out[2] = s[2]; } break; }
@@ -999,7 +1027,7 @@ static void local_optimization(const Problem& pb, const Params& P, u64 seed, Sta
       if (trial < 20) row[5 + 3 * trial] = 0;
       if (sample_size < ni) {
         int sel[21], idx[21];
-        unique_set(seed, 1, (u64)st.graph_cuts, (u64)trial, ni, sample_size, sel);
+        unique_set(seed, pb.stream_base + 1, (u64)st.graph_cuts, (u64)trial, ni, sample_size, sel);
         for (int k = 0; k < sample_size; ++k) idx[k] = inliers[sel[k]];
         if (!fit_nonminimal(pb.pts.data(), idx, sample_size, model)) continue;
       } else if (3 < ni) {
@@ -1019,6 +1047,7 @@ static void local_optimization(const Problem& pb, const Params& P, u64 seed, Sta
       }
     }
     row[0] = st.graph_cuts; row[1] = ni; row[2] = updated ? 1 : 0; row[3] = (int)max_score.value; row[4] = (int)max_score.inliers;
+    if (g_trace.size() > 72 * 4096) g_trace.clear();
     g_trace.insert(g_trace.end(), row.begin(), row.end());
     if (!updated) break;
   }
@@ -1178,6 +1207,456 @@ static int find6dposes(int N, const double* x2d, const double* x3d, const double
   return 1;
 }
 
+
+// ===================================================================================================
+// Progressive-X multi-instance fitting (max_model_number != 1):
+//   /root/reference/external/progressive-x/src/pyprogressivex/src/progressivex_python.cpp:136-221 (dispatch, settings)
+//   .../include/progressive_x.h:397-649 (run), :265-391 (spedUpFitting), :651-673 (getPredictedUnseenInliers),
+//       :675-721 (initialize), :723-749 (isPutativeModelValid), :755-794 (updateCompoundModel)
+//   .../include/scoring_function_with_compound_model.h:127-266 (restated inside get_score above)
+//   .../include/PEARL.h:57-134 (energy functors), :391-536 (run / labeling), :313-389 (parameterEstimation),
+//       :271-311 (rejectInstances); progx_model.h:66-84 (preference vector)
+//   alpha-expansion with label costs: .../graph-cut-ransac/src/pygcransac/include/GCoptimization.cpp:1003-1088
+//       (expansion, standard cycles), :1239-1303 (alpha_expansion), :316-404 (active sites, data / smooth terms),
+//       :1131-1196 (label costs), :452-470 (applyNewLabeling), :259-279,950-986 (energies); energy.h:204-253,324-328;
+//       graph.h:388-397 (add_tweights).  Validated against the reference's own GCoptimization sources compiled into
+//       oracle/_ref (tests/test_oracle_progx.py).
+// ===================================================================================================
+struct MultiParams {
+  int max_model_number;            // > 1, or -1 = "all instances" (DETECTION)
+  int max_model_number_for_pearl;  // maximum_model_number_to_optimize (EPOS: 5)
+  double confidence;               // conf (required_progx_confidence, 0.5)
+  double max_tanimoto;             // 0.9
+  int min_point_number;            // 6: minimum inliers of an instance AND the label cost of PEARL
+};
+constexpr int MAX_INSTANCES = 32;  // cap of the "all instances" mode (the reference's loop is unbounded there)
+
+// The binary energy of one expansion move (energy.h / graph.h), solved with Dinic; var(i) = 1 iff node i belongs to the
+// SINK segment = can still reach the sink in the residual graph (what_segment with default SOURCE).
+struct MoveEnergy {
+  std::vector<double> tr;
+  double flow_const = 0.0;
+  struct E { int x, y; double cap, rev; };
+  std::vector<E> edges;
+  int add_variable() { tr.push_back(0.0); return (int)tr.size() - 1; }
+  void add_tweights(int i, double cap_source, double cap_sink) {          // graph.h:388-397
+    double delta = tr[i];
+    if (delta > 0) cap_source += delta; else cap_sink -= delta;
+    flow_const += (cap_source < cap_sink) ? cap_source : cap_sink;
+    tr[i] = cap_source - cap_sink;
+  }
+  void add_term1(int x, double A, double B) { add_tweights(x, B, A); }    // energy.h:204-209
+  void add_term2(int x, int y, double A, double B, double C, double D) {  // energy.h:211-253
+    add_tweights(x, D, A);
+    B -= A; C -= D;
+    if (B < 0) { add_tweights(x, 0, B); add_tweights(y, 0, -B); edges.push_back({x, y, 0.0, B + C}); }
+    else if (C < 0) { add_tweights(x, 0, -C); add_tweights(y, 0, C); edges.push_back({x, y, B + C, 0.0}); }
+    else edges.push_back({x, y, B, C});
+  }
+  double minimize(std::vector<char>& var) {
+    const int n = (int)tr.size();
+    Dinic dn(n + 2);
+    const int S = n, T = n + 1;
+    for (int i = 0; i < n; ++i) {
+      if (tr[i] > 0) dn.add(S, i, tr[i], 0.0);
+      else if (tr[i] < 0) dn.add(i, T, -tr[i], 0.0);
+    }
+    for (const E& e : edges) dn.add(e.x, e.y, e.cap, e.rev);
+    // flow value = capacity that left the source
+    double before = 0.0, after = 0.0;
+    for (int a : dn.adj[S]) before += dn.arcs[a].cap;
+    dn.run(S, T);
+    for (int a : dn.adj[S]) after += dn.arcs[a].cap;
+    var.assign(n, 0);
+    std::vector<char> in_t(n + 2, 0);
+    std::queue<int> q;
+    in_t[T] = 1; q.push(T);
+    while (!q.empty()) {
+      int v = q.front(); q.pop();
+      for (int a : dn.adj[v]) {
+        int u = dn.arcs[a].to;
+        if (!in_t[u] && dn.arcs[a ^ 1].cap > CUT_EPS) { in_t[u] = 1; q.push(u); }
+      }
+    }
+    for (int i = 0; i < n; ++i) var[i] = in_t[i];
+    return flow_const + (before - after);
+  }
+};
+
+struct AlphaExpansion {
+  int n = 0, L = 0;
+  std::vector<int> label;
+  std::vector<std::vector<std::pair<int, double>>> nb;   // neighbour arrays in the order finalizeNeighbors() produces
+  std::vector<double> D;                                  // data costs [n][L]
+  double lambda = 0.0, label_cost = 0.0;
+  std::vector<int> counts;
+  std::vector<double> lab_cost;
+  int moves = 0;
+
+  double sc(int a, int b) const { return a != b ? lambda : 0.0; }          // PEARL.h:57-79
+  void update_info() {
+    counts.assign(L, 0);
+    lab_cost.resize(n);
+    for (int i = 0; i < n; ++i) { ++counts[label[i]]; lab_cost[i] = D[(size_t)i * L + label[i]]; }
+  }
+  double compute_energy() const {                                           // GCoptimization.cpp:950-986,259-279
+    double data = 0.0, smooth = 0.0, lab = 0.0;
+    for (int i = 0; i < n; ++i) data += lab_cost[i];
+    for (int i = 0; i < n; ++i)
+      for (const auto& e : nb[i])
+        if (e.first < i) smooth += e.second * sc(label[i], label[e.first]);
+    for (int l = L - 1; l >= 0; --l)                                        // m_labelcostsAll is prepended: last label first
+      if (counts[l]) lab += label_cost;
+    return data + smooth + lab;
+  }
+  bool expansion_move(int alpha) {                                          // GCoptimization.cpp:1239-1303
+    std::vector<int> active;
+    for (int i = 0; i < n; ++i) if (label[i] != alpha) active.push_back(i);
+    const int size = (int)active.size();
+    if (size == 0) return false;
+    ++moves;
+    std::vector<int> lookup(n, -1);
+    for (int i = 0; i < size; ++i) lookup[active[i]] = i;
+    MoveEnergy e;
+    e.tr.assign(size, 0.0);
+    double before = 0.0;
+    for (int i = 0; i < size; ++i) {                                        // :328-334
+      const int site = active[i];
+      before += lab_cost[site];
+      e.add_term1(i, D[(size_t)site * L + alpha], lab_cost[site]);
+    }
+    for (int i = size - 1; i >= 0; --i) {                                   // :338-404
+      const int site = active[i];
+      for (const auto& en : nb[site]) {
+        const int ns = en.first; const double w = en.second;
+        if (lookup[ns] == -1) {
+          const double e0 = sc(alpha, label[ns]), e1 = sc(label[site], label[ns]);
+          before += e1 * w;
+          e.add_term1(i, e0 * w, e1 * w);
+        } else if (ns < site) {
+          const double e00 = sc(alpha, alpha), e01 = sc(alpha, label[ns]), e10 = sc(label[site], alpha),
+                       e11 = sc(label[site], label[ns]);
+          before += e11 * w;
+          e.add_term2(i, lookup[ns], e00 * w, e01 * w, e10 * w, e11 * w);
+        }
+      }
+    }
+    double alpha_correction = 0.0;                                          // :1131-1196
+    if (label_cost > 0.0) {
+      std::vector<int> aux(L, -1);
+      aux[alpha] = -2;
+      if (!counts[alpha]) alpha_correction += label_cost;
+      for (int i = 0; i < size; ++i) {
+        const int l = label[active[i]];
+        if (aux[l] == -2) continue;
+        if (aux[l] == -1) {
+          aux[l] = e.add_variable();
+          e.add_term1(aux[l], 0.0, label_cost);
+          before += label_cost;
+        }
+        e.add_term2(i, aux[l], 0.0, 0.0, label_cost, 0.0);
+      }
+    }
+    std::vector<char> var;
+    const double after = e.minimize(var) + alpha_correction;
+    if (after < before) {                                                   // :452-470
+      for (int i = 0; i < size; ++i)
+        if (var[i] == 0) {
+          const int site = active[i];
+          --counts[label[site]]; ++counts[alpha];
+          label[site] = alpha;
+          lab_cost[site] = D[(size_t)site * L + alpha];
+        }
+    }
+    return after < before;
+  }
+  double expansion(int max_iterations) {                                    // :1003-1088, standard cycles
+    update_info();
+    double new_energy = compute_energy(), old_energy;
+    for (int cycle = 1; cycle <= max_iterations; ++cycle) {
+      old_energy = new_energy;
+      for (int a = 0; a < L; ++a) expansion_move(a);
+      new_energy = compute_energy();
+      if (new_energy == old_energy) break;
+    }
+    return new_energy;
+  }
+};
+
+// Neighbour arrays as GCoptimizationGeneralGraph builds them from PEARL.h:517-520: setNeighbors(i, j) for every
+// listing j of i (i ascending) PREPENDS an entry to both sites' lists (GCoptimization.cpp:1683-1708); a mutual pair is
+// therefore entered twice and weighs twice.
+static void gco_neighbors(const std::vector<std::vector<int>>& nbr, std::vector<std::vector<std::pair<int, double>>>& nb) {
+  const int n = (int)nbr.size();
+  nb.assign(n, {});
+  for (int i = 0; i < n; ++i)
+    for (int j : nbr[i])
+      if (j != i && j >= 0) { nb[i].insert(nb[i].begin(), {j, 1.0}); nb[j].insert(nb[j].begin(), {i, 1.0}); }
+}
+
+struct Instance {
+  double m[12];
+  std::vector<double> pref;        // preference vector as of the moment the instance was accepted (progx_model.h:66-84);
+                                   // the reference does NOT refresh it when PEARL refits the instance
+};
+
+struct Pearl {
+  std::vector<int> labels;         // alpha_expansion_engine->whatLabel
+  bool have_engine = false;
+  std::vector<int> outliers;
+  std::vector<std::vector<int>> per_instance;
+  int iterations = 0, moves = 0;
+
+  void run(const Problem& pb, const std::vector<std::vector<std::pair<int, double>>>& nb, std::vector<Instance>& models,
+           double lambda, int min_inliers) {
+    const int N = pb.N;
+    const double T2 = 9.0 / 4.0 * pb.thr_n * pb.thr_n, oml = 1.0 - lambda;   // PEARL.h:49 (not (1.5 thr)^2)
+    int iteration = 0;
+    double energy = 0.0, previous_energy = -1.0;
+    bool rejected = false, converged = false;
+    while (!converged && iteration++ < 50) {
+      const bool init_prev = iteration > 1 && !rejected;
+      if (!models.empty()) {                                               // labeling(), PEARL.h:461-536
+        AlphaExpansion ax;
+        ax.n = N; ax.L = (int)models.size() + 1; ax.lambda = lambda; ax.label_cost = (double)min_inliers;
+        ax.nb = nb;
+        ax.D.resize((size_t)N * ax.L);
+        for (int i = 0; i < N; ++i) {
+          for (int l = 0; l + 1 < ax.L; ++l) {                              // dataEnergyFunctor, PEARL.h:81-134
+            const double r2 = sq_residual(&pb.pts[(size_t)7 * i], models[l].m);
+            ax.D[(size_t)i * ax.L + l] = r2 > T2 ? 2.0 * oml : oml * r2 / T2;
+          }
+          ax.D[(size_t)i * ax.L + ax.L - 1] = oml;
+        }
+        if (init_prev && have_engine) ax.label = labels; else ax.label.assign(N, 0);
+        energy = ax.expansion(1000);
+        labels = ax.label;
+        have_engine = true;
+        moves += ax.moves;
+      }
+      bool changed = false;
+      rejected = false;
+      if (have_engine) {                                                   // parameterEstimation, PEARL.h:313-389
+        const int M = (int)models.size();
+        per_instance.assign(M, {});
+        outliers.clear();
+        for (int i = 0; i < N; ++i) {
+          if (labels[i] < M) per_instance[labels[i]].push_back(i); else outliers.push_back(i);
+        }
+        for (int k = 0; k < M; ++k) {
+          const std::vector<int>& inl = per_instance[k];
+          if ((int)inl.size() < 3) continue;
+          double before = 0.0, after = 0.0;
+          for (int i : inl) before += std::sqrt(sq_residual(&pb.pts[(size_t)7 * i], models[k].m));
+          double m2[12];
+          if (!fit_nonminimal(pb.pts.data(), inl.data(), (int)inl.size(), m2)) continue;
+          for (int i : inl) after += std::sqrt(sq_residual(&pb.pts[(size_t)7 * i], m2));
+          if (after < before) { std::memcpy(models[k].m, m2, sizeof(m2)); changed = true; }
+        }
+      }
+      for (int k = (int)models.size() - 1; k >= 0; --k)                    // rejectInstances, PEARL.h:271-311
+        if ((int)per_instance[k].size() < min_inliers) {
+          outliers.insert(outliers.end(), per_instance[k].begin(), per_instance[k].end());
+          per_instance.erase(per_instance.begin() + k);
+          models.erase(models.begin() + k);
+          rejected = true;
+        }
+      if (!rejected && !changed && std::fabs(energy - previous_energy) < 1e-5 && iteration > 1) converged = true;
+      previous_energy = energy;
+    }
+    iterations += iteration;
+  }
+};
+
+struct MultiStats { int proposals = 0, accepted = 0, ransac_iterations = 0, pearl_iterations = 0, moves = 0, sped_up = 0; };
+
+static void preference_vector(const Problem& pb, const double* model, double T2, std::vector<double>& pref) {
+  pref.resize(pb.N);
+  for (int i = 0; i < pb.N; ++i) {
+    const double v = 1.0 - sq_residual(&pb.pts[(size_t)7 * i], model) / T2;
+    pref[i] = v > 0.0 ? v : 0.0;                                           // MAX(0, v): a NaN residual gives 0
+  }
+}
+
+// 7-column neighbourhood of spedUpFitting (progressive_x.h:288-289: FlannNeighborhoodGraph on the 7-column data with a
+// hard-coded radius of 20): deterministic stand-in = the max_nbr nearest rows within the radius, f32 L2 over
+// (u_n, v_n, x, y, z, u, v), ties by index.
+static void build_neighbors7(Problem& pb, double radius, int max_nbr) {
+  const int N = pb.N;
+  std::vector<float> q((size_t)7 * N);
+  for (size_t k = 0; k < q.size(); ++k) q[k] = (float)pb.pts[k];
+  const float r2 = (float)radius * (float)radius;
+  pb.nbr.assign(N, std::vector<int>());
+  std::vector<std::pair<float, int>> cand;
+  // (u, v) are columns 5, 6: a uniform grid on them bounds the search exactly as in build_neighbors
+  if (N == 0) return;
+  float mnu = q[5], mxu = q[5], mnv = q[6], mxv = q[6];
+  bool finite = true;
+  for (int i = 0; i < N; ++i) {
+    mnu = std::min(mnu, q[7 * i + 5]); mxu = std::max(mxu, q[7 * i + 5]);
+    mnv = std::min(mnv, q[7 * i + 6]); mxv = std::max(mxv, q[7 * i + 6]);
+    finite = finite && std::isfinite(q[7 * i + 5]) && std::isfinite(q[7 * i + 6]);
+  }
+  float cs = (float)radius * 1.0001f + 1e-6f;
+  long long gw = 1, gh = 1;
+  if (finite)
+    for (;;) {
+      gw = (long long)std::floor((mxu - mnu) / cs) + 1; gh = (long long)std::floor((mxv - mnv) / cs) + 1;
+      if (gw * gh <= (1 << 22)) break;
+      cs *= 2.0f;
+    }
+  auto cell = [&](int i, long long* cx, long long* cy) {
+    if (!finite) { *cx = *cy = 0; return; }
+    long long x = (long long)std::floor((q[7 * i + 5] - mnu) / cs), y = (long long)std::floor((q[7 * i + 6] - mnv) / cs);
+    *cx = std::min(std::max(x, 0LL), gw - 1); *cy = std::min(std::max(y, 0LL), gh - 1);
+  };
+  std::vector<std::vector<int>> cells((size_t)(gw * gh));
+  for (int i = 0; i < N; ++i) { long long cx, cy; cell(i, &cx, &cy); cells[(size_t)(cy * gw + cx)].push_back(i); }
+  for (int i = 0; i < N; ++i) {
+    cand.clear();
+    long long cx, cy;
+    cell(i, &cx, &cy);
+    for (long long yy = std::max(cy - 1, 0LL); yy <= std::min(cy + 1, gh - 1); ++yy)
+      for (long long xx = std::max(cx - 1, 0LL); xx <= std::min(cx + 1, gw - 1); ++xx)
+        for (int j : cells[(size_t)(yy * gw + xx)]) {
+          if (j == i) continue;
+          float d = 0.f;
+          for (int k = 0; k < 7; ++k) { float e = q[7 * i + k] - q[7 * j + k]; d = std::fmaf(e, e, d); }
+          if (d <= r2) cand.emplace_back(d, j);
+        }
+    size_t keep = std::min(cand.size(), (size_t)max_nbr);
+    std::partial_sort(cand.begin(), cand.begin() + keep, cand.end());
+    for (size_t k = 0; k < keep; ++k) pb.nbr[i].push_back(cand[k].second);
+  }
+}
+
+// spedUpFitting (progressive_x.h:265-391): sequential GC-RANSAC (plain EPOS score, confidence 1) with removal of the
+// inliers of every accepted proposal; no PEARL; the labeling stays all zero (the reference never writes it).
+static void sped_up_fitting(const Problem& all, const Params& P, const MultiParams& MP, u64 seed,
+                            std::vector<Instance>& models, MultiStats& ms) {
+  ms.sped_up = 1;
+  std::vector<int> indices(all.N);
+  for (int i = 0; i < all.N; ++i) indices[i] = i;
+  const bool unbounded = MP.max_model_number < 0;
+  const int limit = unbounded ? MAX_INSTANCES : MP.max_model_number;
+  for (int it = 0; it < limit; ++it) {
+    Problem cur;
+    cur.N = (int)indices.size();
+    cur.pts.resize((size_t)7 * cur.N);
+    std::map<std::pair<int, int>, int> pix;
+    cur.pixel_id.resize(cur.N);
+    for (int r = 0; r < cur.N; ++r) {
+      std::memcpy(&cur.pts[(size_t)7 * r], &all.pts[(size_t)7 * indices[r]], 7 * sizeof(double));
+      auto key = std::make_pair((int)cur.pts[(size_t)7 * r + 5], (int)cur.pts[(size_t)7 * r + 6]);
+      auto itp = pix.find(key);
+      if (itp == pix.end()) itp = pix.emplace(key, (int)pix.size()).first;
+      cur.pixel_id[r] = itp->second;
+    }
+    cur.used_pixels = all.used_pixels;        // settings.proposal_engine_settings.used_pixels is never refreshed
+    cur.thr_n = all.thr_n; cur.sq_trunc = all.sq_trunc;
+    cur.stream_base = 2 * (u64)it;
+    build_neighbors7(cur, 20.0, P.max_neighbors);
+    Params Pl = P;
+    Pl.confidence = 1.0;
+    Stats st;
+    std::vector<int> inliers;
+    Instance inst;
+    ++ms.proposals;
+    const int found = gcransac_run(cur, Pl, seed, inst.m, inliers, st);
+    if (!found) { if (unbounded) break; continue; }
+    ms.ransac_iterations += st.iterations;
+    models.push_back(inst);
+    ++ms.accepted;
+    if ((int)inliers.size() < MP.min_point_number) { if (unbounded) break; continue; }
+    std::vector<char> mask(cur.N, 0);
+    for (int i : inliers) mask[i] = 1;
+    std::vector<int> rest;
+    for (int r = 0; r < cur.N; ++r) if (!mask[r]) rest.push_back(indices[r]);
+    indices.swap(rest);
+    if (unbounded && (int)indices.size() < MP.min_point_number) break;
+  }
+}
+
+// ProgressiveX::run (progressive_x.h:397-649).  Returns the instances; labeling[i] = instance of point i (outlier label
+// = number of instances; with a single instance 0 = inlier, 1 = outlier), scores[k] = sum of instance k's preferences.
+static void progx_run(Problem& pb, const Params& P, const MultiParams& MP, u64 seed, std::vector<Instance>& models,
+                      std::vector<int>& labeling, std::vector<double>& scores, MultiStats& ms) {
+  const int N = pb.N;
+  labeling.assign(N, 0);
+  scores.clear();
+  models.clear();
+  if (MP.max_model_number < 0 || MP.max_model_number_for_pearl < MP.max_model_number) {   // :417-425 (size_t compare)
+    sped_up_fitting(pb, P, MP, seed, models, ms);
+    scores.assign(models.size(), 0.0);                                      // RANSACStatistics::score is never written
+    return;
+  }
+  const double T2 = 9.0 / 4.0 * pb.thr_n * pb.thr_n;                        // :679
+  std::vector<double> compound(N, 0.0);
+  std::vector<std::vector<std::pair<int, double>>> nb;
+  gco_neighbors(pb.nbr, nb);
+  Pearl pearl;
+  Params Pl = P;
+  Pl.confidence = 1.0;                                                     // settings.proposal_engine_confidence (:66,695)
+  long long total_iterations = 0;
+  int unaccepted = 0, first_model_events = 0;
+  for (int it = 0;; ++it) {                                                // the loop condition of :427 is always true
+    if (it > 100) break;
+    ++ms.proposals;
+    pb.cpref = models.empty() ? nullptr : compound.data();
+    pb.stream_base = 2 * (u64)it;
+    Stats st;
+    std::vector<int> inliers;
+    Instance inst;
+    const int found = gcransac_run(pb, Pl, seed, inst.m, inliers, st);
+    pb.cpref = nullptr; pb.stream_base = 0;
+    if (!found) continue;
+    total_iterations += st.iterations;
+    // isPutativeModelValid (:723-749)
+    bool valid = (int)inliers.size() >= std::max(3, MP.min_point_number);
+    if (valid) {
+      preference_vector(pb, inst.m, T2, inst.pref);
+      double dot = 0.0, na = 0.0, nc = 0.0;
+      for (int i = 0; i < N; ++i) { dot += inst.pref[i] * compound[i]; na += inst.pref[i] * inst.pref[i]; nc += compound[i] * compound[i]; }
+      const double tanimoto = dot / (na + nc - dot);
+      if (MP.max_tanimoto < tanimoto) valid = false;
+    }
+    if (!valid) {
+      ++unaccepted;
+      if (unaccepted == 10) break;                                         // max_proposal_number_without_change
+      continue;
+    }
+    models.push_back(inst);
+    ++ms.accepted;
+    if (models.size() == 1) {                                              // :520-529
+      ++first_model_events;
+      std::fill(labeling.begin(), labeling.end(), 1);
+      for (int i : inliers) labeling[i] = 0;
+    } else {                                                               // :531-547
+      pearl.run(pb, nb, models, P.spatial_coherence_weight, MP.min_point_number);
+      labeling = pearl.labels;
+    }
+    // updateCompoundModel (:755-794)
+    if (!models.empty()) {
+      std::fill(compound.begin(), compound.end(), 0.0);
+      scores.assign(models.size(), 0.0);
+      for (size_t k = 0; k < models.size(); ++k)
+        for (int i = 0; i < N; ++i) {
+          compound[i] = std::max(compound[i], models[k].pref[i]);
+          scores[k] += models[k].pref[i];
+        }
+    }
+    // predicted unseen inliers (:589-615, 651-673)
+    const long long covered = models.size() == 1 ? (long long)first_model_events : (long long)N - (long long)pearl.outliers.size();
+    const double ratio = std::pow(1.0 - std::pow(1.0 - MP.confidence, 1.0 / (double)total_iterations), 1.0 / 3.0);
+    const long long unseen = (long long)std::llround((double)((long long)N - covered) * ratio);
+    if (unseen < MP.min_point_number) break;
+    if ((int)models.size() >= MP.max_model_number) break;
+  }
+  ms.ransac_iterations = (int)total_iterations;
+  ms.pearl_iterations = pearl.iterations;
+  ms.moves = pearl.moves;
+}
+
 }  // namespace ora
 
 // ---------------------------------------------------------------------------------------------------
@@ -1236,7 +1715,7 @@ int ora_score(int N, const double* x2d, const double* x3d, const double* K, cons
   ora::make_problem(N, x2d, x3d, K, *P, pb);
   std::vector<int> inl;
   ora::Score s = ora::get_score(pb, model, best_inl, &inl);
-  out[0] = s.value; out[1] = s.inliers; out[2] = pb.used_pixels;
+  out[0] = (long long)s.value; out[1] = s.inliers; out[2] = pb.used_pixels;
   if (inlier_mask) { for (int i = 0; i < N; ++i) inlier_mask[i] = 0; for (int i : inl) inlier_mask[i] = 1; }
   return 0;
 }
@@ -1300,6 +1779,54 @@ int ora_find6dposes(int N, const double* x2d, const double* x3d, const double* K
   int r = ora::find6dposes(N, x2d, x3d, K, *P, seed, nbr_offsets, nbr_index, pose, labeling_out, st);
   if (stats) { stats[0] = st.iterations; stats[1] = st.graph_cuts; stats[2] = st.lo_runs; stats[3] = st.passes; stats[4] = st.found; }
   return r;
+}
+
+// find6DPoses, multi-instance branch (max_model_number != 1).  poses [max_out][12], scores [max_out], labeling [N];
+// stats: {proposals, accepted, ransac_iterations, pearl_iterations, expansion_moves, sped_up}.  Returns the number of
+// instances found (at most max_out are written).
+int ora_find6dposes_multi(int N, const double* x2d, const double* x3d, const double* K, const ora_params* P,
+                          unsigned long long seed, int max_model_number, int max_model_number_for_pearl, double conf,
+                          double max_tanimoto, int min_point_number, const int* nbr_offsets, const int* nbr_index,
+                          int max_out, double* poses, int* labeling_out, double* scores, int* stats) {
+  ora::Problem pb;
+  ora::make_problem(N, x2d, x3d, K, *P, pb);
+  if (nbr_offsets) {
+    pb.nbr.assign(N, std::vector<int>());
+    for (int i = 0; i < N; ++i) pb.nbr[i].assign(nbr_index + nbr_offsets[i], nbr_index + nbr_offsets[i + 1]);
+  } else {
+    ora::build_neighbors(pb, P->neighborhood_ball_radius, P->scaling_from_millimeters, P->max_neighbors);
+  }
+  ora::MultiParams MP = {max_model_number, max_model_number_for_pearl, conf, max_tanimoto, min_point_number};
+  std::vector<ora::Instance> models;
+  std::vector<int> lab;
+  std::vector<double> sc;
+  ora::MultiStats ms;
+  ora::g_trace.clear();
+  ora::progx_run(pb, *P, MP, seed, models, lab, sc, ms);
+  for (int i = 0; i < N; ++i) labeling_out[i] = lab[i];
+  for (size_t k = 0; k < models.size() && (int)k < max_out; ++k) {
+    std::memcpy(poses + 12 * k, models[k].m, 12 * sizeof(double));
+    scores[k] = sc[k];
+  }
+  if (stats) { stats[0] = ms.proposals; stats[1] = ms.accepted; stats[2] = ms.ransac_iterations; stats[3] = ms.pearl_iterations; stats[4] = ms.moves; stats[5] = ms.sped_up; }
+  return (int)models.size();
+}
+
+// alpha-expansion on an explicit problem (tests: cross-check against the reference's GCoptimization in oracle/_ref).
+// D [n][L] data costs, neighbour listings as CSR (listing j of site i -> setNeighbors(i, j)), Potts weight lambda,
+// uniform label cost; labels in/out (initial labeling).  Returns the energy.
+double ora_alpha_expansion(int n, int L, const double* D, const int* nbr_offsets, const int* nbr_index, double lambda,
+                           double label_cost, int* labels, int max_iterations) {
+  ora::AlphaExpansion ax;
+  ax.n = n; ax.L = L; ax.lambda = lambda; ax.label_cost = label_cost;
+  ax.D.assign(D, D + (size_t)n * L);
+  std::vector<std::vector<int>> nbr(n);
+  for (int i = 0; i < n; ++i) nbr[i].assign(nbr_index + nbr_offsets[i], nbr_index + nbr_offsets[i + 1]);
+  ora::gco_neighbors(nbr, ax.nb);
+  ax.label.assign(labels, labels + n);
+  double e = ax.expansion(max_iterations);
+  for (int i = 0; i < n; ++i) labels[i] = ax.label[i];
+  return e;
 }
 
 }  // extern "C"
