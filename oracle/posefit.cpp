@@ -1573,7 +1573,15 @@ static void sped_up_fitting(const Problem& all, const Params& P, const MultiPara
     std::vector<int> rest;
     for (int r = 0; r < cur.N; ++r) if (!mask[r]) rest.push_back(indices[r]);
     indices.swap(rest);
-    if (unbounded && (int)indices.size() < MP.min_point_number) break;
+    if (unbounded) {
+      // "all instances" (max_model_number = -1): the reference's loop bound is (size_t)-1, i.e. it never terminates
+      // (progressive_x.h:280 compares a size_t counter with an int holding -1).  Defined behaviour here: stop when no
+      // model is found, when a proposal has fewer than min_point_number inliers, or when the termination test of
+      // ProgressiveX::run (:589-611: predicted number of unseen inliers below min_point_number) fires on the points
+      // that remain; at most MAX_INSTANCES instances.
+      const double ratio = std::pow(1.0 - std::pow(1.0 - MP.confidence, 1.0 / (double)ms.ransac_iterations), 1.0 / 3.0);
+      if (std::llround((double)indices.size() * ratio) < MP.min_point_number) break;
+    }
   }
 }
 

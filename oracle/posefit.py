@@ -45,6 +45,35 @@ def ref_lib():
     return _REF
 
 
+_REF_GCO = None
+
+
+def ref_gco_lib():
+    """The reference's own alpha-expansion (oracle/_ref/libref_gco.so), or None when not built."""
+    global _REF_GCO
+    if _REF_GCO is None:
+        so = os.path.join(_HERE, '_ref', 'libref_gco.so')
+        if not os.path.exists(so):
+            return None
+        _REF_GCO = C.CDLL(so)
+        _REF_GCO.ref_gco_expansion.restype = C.c_double
+    return _REF_GCO
+
+
+def ref_alpha_expansion(D, nbr, lam, label_cost, labels=None, max_iterations=1000):
+    """alpha_expansion() through the reference's GCoptimization (None when oracle/_ref is not built)."""
+    r = ref_gco_lib()
+    if r is None:
+        return None
+    D = _d(D)
+    n, L = D.shape
+    off, idx = _csr(nbr)
+    lab = np.zeros(n, np.int32) if labels is None else np.ascontiguousarray(labels, np.int32).copy()
+    e = r.ref_gco_expansion(n, L, _p(D), _p(off, C.c_int), _p(idx, C.c_int), C.c_double(lam), C.c_double(label_cost),
+                            _p(lab, C.c_int), int(labels is not None), int(max_iterations))
+    return lab, float(e)
+
+
 def default_params(**kw):
     p = Params()
     lib().ora_params_default(C.byref(p))
@@ -223,13 +252,29 @@ def ref_bk_labeling(graph, lam):
     return labels
 
 
+def alpha_expansion(D, nbr, lam, label_cost, labels=None, max_iterations=1000):
+    """GCoptimization-style alpha-expansion (standard cycles) on data costs D [n, L], neighbour LISTINGS nbr (list of
+    lists; a mutual pair listed from both sides weighs twice), Potts weight lam and a uniform label cost.
+    Returns (labels, energy)."""
+    D = _d(D)
+    n, L = D.shape
+    off, idx = _csr(nbr)
+    lab = np.zeros(n, np.int32) if labels is None else np.ascontiguousarray(labels, np.int32).copy()
+    f = lib().ora_alpha_expansion
+    f.restype = C.c_double
+    e = f(n, L, _p(D), _p(off, C.c_int), _p(idx, C.c_int), C.c_double(lam), C.c_double(label_cost), _p(lab, C.c_int),
+          int(max_iterations))
+    return lab, float(e)
+
+
 def find6DPoses(x1y1, x2y2z2, K, threshold=4.0, max_model_number=1, conf=0.5, proposal_engine_conf=1.0,
                 spatial_coherence_weight=0.1, neighborhood_ball_radius=20.0, max_tanimoto_similarity=0.9,
                 scaling_from_millimeters=0.1, min_triangle_area=100.0, min_coverage=0.5, max_iters=400,
                 min_point_number=6, use_prosac=False, max_model_number_for_optimization=3,
                 apply_numerical_optimization=True, log=False, seed=0, nbr=None, return_stats=False, max_neighbors=5):
     """Same signature as pyprogressivex.find6DPoses (bindings.cpp:9-28,133-152) + seed / nbr.
-    Only the single-instance branch (max_model_number == 1) is restated."""
+    max_model_number == 1: GC-RANSAC + final LM; otherwise Progressive-X (PEARL for 2..max_model_number_for_optimization
+    instances, sequential propose-and-remove beyond that or for -1)."""
     x1y1, x2y2z2, K = _d(x1y1), _d(x2y2z2), _d(K)
     if x1y1.ndim != 2 or x1y1.shape[1] != 2 or x2y2z2.ndim != 2 or x2y2z2.shape[1] != 3:
         raise ValueError('x1y1 should be an array with dims [n,2], x2y2z2 [n,3]')
@@ -238,13 +283,36 @@ def find6DPoses(x1y1, x2y2z2, K, threshold=4.0, max_model_number=1, conf=0.5, pr
         raise ValueError('x1y1 and x2y2z2 should be the same size, n>=3')
     if K.shape != (3, 3):
         raise ValueError('K should be an array with dims [3,3]')
-    if max_model_number != 1:
-        raise NotImplementedError('oracle restates the single-instance branch only')
     p = default_params(threshold=threshold, spatial_coherence_weight=spatial_coherence_weight,
                        neighborhood_ball_radius=neighborhood_ball_radius,
                        scaling_from_millimeters=scaling_from_millimeters, min_triangle_area=min_triangle_area,
                        min_coverage=min_coverage, confidence=proposal_engine_conf, max_iters=max_iters,
                        max_neighbors=max_neighbors, apply_numerical_optimization=int(apply_numerical_optimization))
+    if max_model_number != 1:
+        # Progressive-X (progressivex_python.cpp:136-221).  proposal_engine_conf is not forwarded by the reference in this
+        # branch (the proposal engine runs at MultiModelSettings::proposal_engine_confidence = 1.0, progressive_x.h:66,695).
+        if max_model_number == 0 or max_model_number < -1:
+            raise ValueError('max_model_number should be -1 or positive')
+        cap = 64 if max_model_number < 0 else max(max_model_number, 1) * 2 + 2
+        poses = np.zeros((cap, 12))
+        labels = np.zeros(n, np.int32)
+        scores = np.zeros(cap)
+        stats = np.zeros(6, np.int32)
+        if nbr is None:
+            off = idx = None
+        else:
+            off, idx = _csr(nbr)
+        m = lib().ora_find6dposes_multi(n, _p(x1y1), _p(x2y2z2), _p(K), C.byref(p), C.c_ulonglong(seed),
+                                        int(max_model_number), int(max_model_number_for_optimization), C.c_double(conf),
+                                        C.c_double(max_tanimoto_similarity), int(min_point_number),
+                                        None if off is None else _p(off, C.c_int), None if idx is None else _p(idx, C.c_int),
+                                        cap, _p(poses), _p(labels, C.c_int), _p(scores), _p(stats, C.c_int))
+        assert m <= cap
+        out = (poses[:m].reshape(3 * m, 4).copy(), labels, scores[:m].copy())
+        if return_stats:
+            out = out + (dict(zip(('proposals', 'accepted', 'ransac_iterations', 'pearl_iterations', 'expansion_moves',
+                                   'sped_up'), stats.tolist())),)
+        return out
     pose = np.zeros(12)
     labels = np.zeros(n, np.int32)
     stats = np.zeros(5, np.int32)
