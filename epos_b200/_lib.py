@@ -22,6 +22,12 @@ class FitParams(C.Structure):
                 ('apply_numerical_optimization', C.c_int32), ('reserved', C.c_int32)]
 
 
+class MultiParams(C.Structure):
+    """epos_multi_params (include/epos_b200.h)."""
+    _fields_ = [('max_model_number_for_pearl', C.c_int32), ('min_point_number', C.c_int32), ('confidence', f64),
+                ('max_tanimoto_similarity', f64)]
+
+
 _SIGS = {
     'epos_last_error': (C.c_char_p, []),
     'epos_version': (i32, []),
@@ -53,6 +59,11 @@ _SIGS = {
     'epos_fit_params_default': (None, [C.POINTER(FitParams)]),
     'epos_fit_poses': (i32, [vp, vp, vp, vp, i32, vp, vp, C.POINTER(FitParams), vp, vp, vp, sz, vp]),
     'epos_fit_workspace_bytes': (sz, [i32, i32, C.POINTER(FitParams)]),
+    'epos_fit_poses_multi': (i32, [vp, vp, vp, vp, i32, vp, vp, C.POINTER(FitParams), C.POINTER(MultiParams), vp, vp, vp,
+                                   vp, vp, vp, vp, sz, vp]),
+    'epos_fit_multi_workspace_bytes': (sz, [i32]),
+    'epos_fit_max_instances': (i32, []),
+    'epos_fit_multi_debug_state': (i32, [vp, i32, vp]),
 }
 
 

@@ -51,7 +51,13 @@ struct ProbState {
   double coverage;
   unsigned long long iter, max_iteration, seed;
   int N, used_pixels, valid, phase, pass;
-  int best_value, best_inl, lo_value, lo_inl;
+  double best_value, lo_value;      // Score::value is a double (pixel count; minus (shared support)^2 with a compound model)
+  int best_inl, lo_inl;
+  // Progressive-X proposal engine only (single-instance problems keep cpref = NULL, stream_base = 0): the compound
+  // model's preference vector and the random-stream pair (stream_base, stream_base + 1) of the current proposal
+  const double* cpref;
+  unsigned long long stream_base;
+  int multi, n_final;               // multi = 1: phase_final keeps (model, inlier list) in the workspace, no final LM
   int lo_runs, gc_count, lo_final, lo_stage;
   int ni, found, err, pad;
   int chunk_base, chunk_n;
@@ -81,11 +87,33 @@ struct Workspace {
   unsigned short* order;    // [P][NMAX]    BFS queue
   PassRecord* recs;         // [P][CHUNK]   hypotheses of the current chunk of RANSAC passes
   int* trace;               // [P][TRACE_ROUNDS][TRACE_COLS] LO rounds: gc, ni, updated, lo_value, lo_inl, (ok, inl, pix) x 20
+  // ---- Progressive-X (multi-instance problems only; NULL otherwise) ----
+  struct MultiState* ms;    // [P]
+  double* fin_model;        // [P][12]            model of the last proposal (phase_final, multi = 1)
+  unsigned short* fin_inl;  // [P][NMAX]          its inlier list (st->n_final entries)
+  double* models;           // [P][MAX_INSTANCES][12]
+  double* pref;             // [P][PEARL_MAX][NMAX]  preference vectors of the instances (as of their acceptance)
+  double* compound;         // [P][NMAX]
+  double* r2tab;            // [P][PEARL_MAX][NMAX]  squared residuals of the current PEARL iteration
+  int* labels;              // [P][NMAX]
+  double* cr;               // [P][NMAX*MAXNB]    reverse capacities of the expansion graph (capf = forward)
+  double* af;               // [P][NMAX]          flow on the arc aux(label) -> site
+  unsigned char* mult;      // [P][NMAX][MAXNB]   multiplicity (1 / 2) of an owned neighbour pair
+  unsigned short* lists;    // [P][NMAX]          scratch index list (instance members)
+};
+constexpr int MAX_INSTANCES = 32;   // instances returned at most ("all instances" mode; PEARL mode keeps <= 5)
+constexpr int PEARL_MAX = 6;        // instances PEARL may hold at once (max_model_number_for_optimization <= 5, + the proposal)
+
+struct MultiState {
+  long long total_iterations;
+  int n_models, unaccepted, first_events, n_outliers, proposals, accepted, pearl_iterations, moves, done;
+  int max_models, sped_up, pad;
+  double scores[MAX_INSTANCES];
 };
 
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
-static size_t workspace_layout(int P, void* base, Workspace* w) {
+static size_t workspace_layout(int P, void* base, Workspace* w, bool multi = false) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return base ? (char*)base + o : (char*)nullptr; };
   char* p;
@@ -104,8 +132,25 @@ static size_t workspace_layout(int P, void* base, Workspace* w) {
   p = take((size_t)P * NMAX * 4); if (w) w->dist = (int*)p;
   p = take((size_t)P * (NMAX + 2) * 4); if (w) w->lstart = (int*)p;
   p = take((size_t)P * NMAX * 2); if (w) w->order = (unsigned short*)p;
-  p = take((size_t)P * 80 * 432); if (w) w->recs = (PassRecord*)p;
+  p = take((size_t)P * 80 * 464); if (w) w->recs = (PassRecord*)p;
   p = take((size_t)P * TRACE_ROUNDS * TRACE_COLS * 4); if (w) w->trace = (int*)p;
+  if (w) { w->ms = nullptr; w->fin_model = nullptr; w->fin_inl = nullptr; w->models = nullptr; w->pref = nullptr;
+           w->compound = nullptr; w->r2tab = nullptr; w->labels = nullptr; w->cr = nullptr; w->af = nullptr;
+           w->mult = nullptr; w->lists = nullptr; }
+  if (multi) {
+    p = take((size_t)P * sizeof(MultiState)); if (w) w->ms = (MultiState*)p;
+    p = take((size_t)P * 12 * 8); if (w) w->fin_model = (double*)p;
+    p = take((size_t)P * NMAX * 2); if (w) w->fin_inl = (unsigned short*)p;
+    p = take((size_t)P * MAX_INSTANCES * 12 * 8); if (w) w->models = (double*)p;
+    p = take((size_t)P * PEARL_MAX * NMAX * 8); if (w) w->pref = (double*)p;
+    p = take((size_t)P * NMAX * 8); if (w) w->compound = (double*)p;
+    p = take((size_t)P * PEARL_MAX * NMAX * 8); if (w) w->r2tab = (double*)p;
+    p = take((size_t)P * NMAX * 4); if (w) w->labels = (int*)p;
+    p = take((size_t)P * NMAX * MAXNB * 8); if (w) w->cr = (double*)p;
+    p = take((size_t)P * NMAX * 8); if (w) w->af = (double*)p;
+    p = take((size_t)P * NMAX * MAXNB); if (w) w->mult = (unsigned char*)p;
+    p = take((size_t)P * NMAX * 2); if (w) w->lists = (unsigned short*)p;
+  }
   return off;
 }
 
@@ -165,9 +210,10 @@ prep_kernel(Workspace ws, const double* __restrict__ c2d, const double* __restri
   if (tid == 0) {
     st->N = N; st->valid = ok ? 1 : 0; st->err = N > NMAX ? 1 : 0;
     st->phase = ok ? PH_MAIN : PH_DONE;
-    st->iter = 0; st->pass = 0; st->best_value = 0; st->best_inl = 0; st->coverage = 0.0;
+    st->iter = 0; st->pass = 0; st->best_value = 0.0; st->best_inl = 0; st->coverage = 0.0;
+    st->cpref = nullptr; st->stream_base = 0ULL; st->multi = 0; st->n_final = 0;
     st->lo_runs = 0; st->gc_count = 0; st->lo_final = 0; st->lo_stage = 0; st->ni = 0; st->found = 0;
-    st->lo_value = 0; st->lo_inl = 0; st->used_pixels = 0; st->chunk_base = 0; st->chunk_n = 0;
+    st->lo_value = 0.0; st->lo_inl = 0; st->used_pixels = 0; st->chunk_base = 0; st->chunk_n = 0;
     st->t_sample = st->t_score = st->t_replay = st->t_total = 0;
     st->t_cut = st->t_trials = st->t_final = st->t_fit = 0;
     st->n_scored_main = st->n_scored_lo = st->n_scored_final = 0;
@@ -438,14 +484,19 @@ __device__ __forceinline__ bool is_inlier(double un, double vn, double x, double
 
 // EPOSScoringFunction::getScore (scoring_function.h:220-267) by one warp: inlier count by ballot, distinct pixels
 // through a per-warp bitset.  bits: NMAX/32 words owned by this warp.  Four points per lane are in flight.
+// cpref != NULL (Progressive-X): *val_out = pixels - (shared support)^2, shared = sum_i min(cpref_i, max(0, 1 - r_i^2/T))
+// over the inliers (scoring_function_with_compound_model.h:216-263).  Summation order as defined by the oracle: point i
+// goes to the partial sum of lane i mod 32 in ascending order, then a butterfly over the lanes.
 __device__ inline void score_warp(const SmemPoints& sp, int N, const double* model, double sq_trunc, unsigned int* bits,
-                                  int lane, int* inl_out, int* pix_out) {
+                                  int lane, int* inl_out, int* pix_out, const double* __restrict__ cpref = nullptr,
+                                  double* val_out = nullptr) {
   double m[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) m[k] = model[k];
   for (int k = lane; k < NMAX / 32; k += 32) bits[k] = 0u;
   __syncwarp();
   int inl = 0;
+  double shared = 0.0;
   for (int base = 0; base < N; base += 128) {
     bool in[4];
 #pragma unroll
@@ -457,8 +508,15 @@ __device__ inline void score_warp(const SmemPoints& sp, int N, const double* mod
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (in[u]) {
-        const unsigned int pid = sp.pix[base + u * 32 + lane];
+        const int i = base + u * 32 + lane;
+        const unsigned int pid = sp.pix[i];
         atomicOr(&bits[pid >> 5], 1u << (pid & 31));
+        if (cpref) {
+          double pref = 1.0 - sq_residual(sp.un[i], sp.vn[i], sp.x[i], sp.y[i], sp.z[i], m) / sq_trunc;
+          if (!(pref > 0.0)) pref = 0.0;
+          const double c = cpref[i];
+          shared += c < pref ? c : pref;
+        }
       }
       inl += __popc(__ballot_sync(0xffffffffu, in[u]));
     }
@@ -470,6 +528,15 @@ __device__ inline void score_warp(const SmemPoints& sp, int N, const double* mod
   for (int o = 16; o > 0; o >>= 1) px += __shfl_xor_sync(0xffffffffu, px, o);
   *inl_out = inl;
   *pix_out = px;
+  if (val_out) {
+    double v = (double)px;
+    if (cpref) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) shared += __shfl_xor_sync(0xffffffffu, shared, o);
+      v -= shared * shared;
+    }
+    *val_out = v;
+  }
 }
 
 // thread 0 only: end of graphCutLocalOptimization (GCRANSAC.h:799-808) + the caller's bookkeeping (:418-427)
@@ -496,6 +563,7 @@ struct PassRecord {
   double models[48];
   int nm, fails;
   int inl[4], pix[4];
+  double val[4];
 };
 
 constexpr int CHUNK = 80;            // RANSAC passes evaluated per chunk (a multiple of the 20 warps) (records survive LO rounds in the workspace)
@@ -513,7 +581,10 @@ __device__ __noinline__ void phase_main(const Workspace& ws, const epos_fit_para
   // state (identical in every thread)
   unsigned long long iter = st->iter, max_iteration = st->max_iteration;
   const unsigned long long seed = st->seed;
-  int pass = st->pass, best_value = st->best_value, best_inl = st->best_inl, lo_runs = st->lo_runs, gc_count = st->gc_count;
+  int pass = st->pass, best_inl = st->best_inl, lo_runs = st->lo_runs, gc_count = st->gc_count;
+  double best_value = st->best_value;
+  const double* cpref = st->cpref;
+  const unsigned long long stream0 = st->stream_base;
   int chunk_base = st->chunk_base, chunk_n = st->chunk_n;
   double coverage = st->coverage;
   const int used_pixels = st->used_pixels;
@@ -537,7 +608,7 @@ __device__ __noinline__ void phase_main(const Workspace& ws, const epos_fit_para
         double models[48];
         while (++fails < prm.max_unsuccessful) {
           int s[3];
-          if (!unique_set(seed, 0, (u64)my_pass, (u64)fails, N, 3, s)) continue;
+          if (!unique_set(seed, stream0, (u64)my_pass, (u64)fails, N, 3, s)) continue;
           // isValidSample (perspective_n_point_estimator.h:172-198): pixel-space triangle area > min_triangle_area
           const double u0 = PU[s[0]], v0 = PU[NMAX + s[0]];
           const double area = 0.5 * fabs((PU[s[1]] - u0) * (PU[NMAX + s[2]] - v0) - (PU[s[2]] - u0) * (PU[NMAX + s[1]] - v0));
@@ -561,8 +632,9 @@ __device__ __noinline__ void phase_main(const Workspace& ws, const epos_fit_para
         const int nm = rc->nm;
         for (int m = 0; m < nm; ++m) {
           int inl, px;
-          score_warp(sp, N, rc->models + 12 * m, sq_trunc, bits, lane, &inl, &px);
-          if (lane == 0) { rc->inl[m] = inl; rc->pix[m] = px; }
+          double val;
+          score_warp(sp, N, rc->models + 12 * m, sq_trunc, bits, lane, &inl, &px, cpref, &val);
+          if (lane == 0) { rc->inl[m] = inl; rc->pix[m] = px; rc->val[m] = val; }
         }
       }
       __syncthreads();
@@ -582,8 +654,9 @@ __device__ __noinline__ void phase_main(const Workspace& ws, const epos_fit_para
       iter += (unsigned long long)rc->fails;
       const int nm = rc->nm;
       for (int m = 0; m < nm; ++m) {
-        int s_inl = rc->inl[m], s_val = rc->pix[m];
-        if (s_inl + 1 < best_inl) { s_inl = 0; s_val = 0; }       // early-out of getScore, scoring_function.h:257-259
+        int s_inl = rc->inl[m];
+        double s_val = rc->val[m];
+        if (s_inl + 1 < best_inl) { s_inl = 0; s_val = 0.0; }     // early-out of getScore, scoring_function.h:257-259
         if (best_value < s_val) {
           best_value = s_val; best_inl = s_inl;
           __syncthreads();
@@ -799,7 +872,7 @@ __device__ __noinline__ void phase_cut(const Workspace& ws, const epos_fit_param
 // =====================================================================================================
 // trials: inner RANSAC of the local optimisation, one warp per trial
 // =====================================================================================================
-struct TrialRecord { double model[12]; int ok, inl, pix, pad; };
+struct TrialRecord { double model[12]; double val; int ok, inl, pix, pad; };
 
 __device__ __noinline__ void phase_trials(const Workspace& ws, const epos_fit_params& prm, int p, unsigned char* smem_raw,
                                           bool& pts_loaded) {
@@ -832,7 +905,7 @@ __device__ __noinline__ void phase_trials(const Workspace& ws, const epos_fit_pa
   for (int t = warp; t < n_eval; t += TW) {
     if (sample_size < ni) {
       int sel[21];
-      unique_set(st->seed, 1, (u64)gc, (u64)t, ni, sample_size, sel);
+      unique_set(st->seed, st->stream_base + 1ULL, (u64)gc, (u64)t, ni, sample_size, sel);
       if (lane < sample_size) sample[lane] = inl[sel[lane]];
     } else {
       if (lane < sample_size) sample[lane] = inl[lane];
@@ -850,8 +923,9 @@ __device__ __noinline__ void phase_trials(const Workspace& ws, const epos_fit_pa
       if (lane < 12) rc->model[lane] = model[lane];
       __syncwarp();
       int in_, px;
-      score_warp(sp, N, rc->model, sq_trunc, bits, lane, &in_, &px);
-      if (lane == 0) { rc->ok = 1; rc->inl = in_; rc->pix = px; }
+      double val;
+      score_warp(sp, N, rc->model, sq_trunc, bits, lane, &in_, &px, st->cpref, &val);
+      if (lane == 0) { rc->ok = 1; rc->inl = in_; rc->pix = px; rc->val = val; }
     }
     __syncwarp();
   }
@@ -860,27 +934,30 @@ __device__ __noinline__ void phase_trials(const Workspace& ws, const epos_fit_pa
     st->t_fit += t_fit;
     for (int t = 0; t < n_eval; ++t) st->n_scored_lo += recs[t].ok ? 1 : 0;
     bool updated = false;
-    int mv = st->lo_value, mi = st->lo_inl;
+    double mv = st->lo_value;
+    int mi = st->lo_inl;
     if (sample_size < ni) {
       for (int t = 0; t < trials; ++t) {
         const TrialRecord* rc = recs + t;
         if (!rc->ok) continue;                                      // failed fit: `continue` (GCRANSAC.h:748-752)
-        int s_inl = rc->inl, s_val = rc->pix;
-        if (s_inl + 1 < mi) { s_inl = 0; s_val = 0; }
+        int s_inl = rc->inl;
+        double s_val = rc->val;
+        if (s_inl + 1 < mi) { s_inl = 0; s_val = 0.0; }
         if (mv < s_val) { updated = true; mv = s_val; mi = s_inl; for (int i = 0; i < 12; ++i) st->lo_model[i] = rc->model[i]; }
       }
     } else if (3 < ni) {
       const TrialRecord* rc = recs;                                 // identical model in every trial: first one decides
       if (rc->ok) {
-        int s_inl = rc->inl, s_val = rc->pix;
-        if (s_inl + 1 < mi) { s_inl = 0; s_val = 0; }
+        int s_inl = rc->inl;
+        double s_val = rc->val;
+        if (s_inl + 1 < mi) { s_inl = 0; s_val = 0.0; }
         if (mv < s_val) { updated = true; mv = s_val; mi = s_inl; for (int i = 0; i < 12; ++i) st->lo_model[i] = rc->model[i]; }
       }
     }
     st->lo_value = mv; st->lo_inl = mi;
     if (gc >= 1 && gc <= TRACE_ROUNDS) {
       int* tr = ws.trace + ((size_t)p * TRACE_ROUNDS + (gc - 1)) * TRACE_COLS;
-      tr[0] = gc; tr[1] = ni; tr[2] = updated ? 1 : 0; tr[3] = mv; tr[4] = mi;
+      tr[0] = gc; tr[1] = ni; tr[2] = updated ? 1 : 0; tr[3] = (int)mv; tr[4] = mi;
       for (int t = 0; t < MAX_TRIALS; ++t) {
         const bool have = t < n_eval;
         tr[5 + 3 * t] = have ? recs[t].ok : -1; tr[6 + 3 * t] = have && recs[t].ok ? recs[t].inl : 0;
@@ -942,6 +1019,7 @@ __device__ __noinline__ void phase_final(const Workspace& ws, const epos_fit_par
   ProbState* st = ws.st + p;
   double* rec = poses + (size_t)p * EPOS_POSE_RECORD_DOUBLES;
   if (st->phase != PH_FINAL) {
+    if (st->multi) { if (tid == 0) { st->n_final = 0; st->found = 0; } __syncthreads(); return; }
     if (tid == 0 && st->valid) { rec[13] = (double)st->iter; rec[15] = (double)st->gc_count; }
     if (tid == 0 && st->err) rec[14] = -1.0;                      // more than NMAX correspondences
     return;
@@ -983,7 +1061,30 @@ __device__ __noinline__ void phase_final(const Workspace& ws, const epos_fit_par
   const double sq_trunc = st->sq_trunc;
   double best_model[12];
   for (int i = 0; i < 12; ++i) best_model[i] = st->best_model[i];
-  const int best_value = st->best_value;
+  const double best_value = st->best_value;
+  const double* cpref = st->cpref;
+  // Progressive-X: score value = pixels - (shared support)^2; the shared support is summed by warp 0 in score_warp's order
+  auto compound_value = [&](const double* model, int pixels) -> double {
+    if (!cpref) return (double)pixels;
+    __syncthreads();
+    if (tid < 32) {
+      double shared = 0.0;
+      for (int i = tid; i < N; i += 32)
+        if (is_inlier(sp.un[i], sp.vn[i], sp.x[i], sp.y[i], sp.z[i], model, sq_trunc)) {
+          double pref = 1.0 - sq_residual(sp.un[i], sp.vn[i], sp.x[i], sp.y[i], sp.z[i], model) / sq_trunc;
+          if (!(pref > 0.0)) pref = 0.0;
+          const double c = cpref[i];
+          shared += c < pref ? c : pref;
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) shared += __shfl_xor_sync(0xffffffffu, shared, o);
+      if (tid == 0) bcast[15] = shared;
+    }
+    __syncthreads();
+    const double sh_ = bcast[15];
+    __syncthreads();
+    return (double)pixels - sh_ * sh_;
+  };
   int nA, pxA;
   int n_scored = 1;
   score_cta(sp, N, best_model, sq_trunc, bits, scan_sh, listA, &nA, &pxA, &red_sh);      // GCRANSAC.h:470-478
@@ -1013,7 +1114,7 @@ __device__ __noinline__ void phase_final(const Workspace& ws, const epos_fit_par
       int nC, pxC;
       score_cta(sp, N, cur, sq_trunc, bits, scan_sh, listC, &nC, &pxC, &red_sh);
       ++n_scored;
-      if (best_value < pxC) {
+      if (best_value < compound_value(cur, pxC)) {
         refit_applied = true;
         for (int i = 0; i < 12; ++i) best_model[i] = cur[i];
         for (int i = tid; i < nC; i += THREADS) listA[i] = listC[i];
@@ -1026,6 +1127,17 @@ __device__ __noinline__ void phase_final(const Workspace& ws, const epos_fit_par
     double m2[12];
     if (fit_list(listA, nA, m2))
       for (int i = 0; i < 12; ++i) best_model[i] = m2[i];
+  }
+  if (st->multi) {
+    // Progressive-X proposal: the model and its inliers stay in the workspace (no final LM in this branch of
+    // progressivex_python.cpp:136-221); the caller continues with validation / PEARL
+    __syncthreads();
+    if (tid < 12) ws.fin_model[(size_t)p * 12 + tid] = best_model[tid];
+    unsigned short* fo = ws.fin_inl + (size_t)p * NMAX;
+    for (int i = tid; i < nA; i += THREADS) fo[i] = listA[i];
+    if (tid == 0) { st->n_final = nA; st->found = 1; st->phase = PH_DONE; st->n_scored_final += n_scored; }
+    __syncthreads();
+    return;
   }
   if (prm.apply_numerical_optimization && nA >= 6) {                                     // progressivex_python.cpp:257-312
     const double R[9] = {best_model[0], best_model[1], best_model[2], best_model[4], best_model[5], best_model[6],
@@ -1065,6 +1177,606 @@ __device__ __noinline__ void phase_final(const Workspace& ws, const epos_fit_par
   }
   const int off = offsets[p];
   for (int i = tid; i < nA; i += THREADS) labeling[off + listA[i]] = 1;
+}
+
+// =====================================================================================================
+// Progressive-X (multi-instance fitting): ProgressiveX::run with PEARL
+//   /root/reference/external/progressive-x/src/pyprogressivex/include/progressive_x.h:397-649,651-794, PEARL.h:271-536,
+//   scoring_function_with_compound_model.h:127-266; alpha-expansion with label costs:
+//   .../graph-cut-ransac/src/pygcransac/include/GCoptimization.cpp:316-404,452-470,1003-1088,1131-1303.
+// One persistent CTA per problem runs the whole outer loop: proposal (the GC-RANSAC state machine above with the
+// compound score) -> validation (Tanimoto) -> PEARL (alpha-expansion by preflow-push, refits, rejections) -> compound
+// model update -> termination test.  Restated against oracle/posefit.cpp (progx_run), which is pinned on the reference's
+// own GCoptimization sources.
+// =====================================================================================================
+struct MultiParams {
+  int max_model_number_for_pearl;   // maximum_model_number_to_optimize
+  int min_point_number;             // minimum inliers of an instance and PEARL's label cost
+  double confidence;                // conf (0.5)
+  double max_tanimoto;              // 0.9
+};
+
+// runs the GC-RANSAC state machine of problem p (phases main / cut / trials) until it is ready for phase_final
+__device__ inline void run_state_machine(const Workspace& ws, const epos_fit_params& prm, int p, unsigned char* smem_raw,
+                                         bool& pts_loaded) {
+  ProbState* st = ws.st + p;
+  for (int guard = 0; guard < 1 << 14; ++guard) {
+    __syncthreads();
+    const int phase = st->phase, stage = st->lo_stage;
+    __syncthreads();
+    if (phase == PH_MAIN) {
+      phase_main(ws, prm, p, smem_raw, pts_loaded);
+    } else if (phase == PH_LO) {
+      if (stage == 0) { phase_cut(ws, prm, p, smem_raw); pts_loaded = false; }
+      else phase_trials(ws, prm, p, smem_raw, pts_loaded);
+    } else {
+      break;
+    }
+  }
+  __syncthreads();
+}
+
+// block-wide sum of one double per thread (fixed order: lanes by butterfly, warps sequentially) -> every thread
+__device__ inline double block_sum(double v, double* sh /* WARPS + 1 doubles */) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) { double s = 0.0; for (int w = 0; w < WARPS; ++w) s += sh[w]; sh[WARPS] = s; }
+  __syncthreads();
+  const double r = sh[WARPS];
+  __syncthreads();
+  return r;
+}
+
+struct PearlCtx {
+  int N, L, KN;                 // sites, labels (instances + outlier), neighbour slots per site
+  double T2, oml, lambda, cost;
+  int* label;                   // [N]   (shared memory)
+  const double* r2tab;          // [L-1][NMAX]
+  const short* nbr; const unsigned char* owned; const unsigned char* mult; const int* rev_off; const int* rev_idx;
+  double* cf; double* cr; double* fl;   // per owned slot (stride KN): capacity owner->nbr, nbr->owner, flow owner->nbr
+  double* exc; double* af;      // [N]   (shared memory)
+  int* dist; unsigned short* order; int* lstart;
+  int* newlab;                  // [N] scratch (shared memory)
+};
+
+__device__ __forceinline__ double pearl_data_cost(const PearlCtx& c, int i, int l) {      // PEARL.h:81-134
+  if (l == c.L - 1) return c.oml;
+  const double r2 = c.r2tab[(size_t)l * NMAX + i];
+  return r2 > c.T2 ? 2.0 * c.oml : c.oml * r2 / c.T2;
+}
+
+// One expansion move on label alpha (GCoptimization.cpp:1239-1303).  The binary energy of the move is minimised by a
+// preflow-push max-flow over: the sites whose label differs from alpha, the neighbour arcs between them, and one
+// auxiliary node per other label in use (label cost; GCoptimization.cpp:1131-1196: source -> aux capacity `cost`,
+// aux -> every site of that label capacity `cost`).  A site keeps its label iff it can still reach the sink in the
+// residual graph (what_segment == SINK, residuals below CUT_EPS count as saturated), otherwise it takes alpha.  The move
+// is applied iff it lowers the energy by more than 1e-9 (the reference compares the flow value with the energy before
+// the move; the oracle uses the same tolerance).  Returns true when the labeling changed.
+__device__ __noinline__ bool pearl_expansion_move(const PearlCtx& c, int alpha, double* red_sh) {
+  __shared__ int s_cnt[PEARL_MAX], s_qn, s_any, s_adist[PEARL_MAX], s_anext[PEARL_MAX], s_changed;
+  __shared__ double s_aexc[PEARL_MAX];
+  const int tid = threadIdx.x, N = c.N, L = c.L, KN = c.KN;
+  if (tid < PEARL_MAX) s_cnt[tid] = 0;
+  if (tid == 0) s_changed = 0;
+  __syncthreads();
+  for (int i = tid; i < N; i += THREADS) atomicAdd(&s_cnt[c.label[i]], 1);
+  __syncthreads();
+  if (s_cnt[alpha] == N) return false;                                // no active site
+  const double lam = c.lambda;
+  // ---- terminal capacities and arc capacities ----
+  for (int i = tid; i < N; i += THREADS) {
+    const int li = c.label[i];
+    const bool act = li != alpha;
+    double tr = act ? pearl_data_cost(c, i, li) - pearl_data_cost(c, i, alpha) : 0.0;   // source minus sink capacity
+    for (int k = 0; k < KN; ++k) {
+      const size_t e = (size_t)i * KN + k;
+      double f = 0.0, r = 0.0;
+      if (c.owned[(size_t)i * MAXNB + k]) {
+        const int j = c.nbr[(size_t)i * MAXNB + k];
+        const int lj = c.label[j];
+        const double w = lam * (double)c.mult[(size_t)i * MAXNB + k];
+        if (act && lj != alpha) {
+          // add_term2(x = larger index, y = smaller index, 0, w, w, D) with D = w [l_x != l_y] (GCoptimization.cpp:391-398):
+          // terminal(x) += D, arc x -> y capacity w, arc y -> x capacity w - D
+          const double D = li != lj ? w : 0.0;
+          if (i > j) { tr += D; f = w; r = w - D; } else { f = w - D; r = w; }
+        } else if (act) {
+          tr += w;                                                    // add_term1(i, 0, w): the neighbour already has alpha
+        }
+      }
+      c.cf[e] = f; c.cr[e] = r; c.fl[e] = 0.0;
+    }
+    for (int a = c.rev_off[i]; a < c.rev_off[i + 1]; ++a) {           // pairs owned by the other endpoint
+      const int e0 = c.rev_idx[a];
+      const int x = e0 / MAXNB, k = e0 % MAXNB;
+      const int lx = c.label[x];
+      const double w = lam * (double)c.mult[(size_t)x * MAXNB + k];
+      if (act && lx != alpha) { if (i > x && li != lx) tr += w; }
+      else if (act) tr += w;
+    }
+    c.exc[i] = tr;
+    c.af[i] = 0.0;
+  }
+  if (tid < PEARL_MAX) s_aexc[tid] = (tid < L && tid != alpha && s_cnt[tid] > 0 && c.cost > 0.0) ? c.cost : 0.0;
+  __syncthreads();
+  // ---- preflow-push in waves (as phase_cut), with the auxiliary label-cost nodes ----
+  int depth_cap = 2;
+  for (int round = 0; round < 8192; ++round) {
+    if (tid == 0) { s_qn = 0; s_any = 0; }
+    if (tid < PEARL_MAX) { s_adist[tid] = DIST_INF; s_anext[tid] = DIST_INF; }
+    __syncthreads();
+    for (int i = tid; i < N; i += THREADS) {
+      const bool root = c.label[i] != alpha && c.exc[i] < -CUT_EPS;
+      c.dist[i] = root ? 0 : DIST_INF;
+      if (root) c.order[atomicAdd(&s_qn, 1)] = (unsigned short)i;
+    }
+    __syncthreads();
+    int level = 0, begin = 0, end = s_qn;
+    if (tid == 0) c.lstart[0] = 0;
+    bool pending = false;   // an auxiliary node carries the current level and its predecessors are not expanded yet
+    while ((begin < end || pending) && level < depth_cap) {
+      // sites of this level: predecessors over neighbour arcs, and the auxiliary node of the site's label
+      for (int q = begin + tid; q < end; q += THREADS) {
+        const int v = c.order[q];
+        for (int k = 0; k < KN; ++k)
+          if (c.owned[(size_t)v * MAXNB + k]) {
+            const int u = c.nbr[(size_t)v * MAXNB + k];
+            const size_t e = (size_t)v * KN + k;
+            if (c.dist[u] == DIST_INF && c.cr[e] + c.fl[e] > CUT_EPS && atomicCAS(&c.dist[u], DIST_INF, level + 1) == DIST_INF) {
+              c.order[atomicAdd(&s_qn, 1)] = (unsigned short)u;
+              if (c.exc[u] > 0.0) s_any = 1;
+            }
+          }
+        for (int a = c.rev_off[v]; a < c.rev_off[v + 1]; ++a) {
+          const int e0 = c.rev_idx[a];
+          const int u = e0 / MAXNB;
+          const size_t e = (size_t)u * KN + (e0 % MAXNB);
+          if (c.dist[u] == DIST_INF && c.cf[e] - c.fl[e] > CUT_EPS && atomicCAS(&c.dist[u], DIST_INF, level + 1) == DIST_INF) {
+            c.order[atomicAdd(&s_qn, 1)] = (unsigned short)u;
+            if (c.exc[u] > 0.0) s_any = 1;
+          }
+        }
+        const int lv = c.label[v];
+        if (c.cost - c.af[v] > CUT_EPS && s_aexc[lv] >= 0.0) {          // arc aux(lv) -> v has residual capacity
+          const int old = atomicCAS(&s_adist[lv], DIST_INF, level + 1);
+          if (old == DIST_INF || old == level + 1) atomicMin(&s_anext[lv], v);
+        }
+      }
+      __syncthreads();
+      // auxiliary nodes labelled at this level: their predecessors are the sites of that label that hold aux flow
+      for (int l = 0; l < L; ++l)
+        if (s_adist[l] == level + 1) {
+          if (tid == 0 && s_aexc[l] > 0.0) s_any = 1;
+        } else if (s_adist[l] == level) {
+          for (int i = tid; i < N; i += THREADS)
+            if (c.label[i] == l && c.af[i] > CUT_EPS && atomicCAS(&c.dist[i], DIST_INF, level + 1) == DIST_INF) {
+              c.order[atomicAdd(&s_qn, 1)] = (unsigned short)i;
+              if (c.exc[i] > 0.0) s_any = 1;
+            }
+        }
+      __syncthreads();
+      begin = end; end = s_qn; ++level;
+      if (tid == 0) c.lstart[level] = begin;
+      pending = false;
+      for (int l = 0; l < L; ++l) pending |= (s_adist[l] == level);
+      __syncthreads();
+    }
+    // an auxiliary node labelled at the last level still has predecessors to visit: the BFS is exhausted only if none is
+    const bool aux_pending = pending;
+    const bool exhausted = begin >= end && !aux_pending;
+    const int maxlevel = (begin >= end) ? level - 1 : level;
+    if (tid == 0) c.lstart[level + 1] = end;
+    __syncthreads();
+    if (!s_any) {
+      if (exhausted) break;
+      depth_cap *= 4;
+      continue;
+    }
+    const int top = aux_pending ? level : maxlevel;
+    for (int d = top; d >= 1; --d) {
+      const int qb = d <= maxlevel ? c.lstart[d] : 0, qe = d <= maxlevel ? c.lstart[d + 1] : 0;
+      for (int q = qb + tid; q < qe; q += THREADS) {
+        const int i = c.order[q];
+        double ex = c.exc[i];
+        if (!(ex > 0.0)) continue;
+        for (int k = 0; k < KN && ex > 0.0; ++k)
+          if (c.owned[(size_t)i * MAXNB + k]) {
+            const int j = c.nbr[(size_t)i * MAXNB + k];
+            if (c.dist[j] != d - 1) continue;
+            const size_t e = (size_t)i * KN + k;
+            const double res = c.cf[e] - c.fl[e];
+            if (!(res > 0.0)) continue;
+            if (ex >= res) { c.fl[e] = c.cf[e]; atomicAdd(&c.exc[j], res); ex -= res; }
+            else { c.fl[e] += ex; atomicAdd(&c.exc[j], ex); ex = 0.0; }
+          }
+        for (int a = c.rev_off[i]; a < c.rev_off[i + 1] && ex > 0.0; ++a) {
+          const int e0 = c.rev_idx[a];
+          const int x = e0 / MAXNB;
+          if (c.dist[x] != d - 1) continue;
+          const size_t e = (size_t)x * KN + (e0 % MAXNB);
+          const double res = c.cr[e] + c.fl[e];
+          if (!(res > 0.0)) continue;
+          if (ex >= res) { c.fl[e] = -c.cr[e]; atomicAdd(&c.exc[x], res); ex -= res; }
+          else { c.fl[e] -= ex; atomicAdd(&c.exc[x], ex); ex = 0.0; }
+        }
+        const int li = c.label[i];
+        if (ex > 0.0 && s_adist[li] == d - 1 && c.af[i] > 0.0) {        // back along the arc aux -> i
+          const double res = c.af[i];
+          const double amt = ex >= res ? res : ex;
+          c.af[i] = ex >= res ? 0.0 : res - ex;
+          atomicAdd(&s_aexc[li], amt);
+          ex -= amt;
+        }
+        c.exc[i] = ex;
+      }
+      if (tid < L && s_adist[tid] == d && s_aexc[tid] > 0.0 && s_anext[tid] != DIST_INF) {
+        const int j = s_anext[tid];                                    // a site of level d - 1 with residual capacity
+        const double res = c.cost - c.af[j];
+        const double amt = s_aexc[tid] >= res ? res : s_aexc[tid];
+        c.af[j] = s_aexc[tid] >= res ? c.cost : c.af[j] + amt;
+        atomicAdd(&c.exc[j], amt);
+        s_aexc[tid] -= amt;
+      }
+      __syncthreads();
+    }
+  }
+  // ---- new labeling + energy change ----
+  double delta = 0.0;
+  int nchg = 0;
+  for (int i = tid; i < N; i += THREADS) {
+    const int li = c.label[i];
+    const int nl = (li != alpha && c.dist[i] == DIST_INF) ? alpha : li;
+    c.newlab[i] = nl;
+    if (nl != li) { delta += pearl_data_cost(c, i, nl) - pearl_data_cost(c, i, li); ++nchg; }
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += THREADS)
+    for (int k = 0; k < KN; ++k)
+      if (c.owned[(size_t)i * MAXNB + k]) {
+        const int j = c.nbr[(size_t)i * MAXNB + k];
+        const double w = lam * (double)c.mult[(size_t)i * MAXNB + k];
+        delta += w * ((c.newlab[i] != c.newlab[j] ? 1.0 : 0.0) - (c.label[i] != c.label[j] ? 1.0 : 0.0));
+      }
+  if (tid < PEARL_MAX) s_adist[tid] = 0;                                // reuse: label counts of the new labeling
+  __syncthreads();
+  for (int i = tid; i < N; i += THREADS) atomicAdd(&s_adist[c.newlab[i]], 1);
+  if (nchg) s_changed = 1;
+  __syncthreads();
+  double lab_delta = 0.0;
+  if (tid == 0)
+    for (int l = 0; l < L; ++l) lab_delta += c.cost * ((s_adist[l] > 0 ? 1.0 : 0.0) - (s_cnt[l] > 0 ? 1.0 : 0.0));
+  delta = block_sum(delta + lab_delta, red_sh);
+  const bool apply = s_changed && delta < -1e-9;
+  if (apply)
+    for (int i = tid; i < N; i += THREADS) c.label[i] = c.newlab[i];
+  __syncthreads();
+  return apply;
+}
+
+// energy of the current labeling (GCoptimization.cpp:950-986)
+__device__ inline double pearl_energy(const PearlCtx& c, double* red_sh) {
+  __shared__ int s_used[PEARL_MAX];
+  const int tid = threadIdx.x;
+  if (tid < PEARL_MAX) s_used[tid] = 0;
+  __syncthreads();
+  double e = 0.0;
+  for (int i = tid; i < c.N; i += THREADS) {
+    const int li = c.label[i];
+    s_used[li] = 1;
+    e += pearl_data_cost(c, i, li);
+    for (int k = 0; k < c.KN; ++k)
+      if (c.owned[(size_t)i * MAXNB + k] && li != c.label[c.nbr[(size_t)i * MAXNB + k]])
+        e += c.lambda * (double)c.mult[(size_t)i * MAXNB + k];
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int l = 0; l < c.L; ++l) if (s_used[l]) e += c.cost;
+  return block_sum(e, red_sh);
+}
+
+constexpr size_t SMEM_PEARL = (size_t)NMAX * (4 + 4 + 8 + 8 + 4 + 2) + (NMAX + 2) * 4 + 64 + FIT_SCRATCH_DOUBLES * 8 +
+                              (size_t)WARPS * FIT_NRED * 8;
+static_assert(SMEM_PEARL <= SMEM_CUT_DYN, "PEARL shared memory must fit in the fit kernel's allocation");
+
+// PEARL::run (PEARL.h:391-459) on the instances ws.models[0 .. n_models) of problem p.  Labels end in ws.labels.
+__device__ __noinline__ void pearl_run(const Workspace& ws, const epos_fit_params& prm, const MultiParams& mp, int p,
+                                       unsigned char* smem_raw, bool& pts_loaded, bool& have_labels) {
+  __shared__ double red_sh[WARPS + 2];
+  __shared__ int s_count[PEARL_MAX], scan_sh[WARPS + 1], s_flag, s_src[PEARL_MAX];
+  const int tid = threadIdx.x;
+  ProbState* st = ws.st + p;
+  MultiState* ms = ws.ms + p;
+  const int N = st->N;
+  double* models = ws.models + (size_t)p * MAX_INSTANCES * 12;
+  double* prefs = ws.pref + (size_t)p * PEARL_MAX * NMAX;
+  int* glabels = ws.labels + (size_t)p * NMAX;
+  const double* P5 = ws.pts + (size_t)p * 7 * NMAX;
+  PearlCtx c;
+  c.N = N; c.KN = prm.max_neighbors < MAXNB ? prm.max_neighbors : MAXNB;
+  c.T2 = 9.0 / 4.0 * st->thr_n * st->thr_n;                           // PEARL.h:49 (not (1.5 thr)^2)
+  c.lambda = prm.spatial_coherence_weight; c.oml = 1.0 - c.lambda; c.cost = (double)mp.min_point_number;
+  c.r2tab = ws.r2tab + (size_t)p * PEARL_MAX * NMAX;
+  c.nbr = ws.nbr + (size_t)p * NMAX * MAXNB; c.owned = ws.owned + (size_t)p * NMAX * MAXNB;
+  c.mult = ws.mult + (size_t)p * NMAX * MAXNB;
+  c.rev_off = ws.rev_off + (size_t)p * (NMAX + 1); c.rev_idx = ws.rev_idx + (size_t)p * NMAX * MAXNB;
+  c.cf = ws.capf + (size_t)p * NMAX * MAXNB; c.cr = ws.cr + (size_t)p * NMAX * MAXNB; c.fl = ws.flow + (size_t)p * NMAX * MAXNB;
+  // shared-memory carve-up (the point set is evicted; fits below read the points from the L2-resident workspace)
+  unsigned char* sm = smem_raw;
+  c.label = reinterpret_cast<int*>(sm); sm += NMAX * 4;
+  c.newlab = reinterpret_cast<int*>(sm); sm += NMAX * 4;
+  c.exc = reinterpret_cast<double*>(sm); sm += NMAX * 8;
+  c.af = reinterpret_cast<double*>(sm); sm += NMAX * 8;
+  c.dist = reinterpret_cast<int*>(sm); sm += NMAX * 4;
+  c.lstart = reinterpret_cast<int*>(sm); sm += (NMAX + 2) * 4;
+  c.order = reinterpret_cast<unsigned short*>(sm); sm += NMAX * 2;
+  sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sm) + 15) & ~(uintptr_t)15);
+  double* fit_sh = reinterpret_cast<double*>(sm); sm += FIT_SCRATCH_DOUBLES * 8;
+  double* part = reinterpret_cast<double*>(sm); sm += WARPS * FIT_NRED * 8;
+  pts_loaded = false;
+  CtaGroup g;
+  g.rank = tid; g.size = THREADS; g.sh = fit_sh; g.part = part;
+  unsigned short* list = ws.lists + (size_t)p * NMAX;
+  int iteration = 0;
+  double energy = 0.0, previous_energy = -1.0;
+  bool rejected = false, converged = false;
+  __syncthreads();
+  while (!converged && iteration++ < 50) {
+    const bool init_prev = iteration > 1 && !rejected;
+    int M = ms->n_models;
+    __syncthreads();
+    if (M > 0) {                                                      // labeling(), PEARL.h:461-536
+      c.L = M + 1;
+      double* r2 = const_cast<double*>(c.r2tab);
+      for (int i = tid; i < N; i += THREADS)
+        for (int l = 0; l < M; ++l)
+          r2[(size_t)l * NMAX + i] = sq_residual(P5[i], P5[NMAX + i], P5[2 * NMAX + i], P5[3 * NMAX + i], P5[4 * NMAX + i],
+                                                 models + 12 * l);
+      for (int i = tid; i < N; i += THREADS) c.label[i] = (init_prev && have_labels) ? glabels[i] : 0;
+      __syncthreads();
+      for (int cycle = 1; cycle <= 1000; ++cycle) {                   // GCoptimization.cpp:1063-1075, standard cycles
+        bool any = false;
+        for (int a = 0; a < c.L; ++a) {
+          any |= pearl_expansion_move(c, a, red_sh);
+          if (tid == 0) ++ms->moves;
+        }
+        if (!any) break;
+      }
+      energy = pearl_energy(c, red_sh);
+      for (int i = tid; i < N; i += THREADS) glabels[i] = c.label[i];
+      have_labels = true;
+      __syncthreads();
+    }
+    bool changed = false;
+    rejected = false;
+    M = ms->n_models;
+    if (have_labels) {                                                // parameterEstimation, PEARL.h:313-389
+      if (tid < PEARL_MAX) s_count[tid] = 0;
+      __syncthreads();
+      for (int k = 0; k < M; ++k) {
+        // ordered member list of instance k
+        int cnt = 0;
+        const int per = PER_THREAD;
+        for (int q = 0; q < per; ++q) { const int i = tid * per + q; cnt += (i < N && glabels[i] == k); }
+        int total;
+        int base = block_excl_scan<WARPS>(cnt, scan_sh, &total);
+        for (int q = 0; q < per; ++q) { const int i = tid * per + q; if (i < N && glabels[i] == k) list[base++] = (unsigned short)i; }
+        if (tid == 0) s_count[k] = total;
+        __syncthreads();
+        if (total < 3) continue;
+        double before = 0.0;
+        for (int q = tid; q < total; q += THREADS) {
+          const int i = list[q];
+          before += sqrt(sq_residual(P5[i], P5[NMAX + i], P5[2 * NMAX + i], P5[3 * NMAX + i], P5[4 * NMAX + i], models + 12 * k));
+        }
+        before = block_sum(before, red_sh);
+        PointView v;
+        v.un = P5; v.vn = P5 + NMAX; v.x = P5 + 2 * NMAX; v.y = P5 + 3 * NMAX; v.z = P5 + 4 * NMAX; v.idx = list; v.n = total;
+        double m2[12];
+        const bool ok = fit_nonminimal_group(g, v, m2);
+        __syncthreads();
+        if (!ok) continue;
+        double after = 0.0;
+        for (int q = tid; q < total; q += THREADS) {
+          const int i = list[q];
+          after += sqrt(sq_residual(P5[i], P5[NMAX + i], P5[2 * NMAX + i], P5[3 * NMAX + i], P5[4 * NMAX + i], m2));
+        }
+        after = block_sum(after, red_sh);
+        if (after < before) {
+          __syncthreads();
+          if (tid < 12) models[12 * k + tid] = m2[tid];
+          changed = true;
+          __syncthreads();
+        }
+      }
+      // outliers of this labeling (before rejections)
+      int oc = 0;
+      for (int i = tid; i < N; i += THREADS) oc += glabels[i] >= M;
+      oc = (int)(block_sum((double)oc, red_sh) + 0.5);
+      // rejectInstances, PEARL.h:271-311 (last to first; removed instances hand their points to the outliers)
+      if (tid == 0) {
+        int nm = 0;
+        for (int k = 0; k < M; ++k) {
+          if (s_count[k] < mp.min_point_number) oc += s_count[k]; else s_src[nm++] = k;
+        }
+        s_flag = nm;
+        ms->n_models = nm;
+        ms->n_outliers = oc;
+      }
+      __syncthreads();
+      const int nm = s_flag;
+      rejected = nm != M;
+      if (rejected)
+        for (int q = 0; q < nm; ++q) {                                // survivors move down in order (src >= q)
+          const int src = s_src[q];
+          if (src != q) {
+            if (tid < 12) models[12 * q + tid] = models[12 * src + tid];
+            for (int i = tid; i < N; i += THREADS) prefs[(size_t)q * NMAX + i] = prefs[(size_t)src * NMAX + i];
+          }
+          __syncthreads();
+        }
+      __syncthreads();
+    }
+    if (!rejected && !changed && fabs(energy - previous_energy) < 1e-5 && iteration > 1) converged = true;
+    previous_energy = energy;
+  }
+  if (tid == 0) ms->pearl_iterations += iteration > 50 ? 50 : iteration;
+  __syncthreads();
+}
+
+// thread 0: state of a fresh GC-RANSAC run (proposal `it`) on problem p
+__device__ inline void proposal_reset(ProbState* st, int it, const double* cpref) {
+  st->phase = PH_MAIN; st->iter = 0; st->pass = 0; st->best_value = 0.0; st->best_inl = 0; st->coverage = 0.0;
+  st->lo_runs = 0; st->gc_count = 0; st->lo_final = 0; st->lo_stage = 0; st->ni = 0; st->found = 0;
+  st->lo_value = 0.0; st->lo_inl = 0; st->chunk_base = 0; st->chunk_n = 0; st->n_final = 0;
+  st->max_iteration = ~0ULL;
+  for (int i = 0; i < 12; ++i) { st->best_model[i] = 0.0; st->lo_model[i] = 0.0; }
+  st->cpref = cpref; st->stream_base = 2ULL * (unsigned long long)it; st->multi = 1;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+progx_kernel(Workspace ws, epos_fit_params prm, MultiParams mp, const int* __restrict__ offsets,
+             const int* __restrict__ max_models, double* __restrict__ poses, int* __restrict__ labeling,
+             double* __restrict__ multi_poses, double* __restrict__ multi_scores, int* __restrict__ multi_counts) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ double red_sh[WARPS + 2];
+  __shared__ int s_stop;
+  const int p = blockIdx.x, tid = threadIdx.x;
+  ProbState* st = ws.st + p;
+  MultiState* ms = ws.ms + p;
+  const int N = st->N, off = offsets[p];
+  const int max_model_number = max_models[p];
+  double* models = ws.models + (size_t)p * MAX_INSTANCES * 12;
+  double* prefs = ws.pref + (size_t)p * PEARL_MAX * NMAX;
+  double* compound = ws.compound + (size_t)p * NMAX;
+  int* glabels = ws.labels + (size_t)p * NMAX;
+  const double* P5 = ws.pts + (size_t)p * 7 * NMAX;
+  double* out_poses = multi_poses + (size_t)p * MAX_INSTANCES * 12;
+  double* out_scores = multi_scores + (size_t)p * MAX_INSTANCES;
+  if (tid == 0) {
+    ms->total_iterations = 0; ms->n_models = 0; ms->unaccepted = 0; ms->first_events = 0; ms->n_outliers = 0;
+    ms->proposals = 0; ms->accepted = 0; ms->pearl_iterations = 0; ms->moves = 0; ms->done = 0;
+    ms->max_models = max_model_number; ms->sped_up = 0;
+    multi_counts[p] = 0;
+  }
+  for (int i = tid; i < N; i += THREADS) { compound[i] = 0.0; labeling[off + i] = 0; }
+  // multiplicity of the owned neighbour pairs: PEARL enters a pair once per LISTING (PEARL.h:517-520)
+  {
+    const short* nbr = ws.nbr + (size_t)p * NMAX * MAXNB;
+    const unsigned char* owned = ws.owned + (size_t)p * NMAX * MAXNB;
+    unsigned char* mult = ws.mult + (size_t)p * NMAX * MAXNB;
+    for (int i = tid; i < N; i += THREADS)
+      for (int k = 0; k < MAXNB; ++k) {
+        unsigned char m = 0;
+        if (owned[(size_t)i * MAXNB + k]) {
+          const int j = nbr[(size_t)i * MAXNB + k];
+          m = 1;
+          for (int q = 0; q < MAXNB; ++q) m += (nbr[(size_t)j * MAXNB + q] == i) ? 1 : 0;
+        }
+        mult[(size_t)i * MAXNB + k] = m;
+      }
+  }
+  __syncthreads();
+  if (!st->valid || st->phase == PH_DONE) return;                      // fewer than 6 correspondences, singular K, ...
+  if (max_model_number < 2 || max_model_number > mp.max_model_number_for_pearl) {
+    if (tid == 0) multi_counts[p] = -1;                                // not a PEARL-mode problem: rejected
+    return;
+  }
+  const double T2 = 9.0 / 4.0 * st->thr_n * st->thr_n;                 // progressive_x.h:679
+  bool pts_loaded = false, have_labels = false;
+  for (int it = 0; it <= 100; ++it) {                                  // progressive_x.h:427-437
+    __syncthreads();
+    if (tid == 0) { proposal_reset(st, it, ms->n_models > 0 ? compound : nullptr); ++ms->proposals; }
+    __syncthreads();
+    run_state_machine(ws, prm, p, smem_raw, pts_loaded);
+    phase_final(ws, prm, p, smem_raw, pts_loaded, offsets, poses, labeling);
+    __syncthreads();
+    if (!st->found) continue;
+    const int nin = st->n_final;
+    if (tid == 0) ms->total_iterations += (long long)st->iter;
+    // ---- isPutativeModelValid (progressive_x.h:723-749) ----
+    bool valid = nin >= (3 > mp.min_point_number ? 3 : mp.min_point_number);
+    const int slot = ms->n_models;                                     // where the proposal goes if accepted
+    __syncthreads();
+    if (valid) {
+      const double* fm = ws.fin_model + (size_t)p * 12;
+      double dot = 0.0, na = 0.0, nc = 0.0;
+      for (int i = tid; i < N; i += THREADS) {
+        double v = 1.0 - sq_residual(P5[i], P5[NMAX + i], P5[2 * NMAX + i], P5[3 * NMAX + i], P5[4 * NMAX + i], fm) / T2;
+        if (!(v > 0.0)) v = 0.0;
+        prefs[(size_t)slot * NMAX + i] = v;
+        const double cc = compound[i];
+        dot += v * cc; na += v * v; nc += cc * cc;
+      }
+      dot = block_sum(dot, red_sh); na = block_sum(na, red_sh); nc = block_sum(nc, red_sh);
+      const double tanimoto = dot / (na + nc - dot);
+      if (mp.max_tanimoto < tanimoto) valid = false;
+    }
+    if (!valid) {
+      if (tid == 0) { ++ms->unaccepted; s_stop = ms->unaccepted == 10; }
+      __syncthreads();
+      if (s_stop) break;
+      continue;
+    }
+    // ---- accept: compound instance optimisation (progressive_x.h:505-547) ----
+    if (tid < 12) models[12 * slot + tid] = ws.fin_model[(size_t)p * 12 + tid];
+    if (tid == 0) { ms->n_models = slot + 1; ++ms->accepted; }
+    __syncthreads();
+    if (slot == 0) {
+      const unsigned short* fi = ws.fin_inl + (size_t)p * NMAX;
+      for (int i = tid; i < N; i += THREADS) glabels[i] = 1;
+      __syncthreads();
+      for (int i = tid; i < nin; i += THREADS) glabels[fi[i]] = 0;
+      if (tid == 0) ++ms->first_events;
+      have_labels = false;                 // PEARL's own engine does not exist yet (labels above are ProgressiveX's)
+      __syncthreads();
+    } else {
+      pearl_run(ws, prm, mp, p, smem_raw, pts_loaded, have_labels);
+    }
+    // ---- updateCompoundModel (progressive_x.h:755-794) ----
+    const int M = ms->n_models;
+    __syncthreads();
+    if (M > 0) {
+      for (int i = tid; i < N; i += THREADS) {
+        double mx = 0.0;
+        for (int k = 0; k < M; ++k) mx = fmax(mx, prefs[(size_t)k * NMAX + i]);
+        compound[i] = mx;
+      }
+      for (int k = 0; k < M; ++k) {
+        double sc = 0.0;
+        for (int i = tid; i < N; i += THREADS) sc += prefs[(size_t)k * NMAX + i];
+        sc = block_sum(sc, red_sh);
+        if (tid == 0) ms->scores[k] = sc;
+      }
+    }
+    // ---- termination (progressive_x.h:589-615, 651-673) ----
+    if (tid == 0) {
+      const long long covered = M == 1 ? (long long)ms->first_events : (long long)N - (long long)ms->n_outliers;
+      const double ratio = pow(1.0 - pow(1.0 - mp.confidence, 1.0 / (double)ms->total_iterations), 1.0 / 3.0);
+      const long long unseen = llround((double)((long long)N - covered) * ratio);
+      s_stop = (unseen < (long long)mp.min_point_number) || (M >= max_model_number);
+    }
+    __syncthreads();
+    if (s_stop) break;
+  }
+  __syncthreads();
+  // ---- outputs ----
+  const int M = ms->n_models;
+  for (int i = tid; i < 12 * M; i += THREADS) out_poses[i] = models[i];
+  for (int i = tid; i < M; i += THREADS) out_scores[i] = ms->scores[i];
+  if (ms->accepted > 0)
+    for (int i = tid; i < N; i += THREADS) labeling[off + i] = glabels[i];
+  if (tid == 0) {
+    multi_counts[p] = M;
+    ms->done = 1;
+    double* rec = poses + (size_t)p * EPOS_POSE_RECORD_DOUBLES;      // record = first instance (valid = number of instances)
+    for (int i = 0; i < 12; ++i) rec[i] = M > 0 ? models[i] : 0.0;
+    int n0 = 0;
+    if (M > 0) for (int i = 0; i < N; ++i) n0 += glabels[i] == 0;
+    rec[12] = (double)n0; rec[13] = (double)ms->total_iterations; rec[14] = (double)M; rec[15] = (double)ms->proposals;
+  }
 }
 
 // One persistent CTA per problem runs the whole state machine; phases re-carve the dynamic shared memory
@@ -1113,7 +1825,7 @@ fit_kernel(Workspace ws, epos_fit_params prm, const int* __restrict__ offsets, d
 
 constexpr size_t SMEM_POINTS = 5 * NMAX * 8 + NMAX * 2;
 constexpr size_t SMEM_PREP = 5 * NMAX * 4 + 8192 * 8 + 64 * 4 + 8192 * 2 + 64;
-static_assert(sizeof(PassRecord) <= 432 && CHUNK == 80, "workspace_layout reserves 80 x 432 bytes of pass records");
+static_assert(sizeof(PassRecord) <= 464 && CHUNK == 80, "workspace_layout reserves 80 x 464 bytes of pass records");
 constexpr size_t SMEM_MAIN = SMEM_POINTS + WARPS * (NMAX / 32) * 4 + 12 * 8 + 64;
 constexpr size_t SMEM_CUT = SMEM_CUT_DYN;
 static_assert(FIT_SCRATCH_DOUBLES * 8 >= (NMAX / 32) * 4, "bitset must fit in the fit scratch");
@@ -1191,6 +1903,7 @@ static int set_smem_attrs() {
   if (done[dslot].load(std::memory_order_acquire)) return EPOS_OK;
   EPOS_CUDA(cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PREP));
   EPOS_CUDA(cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FIT));
+  EPOS_CUDA(cudaFuncSetAttribute(progx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FIT));
   done[dslot].store(1, std::memory_order_release);
   return EPOS_OK;
 }
@@ -1212,6 +1925,68 @@ int epos_fit_last_kernel_ms(float* prep_ms, float* fit_ms) {
   EPOS_CUDA(cudaEventSynchronize(g_fit_ev[2]));
   EPOS_CUDA(cudaEventElapsedTime(prep_ms, g_fit_ev[0], g_fit_ev[1]));
   EPOS_CUDA(cudaEventElapsedTime(fit_ms, g_fit_ev[1], g_fit_ev[2]));
+  return EPOS_OK;
+}
+
+size_t epos_fit_multi_workspace_bytes(int P) {
+  if (P <= 0) return 0;
+  return workspace_layout(P, nullptr, nullptr, true);
+}
+
+int epos_fit_max_instances(void) { return MAX_INSTANCES; }
+
+int epos_fit_poses_multi(const double* coord_2d, const double* coord_3d, const int32_t* offsets, const int32_t* counts, int P,
+                         const double* K, const uint64_t* seeds, const epos_fit_params* params,
+                         const epos_multi_params* mparams, const int32_t* max_models, double* poses, int32_t* labeling,
+                         double* multi_poses, double* multi_scores, int32_t* multi_counts, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  EPOS_CHECK_ARG(coord_2d && coord_3d && offsets && counts && K && seeds && params && mparams && max_models && poses &&
+                 labeling && multi_poses && multi_scores && multi_counts && workspace);
+  EPOS_CHECK_ARG(P > 0);
+  EPOS_CHECK_ARG(params->max_neighbors >= 0 && params->max_neighbors <= MAXNB);
+  EPOS_CHECK_ARG(params->max_lo_trials >= 0 && params->max_lo_trials <= MAX_TRIALS);
+  EPOS_CHECK_ARG(params->max_graph_cuts >= 1 && params->max_graph_cuts <= 64);
+  EPOS_CHECK_ARG(params->spatial_coherence_weight > 0.0);
+  EPOS_CHECK_ARG(mparams->max_model_number_for_pearl >= 2 && mparams->max_model_number_for_pearl < PEARL_MAX);
+  EPOS_CHECK_ARG(mparams->min_point_number >= 1 && mparams->confidence > 0.0 && mparams->confidence < 1.0);
+  EPOS_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0);
+  if (workspace_bytes < workspace_layout(P, nullptr, nullptr, true)) {
+    set_error("epos_fit_poses_multi: workspace too small (%zu < %zu)", workspace_bytes, workspace_layout(P, nullptr, nullptr, true));
+    return EPOS_ERR_INVALID_ARG;
+  }
+  int rc = set_smem_attrs();
+  if (rc) return rc;
+  Workspace ws;
+  workspace_layout(P, workspace, &ws, true);
+  cudaStream_t s = (cudaStream_t)stream;
+  MultiParams mp;
+  mp.max_model_number_for_pearl = mparams->max_model_number_for_pearl; mp.min_point_number = mparams->min_point_number;
+  mp.confidence = mparams->confidence; mp.max_tanimoto = mparams->max_tanimoto_similarity;
+  prep_kernel<<<P, PT, SMEM_PREP, s>>>(ws, coord_2d, coord_3d, offsets, counts, K,
+                                            reinterpret_cast<const unsigned long long*>(seeds), *params, labeling, poses);
+  EPOS_LAUNCH_CHECK();
+  progx_kernel<<<P, THREADS, SMEM_FIT, s>>>(ws, *params, mp, offsets, max_models, poses, labeling, multi_poses, multi_scores,
+                                            multi_counts);
+  EPOS_LAUNCH_CHECK();
+  return EPOS_OK;
+}
+
+// host copy of the per-problem Progressive-X counters of the last epos_fit_poses_multi (synchronous):
+// out [P][8] i64: proposals, accepted, total RANSAC iterations, PEARL iterations, expansion moves, instances, unaccepted, 0
+int epos_fit_multi_debug_state(const void* workspace, int P, long long* out) {
+  EPOS_CHECK_ARG(workspace && out && P > 0);
+  Workspace ws;
+  workspace_layout(P, const_cast<void*>(workspace), &ws, true);
+  MultiState* h = (MultiState*)malloc((size_t)P * sizeof(MultiState));
+  if (!h) return EPOS_ERR_CUDA;
+  cudaError_t e = cudaMemcpy(h, ws.ms, (size_t)P * sizeof(MultiState), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { free(h); set_error("epos_fit_multi_debug_state: %s", cudaGetErrorString(e)); return EPOS_ERR_CUDA; }
+  for (int i = 0; i < P; ++i) {
+    long long* o = out + (size_t)i * 8;
+    o[0] = h[i].proposals; o[1] = h[i].accepted; o[2] = h[i].total_iterations; o[3] = h[i].pearl_iterations;
+    o[4] = h[i].moves; o[5] = h[i].n_models; o[6] = h[i].unaccepted; o[7] = 0;
+  }
+  free(h);
   return EPOS_OK;
 }
 

@@ -62,6 +62,49 @@ class PoseFitter:
         return float((d[:, 0] * (d[:, 16] + d[:, 17] + d[:, 18])).sum()) * 48.0
 
 
+def multi_params(max_model_number_for_pearl=5, min_point_number=6, confidence=0.5, max_tanimoto_similarity=0.9):
+    return _lib.MultiParams(int(max_model_number_for_pearl), int(min_point_number), float(confidence),
+                            float(max_tanimoto_similarity))
+
+
+class MultiPoseFitter:
+    """P independent multi-instance (Progressive-X + PEARL) problems per call, one persistent CTA each
+    (epos_fit_poses_multi).  max_models [P]: the instance bound of each problem, 2 .. max_model_number_for_pearl."""
+
+    def __init__(self, device, max_problems, params=None, mparams=None):
+        self.lib = _lib.lib()
+        self.dev = torch.device(device)
+        self.params = params or default_params()
+        self.mparams = mparams or multi_params()
+        self.P = max_problems
+        self.MAXI = self.lib.epos_fit_max_instances()
+        nbytes = self.lib.epos_fit_multi_workspace_bytes(max_problems)
+        self.workspace = torch.empty((nbytes + 256,), dtype=torch.uint8, device=self.dev)
+        self._ws_ptr = (self.workspace.data_ptr() + 255) // 256 * 256
+
+    def fit(self, coord_2d, coord_3d, offsets, counts, K, seeds, max_models):
+        """Device tensors as PoseFitter.fit + max_models [P] i32.  Returns (records [P,16], labeling [R] i32,
+        multi_poses [P,MAXI,12], multi_scores [P,MAXI], multi_counts [P] i32)."""
+        P = offsets.numel()
+        assert P <= self.P and max_models.numel() == P and max_models.dtype == torch.int32
+        poses = torch.zeros((P, 16), dtype=torch.float64, device=self.dev)
+        labeling = torch.zeros((coord_2d.shape[0],), dtype=torch.int32, device=self.dev)
+        mposes = torch.zeros((P, self.MAXI, 12), dtype=torch.float64, device=self.dev)
+        mscores = torch.zeros((P, self.MAXI), dtype=torch.float64, device=self.dev)
+        mcounts = torch.zeros((P,), dtype=torch.int32, device=self.dev)
+        _lib.check(self.lib.epos_fit_poses_multi(
+            coord_2d.data_ptr(), coord_3d.data_ptr(), offsets.data_ptr(), counts.data_ptr(), P, K.data_ptr(),
+            seeds.data_ptr(), C.byref(self.params), C.byref(self.mparams), max_models.data_ptr(), poses.data_ptr(),
+            labeling.data_ptr(), mposes.data_ptr(), mscores.data_ptr(), mcounts.data_ptr(), self._ws_ptr,
+            self.workspace.numel() - 256, _lib.stream_ptr()), 'epos_fit_poses_multi')
+        return poses, labeling, mposes, mscores, mcounts
+
+    def debug_state(self, P):
+        out = np.zeros((P, 8), np.int64)
+        _lib.check(self.lib.epos_fit_multi_debug_state(self._ws_ptr, P, out.ctypes.data), 'epos_fit_multi_debug_state')
+        return out
+
+
 class BatchFitter:
     """model.predict outputs -> correspondences -> poses for a whole batch: [B, J, 16] pose records on the device
     (record layout: include/epos_b200.h EPOS_POSE_RECORD_DOUBLES)."""
@@ -144,8 +187,9 @@ def find6DPoses(x1y1, x2y2z2, K, threshold=4.0, max_model_number=-1, conf=0.5, p
                 apply_numerical_optimization=True, log=False, seed=0, device='cuda:0', max_neighbors=5):
     """Same name / keyword arguments / return triple as pyprogressivex.find6DPoses (bindings.cpp:9-28,117,133-152):
     (poses [3M,4] f64, labeling [N] i32, scores [M] f64) as numpy arrays.  Errors: ValueError for malformed shapes
-    (bindings.cpp:30-58).  Only max_model_number == 1 (plain GC-RANSAC) is built; `seed` selects the RANSAC stream
-    (the reference seeds from std::random_device)."""
+    (bindings.cpp:30-58).  max_model_number == 1: GC-RANSAC + final LM; 2 .. max_model_number_for_optimization:
+    Progressive-X with PEARL (one pose per instance, labeling = instance index, scores = instance support).  `seed`
+    selects the RANSAC stream (the reference seeds from std::random_device)."""
     x1y1 = np.ascontiguousarray(x1y1, np.float64)
     x2y2z2 = np.ascontiguousarray(x2y2z2, np.float64)
     K = np.ascontiguousarray(K, np.float64)
@@ -156,11 +200,38 @@ def find6DPoses(x1y1, x2y2z2, K, threshold=4.0, max_model_number=-1, conf=0.5, p
         raise ValueError('x2y2z2 should be an array with dims [n,3], n>=3, same n as x1y1')
     if K.shape != (3, 3):
         raise ValueError('K should be an array with dims [3,3]')
-    if max_model_number != 1:
-        raise NotImplementedError('multi-instance Progressive-X is not built yet (SURVEY.md 8f rank 2)')
     if proposal_engine_conf != 1.0:
         raise NotImplementedError('proposal_engine_conf must be 1.0 (scripts/infer.py:90)')
     dev = torch.device(device)
+    if max_model_number != 1:
+        # Progressive-X (progressivex_python.cpp:136-221).  PEARL mode: 2 .. max_model_number_for_optimization instances.
+        if max_model_number == 0 or max_model_number < -1:
+            raise ValueError('max_model_number should be -1 or positive')
+        if max_model_number == -1 or max_model_number > max_model_number_for_optimization:
+            raise NotImplementedError('sequential propose-and-remove fitting (max_model_number = -1 or > '
+                                      'max_model_number_for_optimization, progressive_x.h:265-391) is not built on the device')
+        if max_model_number_for_optimization > 5:
+            raise ValueError('max_model_number_for_optimization must be <= 5 (infer.py max_model_number_for_pearl default)')
+        if n > _lib.lib().epos_fit_max_points():
+            raise ValueError('more than %d correspondences' % _lib.lib().epos_fit_max_points())
+        p = default_params(threshold=threshold, spatial_coherence_weight=spatial_coherence_weight,
+                           neighborhood_ball_radius=neighborhood_ball_radius,
+                           scaling_from_millimeters=scaling_from_millimeters, min_triangle_area=min_triangle_area,
+                           min_coverage=min_coverage, max_iters=max_iters, max_neighbors=max_neighbors,
+                           apply_numerical_optimization=0)
+        mp = multi_params(max_model_number_for_optimization, min_point_number, conf, max_tanimoto_similarity)
+        f = MultiPoseFitter(dev, 1, p, mp)
+        rec, lab, mposes, mscores, mcounts = f.fit(
+            torch.from_numpy(x1y1).to(dev), torch.from_numpy(x2y2z2).to(dev), torch.zeros(1, dtype=torch.int32, device=dev),
+            torch.tensor([n], dtype=torch.int32, device=dev), torch.from_numpy(K.reshape(1, 3, 3)).to(dev),
+            torch.tensor([seed], dtype=torch.int64, device=dev), torch.tensor([max_model_number], dtype=torch.int32, device=dev))
+        m = int(mcounts.cpu().numpy()[0])
+        if m < 0:
+            raise RuntimeError('epos_fit_poses_multi rejected max_model_number=%d' % max_model_number)
+        find6DPoses.last_record = rec.cpu().numpy()[0]
+        find6DPoses.last_multi_state = f.debug_state(1)[0]
+        return (mposes.cpu().numpy()[0, :m].reshape(3 * m, 4).copy(), lab.cpu().numpy().astype(np.int32),
+                mscores.cpu().numpy()[0, :m].copy())
     p = default_params(threshold=threshold, spatial_coherence_weight=spatial_coherence_weight,
                        neighborhood_ball_radius=neighborhood_ball_radius,
                        scaling_from_millimeters=scaling_from_millimeters, min_triangle_area=min_triangle_area,

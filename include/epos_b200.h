@@ -233,6 +233,37 @@ int epos_fit_max_points(void);
 #define EPOS_FIT_DEBUG_COLS 20
 int epos_fit_debug_state(const void* workspace, int P, long long* out);
 
+/* ---- multi-instance fitting: the Progressive-X branch of find6DPoses (max_model_number in 2 ..
+ * max_model_number_for_optimization; progressivex_python.cpp:136-221, progressive_x.h:397-649, PEARL.h:391-536) for P
+ * independent problems, one persistent CTA each: proposal (GC-RANSAC with the compound-model score,
+ * scoring_function_with_compound_model.h:127-266) -> Tanimoto validation -> PEARL (alpha-expansion with label costs,
+ * refits, rejections) -> compound update -> unseen-inlier termination. -------------------------------------------- */
+typedef struct {
+  int32_t max_model_number_for_pearl;   /* maximum_model_number_to_optimize (infer.py max_model_number_for_pearl, 5; <= 5) */
+  int32_t min_point_number;             /* 6: minimum inliers of an instance and PEARL's label cost (infer.py:486) */
+  double confidence;                    /* conf = required_progx_confidence (0.5) */
+  double max_tanimoto_similarity;       /* 0.9 */
+} epos_multi_params;
+
+/* Inputs as epos_fit_poses plus max_models [P] i32 (device): the instance bound of each problem (2 .. max_model_number_for_pearl).
+ * Outputs: multi_counts [P] (instances found; -1 = max_models outside the supported range), multi_poses
+ * [P][epos_fit_max_instances()][12] row-major [R|t] per instance (no final LM in this branch, as in the reference),
+ * multi_scores [P][epos_fit_max_instances()] (sum of the instance's preferences, progressive_x.h:781-790), labeling
+ * (instance index per correspondence; outliers = number of instances; with one instance 0 = inlier, 1 = outlier),
+ * poses [P][16] = first instance + (points of instance 0, total RANSAC iterations, instances, proposals). */
+int epos_fit_poses_multi(const double* coord_2d, const double* coord_3d,
+                         const int32_t* offsets, const int32_t* counts, int P,
+                         const double* K, const uint64_t* seeds, const epos_fit_params* params,
+                         const epos_multi_params* mparams, const int32_t* max_models,
+                         double* poses, int32_t* labeling,
+                         double* multi_poses, double* multi_scores, int32_t* multi_counts,
+                         void* workspace, size_t workspace_bytes, void* stream);
+size_t epos_fit_multi_workspace_bytes(int P);
+int epos_fit_max_instances(void);
+/* Profiling aid (synchronous): out [P][8] i64 = proposals, accepted, RANSAC iterations, PEARL iterations, expansion
+ * moves, instances, rejected proposals, 0. */
+int epos_fit_multi_debug_state(const void* workspace, int P, long long* out);
+
 /* Debugging aid (synchronous): local-optimisation rounds of problem p of the last epos_fit_poses.
  * out [16][72] i32: graph-cut number, labelled inliers, updated, LO value, LO inliers, then (ok, inliers, pixels) of
  * the 20 inner fits (ok = -1: not evaluated). */

@@ -396,3 +396,93 @@ def test_pipelined_engine_equals_serial_engine():
     # run_host sees batches 4..7 of each engine's seed stream: same keys in both engines
     for a, b in zip(res[(False, 'host')], res[(True, 'host')]):
         assert np.array_equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------------
+# multi-instance fitting (Progressive-X + PEARL)
+def _multi_both(x2d, x3d, K, seed, mm, **kw):
+    from epos_b200 import posefit
+    from oracle import posefit as opf
+    gp, gl, gs = posefit.find6DPoses(x2d, x3d, K, max_model_number=mm, max_model_number_for_optimization=5, seed=seed, **kw)
+    state = posefit.find6DPoses.last_multi_state.copy()
+    op, ol, os_, st = opf.find6DPoses(x2d, x3d, K, max_model_number=mm, max_model_number_for_optimization=5, seed=seed,
+                                      return_stats=True, **kw)
+    return gp, gl, gs, state, op, ol, os_, st
+
+
+def _assert_same_multi(gp, gl, gs, state, op, ol, os_, st, tol=1e-4):
+    """Same instances (count, order), same labeling, poses within 1e-4 (relative for t), same number of proposals and
+    RANSAC iterations.  PEARL iteration counts may differ by the refits that change a converged model in the last bits."""
+    assert gp.shape == op.shape, (gp.shape, op.shape, state, st)
+    assert int(state[0]) == st['proposals'] and int(state[1]) == st['accepted'] and int(state[2]) == st['ransac_iterations'], (state, st)
+    assert np.array_equal(gl, ol), (int((gl != ol).sum()), np.bincount(gl).tolist(), np.bincount(ol).tolist())
+    for k in range(op.shape[0] // 3):
+        a, b = gp[3 * k:3 * k + 3], op[3 * k:3 * k + 3]
+        assert np.abs(a[:, :3] - b[:, :3]).max() < tol, (k, np.abs(a - b).max())
+        assert np.linalg.norm(a[:, 3] - b[:, 3]) < tol * max(1.0, np.linalg.norm(b[:, 3]))
+    np.testing.assert_allclose(gs, os_, rtol=1e-6, atol=1e-6)
+
+
+def _two_instance_scene(rng, n_per=350, n_out=250, noise=0.8):
+    from epos_b200 import synthetic
+    K = synthetic.default_K()
+    pts = []
+    poses = []
+    for _ in range(2):
+        rv = rng.normal(size=3)
+        rv *= rng.uniform(0.3, 2.5) / np.linalg.norm(rv)
+        R = synthetic.rodrigues(rv)
+        t = np.array([rng.uniform(-150, 150), rng.uniform(-100, 100), rng.uniform(600, 1100)])
+        X = rng.normal(size=(n_per, 3))
+        X *= 100.0 / np.linalg.norm(X, axis=1, keepdims=True)
+        Xc = X @ R.T + t
+        front = (Xc - t)[:, 2] < 0                                    # visible half of the sphere
+        X, Xc = X[front], Xc[front]
+        uv = (Xc[:, :2] / Xc[:, 2:3]) * np.array([K[0, 0], K[1, 1]]) + np.array([K[0, 2], K[1, 2]])
+        uv = 4.0 * (np.floor(uv / 4.0) + 0.5) + rng.normal(0, noise, uv.shape) * 0     # pixel-centre grid like corresp.py
+        pts.append(np.concatenate([uv + rng.normal(0, noise, uv.shape), X], 1))
+        poses.append((R, t))
+    out = np.concatenate([4.0 * (rng.integers(0, 160, (n_out, 2)) + 0.5), rng.uniform(-100, 100, (n_out, 3))], 1)
+    allp = np.concatenate(pts + [out])
+    return allp[rng.permutation(len(allp))], K, poses
+
+
+def test_multi_instance_tless_fixture_matches_oracle():
+    g = json.load(open(os.path.join(GOLDEN, 'tless.json')))
+    c, K = np.array(g['corrs']), np.array(g['K'])
+    for mm, seeds in ((2, (0, 1)), (3, (0,))):
+        for seed in seeds:
+            out = _multi_both(c[:, :2], c[:, 2:], K, seed, mm, threshold=4.0, min_triangle_area=0.0)
+            assert out[4].shape[0] == 3 * mm
+            _assert_same_multi(*out)
+
+
+def test_multi_instance_planted_scenes_match_oracle_and_ground_truth():
+    rng = np.random.default_rng(5)
+    for trial in range(3):
+        pts, K, poses = _two_instance_scene(rng)
+        out = _multi_both(pts[:, :2], pts[:, 2:], K, 10 + trial, 2, threshold=4.0, min_triangle_area=0.0)
+        _assert_same_multi(*out)
+        gp = out[0]
+        assert gp.shape[0] == 6
+        for R, t in poses:
+            errs = [np.abs(gp[3 * k:3 * k + 3, :3] - R).max() for k in range(2)]
+            assert min(errs) < 3e-2, errs
+    # a bound above the number of real instances: the extra proposals are rejected (Tanimoto / too few inliers)
+    pts, K, poses = _two_instance_scene(rng, n_out=100)
+    out = _multi_both(pts[:, :2], pts[:, 2:], K, 3, 4, threshold=4.0, min_triangle_area=0.0)
+    _assert_same_multi(*out)
+
+
+def test_multi_instance_no_consensus_and_argument_checks():
+    from epos_b200 import posefit
+    K = np.array([[1066.778, 0, 312.9869], [0, 1067.487, 241.3109], [0, 0, 1]])
+    rng = np.random.default_rng(4)
+    x2d, x3d = rng.uniform(0, 640, (40, 2)), rng.uniform(-50, 50, (40, 3))
+    out = _multi_both(x2d, x3d, K, 0, 2, threshold=0.02, min_triangle_area=0.0, max_iters=50)
+    assert out[0].shape == (0, 4) and out[4].shape == (0, 4) and int(out[3][0]) == 101
+    _assert_same_multi(*out)
+    with pytest.raises(ValueError):
+        posefit.find6DPoses(x2d, x3d, K, max_model_number=0)
+    with pytest.raises(NotImplementedError):
+        posefit.find6DPoses(x2d, x3d, K, max_model_number=-1)
