@@ -1359,7 +1359,11 @@ struct AlphaExpansion {
     }
     std::vector<char> var;
     const double after = e.minimize(var) + alpha_correction;
-    if (after < before) {                                                   // :452-470
+    // The reference applies the move iff after < before (flow value vs energy before the move).  When the move cannot
+    // improve anything the two are equal in exact arithmetic and the comparison is decided by rounding; a tolerance
+    // makes that case "no move" for every implementation (the CUDA kernel compares the energies of the two labelings).
+    const bool improves = before - after > 1e-9;
+    if (improves) {                                                         // :452-470
       for (int i = 0; i < size; ++i)
         if (var[i] == 0) {
           const int site = active[i];
@@ -1368,7 +1372,7 @@ struct AlphaExpansion {
           lab_cost[site] = D[(size_t)site * L + alpha];
         }
     }
-    return after < before;
+    return improves;
   }
   double expansion(int max_iterations) {                                    // :1003-1088, standard cycles
     update_info();
