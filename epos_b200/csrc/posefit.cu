@@ -1636,6 +1636,251 @@ __device__ inline void proposal_reset(ProbState* st, int it, const double* cpref
   st->cpref = cpref; st->stream_base = 2ULL * (unsigned long long)it; st->multi = 1;
 }
 
+// Neighbourhood graph of spedUpFitting (progressive_x.h:288-289: FlannNeighborhoodGraph over ALL 7 columns of the
+// remaining rows with a hard-coded radius of 20): deterministic stand-in as in prep_kernel -- the max_neighbors nearest
+// rows within the radius, f32 L2 over (u_n, v_n, x, y, z, u, v), ties by index -- plus edge ownership and reverse
+// adjacency.  Called by the whole CTA (THREADS threads) on the current (compacted) point set of problem p.
+__device__ __noinline__ void build_graph7(const Workspace& ws, const epos_fit_params& prm, int p, int N, unsigned char* smem_raw) {
+  constexpr int NT = THREADS, DIMS = 7, UROW = 5, VROW = 6, MAXCELL = 4096;
+  __shared__ float s_red[4][NT / 32];
+  __shared__ float s_box[4];
+  __shared__ int scan_sh[NT / 32 + 1];
+  const int tid = threadIdx.x;
+  const double* P5 = ws.pts + (size_t)p * 7 * NMAX;
+  float* q = reinterpret_cast<float*>(smem_raw);                                   // [7][NMAX]
+  int* cell_start = reinterpret_cast<int*>(smem_raw + (size_t)DIMS * NMAX * 4);    // [MAXCELL + 8]
+  unsigned short* sorted = reinterpret_cast<unsigned short*>(cell_start + MAXCELL + 8);   // [NMAX]
+  int* cursor = reinterpret_cast<int*>(sorted + NMAX);                             // [MAXCELL]
+  __syncthreads();
+  for (int i = tid; i < N; i += NT)
+    for (int d = 0; d < DIMS; ++d) q[d * NMAX + i] = (float)P5[(size_t)d * NMAX + i];
+  __syncthreads();
+  const int KN = prm.max_neighbors < MAXNB ? prm.max_neighbors : MAXNB;
+  const float rad = 20.0f, r2 = rad * rad;
+  short* nbr = ws.nbr + (size_t)p * NMAX * MAXNB;
+  {
+    float mnu = INFINITY, mnv = INFINITY, mxu = -INFINITY, mxv = -INFINITY;
+    for (int i = tid; i < N; i += NT) {
+      mnu = fminf(mnu, q[UROW * NMAX + i]); mxu = fmaxf(mxu, q[UROW * NMAX + i]);
+      mnv = fminf(mnv, q[VROW * NMAX + i]); mxv = fmaxf(mxv, q[VROW * NMAX + i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mnu = fminf(mnu, __shfl_xor_sync(0xffffffffu, mnu, o)); mxu = fmaxf(mxu, __shfl_xor_sync(0xffffffffu, mxu, o));
+      mnv = fminf(mnv, __shfl_xor_sync(0xffffffffu, mnv, o)); mxv = fmaxf(mxv, __shfl_xor_sync(0xffffffffu, mxv, o));
+    }
+    if ((tid & 31) == 0) { s_red[0][tid >> 5] = mnu; s_red[1][tid >> 5] = mxu; s_red[2][tid >> 5] = mnv; s_red[3][tid >> 5] = mxv; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int k = 1; k < NT / 32; ++k) {
+        s_red[0][0] = fminf(s_red[0][0], s_red[0][k]); s_red[1][0] = fmaxf(s_red[1][0], s_red[1][k]);
+        s_red[2][0] = fminf(s_red[2][0], s_red[2][k]); s_red[3][0] = fmaxf(s_red[3][0], s_red[3][k]);
+      }
+      float cs = rad * 1.0001f + 1e-6f;
+      int gw = 1, gh = 1;
+      if (N > 0)
+        for (;;) {
+          gw = (int)floorf((s_red[1][0] - s_red[0][0]) / cs) + 1;
+          gh = (int)floorf((s_red[3][0] - s_red[2][0]) / cs) + 1;
+          if (gw > 0 && gh > 0 && (long long)gw * gh <= MAXCELL) break;
+          cs *= 2.0f;
+          if (!(cs < 1e30f)) { gw = gh = 1; break; }
+        }
+      s_box[0] = s_red[0][0]; s_box[1] = s_red[2][0]; s_box[2] = cs; s_box[3] = __int_as_float(gw | (gh << 16));
+    }
+    __syncthreads();
+  }
+  const float bu = s_box[0], bv = s_box[1], ics = 1.0f / s_box[2];
+  const int gw = __float_as_int(s_box[3]) & 0xffff, gh = __float_as_int(s_box[3]) >> 16;
+  const int ncell = gw * gh;
+  auto cell_of = [&](int i, int* cx, int* cy) {
+    int x = (int)floorf((q[UROW * NMAX + i] - bu) * ics), y = (int)floorf((q[VROW * NMAX + i] - bv) * ics);
+    *cx = x < 0 ? 0 : (x >= gw ? gw - 1 : x);
+    *cy = y < 0 ? 0 : (y >= gh ? gh - 1 : y);
+  };
+  for (int c = tid; c <= ncell; c += NT) cell_start[c] = 0;
+  __syncthreads();
+  for (int i = tid; i < N; i += NT) { int cx, cy; cell_of(i, &cx, &cy); atomicAdd(&cell_start[cy * gw + cx + 1], 1); }
+  __syncthreads();
+  {
+    constexpr int per = (MAXCELL + NT - 1) / NT;
+    int loc = 0;
+    for (int k = 0; k < per; ++k) { const int c = tid * per + k + 1; if (c <= ncell) loc += cell_start[c]; }
+    int total;
+    int base = block_excl_scan<NT / 32>(loc, scan_sh, &total);
+    for (int k = 0; k < per; ++k) { const int c = tid * per + k + 1; if (c <= ncell) { base += cell_start[c]; cell_start[c] = base; } }
+  }
+  __syncthreads();
+  for (int c = tid; c < ncell; c += NT) cursor[c] = cell_start[c + 1];
+  __syncthreads();
+  for (int i = tid; i < N; i += NT) { int cx, cy; cell_of(i, &cx, &cy); sorted[atomicSub(&cursor[cy * gw + cx], 1) - 1] = (unsigned short)i; }
+  __syncthreads();
+  for (int i = tid; i < N; i += NT) {
+    float bd[MAXNB];
+    int bj[MAXNB];
+#pragma unroll
+    for (int k = 0; k < MAXNB; ++k) { bd[k] = INFINITY; bj[k] = -1; }
+    float a[DIMS];
+#pragma unroll
+    for (int d = 0; d < DIMS; ++d) a[d] = q[d * NMAX + i];
+    int cx, cy;
+    cell_of(i, &cx, &cy);
+    for (int yy = max(cy - 1, 0); yy <= min(cy + 1, gh - 1); ++yy) {
+      const int c0 = yy * gw + max(cx - 1, 0), c1 = yy * gw + min(cx + 1, gw - 1);
+      for (int s_ = cell_start[c0]; s_ < cell_start[c1 + 1]; ++s_) {
+        const int j = sorted[s_];
+        float dsum = 0.f;
+#pragma unroll
+        for (int d = 0; d < DIMS; ++d) { const float e = a[d] - q[d * NMAX + j]; dsum = __fmaf_rn(e, e, dsum); }
+        if (j == i || !(dsum <= r2)) continue;
+        float cd = dsum; int cj = j;
+        bool ins = false;
+#pragma unroll
+        for (int k = 0; k < MAXNB; ++k) {
+          if (ins || bj[k] < 0 || cd < bd[k] || (cd == bd[k] && cj < bj[k])) {
+            const float td = bd[k]; const int tj = bj[k];
+            bd[k] = cd; bj[k] = cj; cd = td; cj = tj;
+            ins = true;
+            if (cj < 0) break;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < MAXNB; ++k) nbr[(size_t)i * MAXNB + k] = (short)((k < KN) ? bj[k] : -1);
+  }
+  __syncthreads();
+  // edge ownership + reverse adjacency (as prep_kernel)
+  unsigned char* owned = ws.owned + (size_t)p * NMAX * MAXNB;
+  int* rev_off = ws.rev_off + (size_t)p * (NMAX + 1);
+  int* rev_idx = ws.rev_idx + (size_t)p * NMAX * MAXNB;
+  int* indeg = reinterpret_cast<int*>(smem_raw);                                   // q is dead now
+  for (int i = tid; i <= N; i += NT) indeg[i] = 0;
+  __syncthreads();
+  for (int i = tid; i < N; i += NT)
+    for (int k = 0; k < MAXNB; ++k) {
+      const int j = nbr[(size_t)i * MAXNB + k];
+      unsigned char own = 0;
+      if (j >= 0 && j != i) {
+        own = 1;
+        if (j < i)
+          for (int m = 0; m < MAXNB; ++m) own &= (nbr[(size_t)j * MAXNB + m] != i);
+      }
+      owned[(size_t)i * MAXNB + k] = own;
+      if (own) atomicAdd(&indeg[j], 1);
+    }
+  __syncthreads();
+  {
+    constexpr int per = (NMAX + NT - 1) / NT;
+    int loc[per];
+    int s = 0;
+    for (int k = 0; k < per; ++k) { const int i = tid * per + k; loc[k] = i < N ? indeg[i] : 0; s += loc[k]; }
+    int total;
+    int base = block_excl_scan<NT / 32>(s, scan_sh, &total);
+    for (int k = 0; k < per; ++k) { const int i = tid * per + k; if (i < N) rev_off[i] = base; base += loc[k]; }
+    if (tid == 0) rev_off[N] = total;
+    __syncthreads();
+    for (int i = tid; i < N; i += NT) indeg[i] = rev_off[i];
+    __syncthreads();
+    for (int i = tid; i < N; i += NT)
+      for (int k = 0; k < MAXNB; ++k)
+        if (owned[(size_t)i * MAXNB + k]) {
+          const int j = nbr[(size_t)i * MAXNB + k];
+          rev_idx[atomicAdd(&indeg[j], 1)] = i * MAXNB + k;
+        }
+    __syncthreads();
+    for (int i = tid; i < N; i += NT) {
+      const int b = rev_off[i], e = rev_off[i + 1];
+      for (int a2 = b + 1; a2 < e; ++a2) {
+        const int v = rev_idx[a2];
+        int c2 = a2 - 1;
+        while (c2 >= b && rev_idx[c2] > v) { rev_idx[c2 + 1] = rev_idx[c2]; --c2; }
+        rev_idx[c2 + 1] = v;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// spedUpFitting (progressive_x.h:265-391): sequential GC-RANSAC proposals (plain EPOS score, confidence 1) on the points
+// the accepted proposals have not explained yet; no PEARL; the labeling stays zero and the scores stay zero as in the
+// reference.  max_model_number = -1 ("all instances"): the reference's loop never terminates (size_t counter against an
+// int holding -1); defined here as in the oracle: stop when no model is found, when a proposal has fewer than
+// min_point_number inliers, or when the unseen-inlier test of ProgressiveX::run fires; at most MAX_INSTANCES instances.
+__device__ __noinline__ void sped_up_fitting(const Workspace& ws, const epos_fit_params& prm, const MultiParams& mp, int p,
+                                             int max_model_number, unsigned char* smem_raw, const int* __restrict__ offsets,
+                                             double* __restrict__ poses, int* __restrict__ labeling) {
+  __shared__ int scan_sh[WARPS + 1], s_stop;
+  const int tid = threadIdx.x;
+  ProbState* st = ws.st + p;
+  MultiState* ms = ws.ms + p;
+  double* models = ws.models + (size_t)p * MAX_INSTANCES * 12;
+  double* P5 = ws.pts + (size_t)p * 7 * NMAX;
+  unsigned short* pixg = ws.pix + (size_t)p * NMAX;
+  const bool unbounded = max_model_number < 0;
+  const int limit = unbounded ? MAX_INSTANCES : (max_model_number < MAX_INSTANCES ? max_model_number : MAX_INSTANCES);
+  bool pts_loaded = false;
+  if (tid == 0) ms->sped_up = 1;
+  for (int it = 0; it < limit; ++it) {
+    __syncthreads();
+    const int N = st->N;
+    build_graph7(ws, prm, p, N, smem_raw);
+    pts_loaded = false;
+    if (tid == 0) { proposal_reset(st, it, nullptr); ++ms->proposals; }
+    __syncthreads();
+    run_state_machine(ws, prm, p, smem_raw, pts_loaded);
+    phase_final(ws, prm, p, smem_raw, pts_loaded, offsets, poses, labeling);
+    __syncthreads();
+    if (!st->found) { if (unbounded) break; continue; }
+    const int nin = st->n_final;
+    const int slot = ms->n_models;
+    __syncthreads();
+    if (tid < 12) models[12 * slot + tid] = ws.fin_model[(size_t)p * 12 + tid];
+    if (tid == 0) { ms->total_iterations += (long long)st->iter; ms->n_models = slot + 1; ++ms->accepted; ms->scores[slot] = 0.0; }
+    __syncthreads();
+    if (nin < mp.min_point_number) { if (unbounded) break; continue; }
+    // ---- remove the proposal's inliers: ordered compaction of the 7 point rows and the pixel ids ----
+    int* newidx = reinterpret_cast<int*>(smem_raw);                 // [NMAX]  -1 = removed
+    double* buf = reinterpret_cast<double*>(smem_raw + NMAX * 4);   // [NMAX]
+    const unsigned short* fi = ws.fin_inl + (size_t)p * NMAX;
+    for (int i = tid; i < N; i += THREADS) newidx[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < nin; i += THREADS) newidx[fi[i]] = -1;
+    __syncthreads();
+    {
+      const int per = PER_THREAD;
+      int cnt = 0;
+      for (int q = 0; q < per; ++q) { const int i = tid * per + q; cnt += (i < N && newidx[i] == 0); }
+      int total;
+      int base = block_excl_scan<WARPS>(cnt, scan_sh, &total);
+      for (int q = 0; q < per; ++q) { const int i = tid * per + q; if (i < N && newidx[i] == 0) newidx[i] = base++; }
+      __syncthreads();
+      for (int r = 0; r < 7; ++r) {
+        for (int i = tid; i < N; i += THREADS) buf[i] = P5[(size_t)r * NMAX + i];
+        __syncthreads();
+        for (int i = tid; i < N; i += THREADS) if (newidx[i] >= 0) P5[(size_t)r * NMAX + newidx[i]] = buf[i];
+        __syncthreads();
+      }
+      unsigned short* sb = reinterpret_cast<unsigned short*>(buf);
+      for (int i = tid; i < N; i += THREADS) sb[i] = pixg[i];
+      __syncthreads();
+      for (int i = tid; i < N; i += THREADS) if (newidx[i] >= 0) pixg[newidx[i]] = sb[i];
+      __syncthreads();
+      if (tid == 0) {
+        st->N = total;
+        s_stop = 0;
+        if (unbounded) {
+          const double ratio = pow(1.0 - pow(1.0 - mp.confidence, 1.0 / (double)ms->total_iterations), 1.0 / 3.0);
+          s_stop = llround((double)total * ratio) < (long long)mp.min_point_number;
+        }
+      }
+      __syncthreads();
+    }
+    if (s_stop) break;
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 progx_kernel(Workspace ws, epos_fit_params prm, MultiParams mp, const int* __restrict__ offsets,
              const int* __restrict__ max_models, double* __restrict__ poses, int* __restrict__ labeling,
@@ -1680,8 +1925,22 @@ progx_kernel(Workspace ws, epos_fit_params prm, MultiParams mp, const int* __res
   }
   __syncthreads();
   if (!st->valid || st->phase == PH_DONE) return;                      // fewer than 6 correspondences, singular K, ...
-  if (max_model_number < 2 || max_model_number > mp.max_model_number_for_pearl) {
-    if (tid == 0) multi_counts[p] = -1;                                // not a PEARL-mode problem: rejected
+  if (max_model_number == 0 || max_model_number == 1 || max_model_number < -1) {
+    if (tid == 0) multi_counts[p] = -1;                                // not a multi-instance bound: rejected
+    return;
+  }
+  if (max_model_number < 0 || max_model_number > mp.max_model_number_for_pearl) {          // progressive_x.h:417-425
+    sped_up_fitting(ws, prm, mp, p, max_model_number, smem_raw, offsets, poses, labeling);
+    const int M = ms->n_models;
+    for (int i = tid; i < 12 * M; i += THREADS) out_poses[i] = models[i];
+    for (int i = tid; i < M; i += THREADS) out_scores[i] = 0.0;        // RANSACStatistics::score is never written
+    if (tid == 0) {
+      multi_counts[p] = M;
+      ms->done = 1;
+      double* rec = poses + (size_t)p * EPOS_POSE_RECORD_DOUBLES;
+      for (int i = 0; i < 12; ++i) rec[i] = M > 0 ? models[i] : 0.0;
+      rec[12] = 0.0; rec[13] = (double)ms->total_iterations; rec[14] = (double)M; rec[15] = (double)ms->proposals;
+    }
     return;
   }
   const double T2 = 9.0 / 4.0 * st->thr_n * st->thr_n;                 // progressive_x.h:679

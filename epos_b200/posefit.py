@@ -188,8 +188,9 @@ def find6DPoses(x1y1, x2y2z2, K, threshold=4.0, max_model_number=-1, conf=0.5, p
     """Same name / keyword arguments / return triple as pyprogressivex.find6DPoses (bindings.cpp:9-28,117,133-152):
     (poses [3M,4] f64, labeling [N] i32, scores [M] f64) as numpy arrays.  Errors: ValueError for malformed shapes
     (bindings.cpp:30-58).  max_model_number == 1: GC-RANSAC + final LM; 2 .. max_model_number_for_optimization:
-    Progressive-X with PEARL (one pose per instance, labeling = instance index, scores = instance support).  `seed`
-    selects the RANSAC stream (the reference seeds from std::random_device)."""
+    Progressive-X with PEARL (one pose per instance, labeling = instance index, scores = instance support); more, or -1:
+    sequential propose-and-remove fitting (spedUpFitting; labeling and scores zero as in the reference; -1 is bounded,
+    see include/epos_b200.h).  `seed` selects the RANSAC stream (the reference seeds from std::random_device)."""
     x1y1 = np.ascontiguousarray(x1y1, np.float64)
     x2y2z2 = np.ascontiguousarray(x2y2z2, np.float64)
     K = np.ascontiguousarray(K, np.float64)
@@ -207,9 +208,6 @@ def find6DPoses(x1y1, x2y2z2, K, threshold=4.0, max_model_number=-1, conf=0.5, p
         # Progressive-X (progressivex_python.cpp:136-221).  PEARL mode: 2 .. max_model_number_for_optimization instances.
         if max_model_number == 0 or max_model_number < -1:
             raise ValueError('max_model_number should be -1 or positive')
-        if max_model_number == -1 or max_model_number > max_model_number_for_optimization:
-            raise NotImplementedError('sequential propose-and-remove fitting (max_model_number = -1 or > '
-                                      'max_model_number_for_optimization, progressive_x.h:265-391) is not built on the device')
         if max_model_number_for_optimization > 5:
             raise ValueError('max_model_number_for_optimization must be <= 5 (infer.py max_model_number_for_pearl default)')
         if n > _lib.lib().epos_fit_max_points():

@@ -245,8 +245,14 @@ typedef struct {
   double max_tanimoto_similarity;       /* 0.9 */
 } epos_multi_params;
 
-/* Inputs as epos_fit_poses plus max_models [P] i32 (device): the instance bound of each problem (2 .. max_model_number_for_pearl).
- * Outputs: multi_counts [P] (instances found; -1 = max_models outside the supported range), multi_poses
+/* Inputs as epos_fit_poses plus max_models [P] i32 (device): the instance bound of each problem.  2 ..
+ * max_model_number_for_pearl: Progressive-X with PEARL.  Larger, or -1 ("all instances", DETECTION): sequential
+ * propose-and-remove fitting without PEARL (spedUpFitting, progressive_x.h:265-391; neighbourhood rebuilt over the 7
+ * columns of the remaining rows; labeling and scores stay zero as in the reference).  For -1 the reference's loop never
+ * terminates (a size_t counter compared with an int holding -1, progressive_x.h:280); here it stops when no model is
+ * found, when a proposal has fewer than min_point_number inliers or when the unseen-inlier test of ProgressiveX::run
+ * (:589-611) fires on the remaining points; at most epos_fit_max_instances() instances either way.
+ * Outputs: multi_counts [P] (instances found; -1 = max_models is 0, 1 or < -1), multi_poses
  * [P][epos_fit_max_instances()][12] row-major [R|t] per instance (no final LM in this branch, as in the reference),
  * multi_scores [P][epos_fit_max_instances()] (sum of the instance's preferences, progressive_x.h:781-790), labeling
  * (instance index per correspondence; outliers = number of instances; with one instance 0 = inlier, 1 = outlier),

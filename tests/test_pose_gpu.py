@@ -484,5 +484,27 @@ def test_multi_instance_no_consensus_and_argument_checks():
     _assert_same_multi(*out)
     with pytest.raises(ValueError):
         posefit.find6DPoses(x2d, x3d, K, max_model_number=0)
-    with pytest.raises(NotImplementedError):
-        posefit.find6DPoses(x2d, x3d, K, max_model_number=-1)
+
+
+def test_multi_instance_sequential_fitting_matches_oracle():
+    """More instances than max_model_number_for_optimization, or -1 (DETECTION): spedUpFitting (progressive_x.h:265-391):
+    proposals on the points the earlier ones left, neighbourhood rebuilt over all 7 columns, no PEARL."""
+    from epos_b200 import posefit
+    from oracle import posefit as opf
+    g = json.load(open(os.path.join(GOLDEN, 'tless.json')))
+    c, K = np.array(g['corrs']), np.array(g['K'])
+    rng = np.random.default_rng(8)
+    pts, K2, poses = _two_instance_scene(rng)
+    for (x2d, x3d, Kc, mm, mopt, seed) in ((c[:, :2], c[:, 2:], K, 4, 3, 0), (pts[:, :2], pts[:, 2:], K2, 7, 5, 1),
+                                           (pts[:, :2], pts[:, 2:], K2, -1, 5, 2)):
+        kw = dict(threshold=4.0, min_triangle_area=0.0, max_model_number=mm, max_model_number_for_optimization=mopt, seed=seed)
+        gp, gl, gs = posefit.find6DPoses(x2d, x3d, Kc, **kw)
+        state = posefit.find6DPoses.last_multi_state.copy()
+        op, ol, os_, st = opf.find6DPoses(x2d, x3d, Kc, return_stats=True, **kw)
+        assert st['sped_up'] == 1 and gp.shape == op.shape and op.shape[0] >= 6, (gp.shape, op.shape, state, st)
+        assert int(state[0]) == st['proposals'] and int(state[2]) == st['ransac_iterations'], (state, st)
+        assert not gl.any() and not ol.any() and not gs.any() and not os_.any()
+        for k in range(op.shape[0] // 3):
+            a, b = gp[3 * k:3 * k + 3], op[3 * k:3 * k + 3]
+            assert np.abs(a[:, :3] - b[:, :3]).max() < 1e-4, (k, np.abs(a - b).max())
+            assert np.linalg.norm(a[:, 3] - b[:, 3]) < 1e-4 * max(1.0, np.linalg.norm(b[:, 3]))
