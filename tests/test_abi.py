@@ -55,8 +55,12 @@ def test_find6dposes_shim_argument_errors():
         posefit.find6DPoses(np.zeros((5, 2)), np.zeros((4, 3)), K, max_model_number=1)
     with pytest.raises(ValueError):
         posefit.find6DPoses(np.zeros((5, 2)), np.zeros((5, 3)), np.eye(4), max_model_number=1)
+    with pytest.raises(ValueError):
+        posefit.find6DPoses(np.zeros((5, 2)), np.zeros((5, 3)), K, max_model_number=0)
+    with pytest.raises(ValueError):                                          # PEARL holds at most 5 instances + the proposal
+        posefit.find6DPoses(np.zeros((5, 2)), np.zeros((5, 3)), K, max_model_number=2, max_model_number_for_optimization=9)
     with pytest.raises(NotImplementedError):
-        posefit.find6DPoses(np.zeros((5, 2)), np.zeros((5, 3)), K)          # default -1 = Progressive-X
+        posefit.find6DPoses(np.zeros((5, 2)), np.zeros((5, 3)), K, max_model_number=1, proposal_engine_conf=0.9)
 
 
 def test_fit_params_defaults_match_reference_flags():
