@@ -22,7 +22,7 @@ class Engine:
 
     def __init__(self, weights, num_objs, num_frags, device, stages=STAGES_CNN, model_store=None, K=None,
                  fit_params=None, max_correspondences=4096, seed=0, min_obj_conf=0.1, min_frag_rel_conf=0.5,
-                 model_options=None, pipelined=False, post_fit=None, lazy_loc=True):
+                 model_options=None, pipelined=False, post_fit=None, lazy_loc=True, multi_params=None):
         self.dev = torch.device(device)
         self.net = model.EposNet(weights, num_objs, num_frags, self.dev, model_options=model_options)
         self.O, self.F = num_objs, num_frags
@@ -47,24 +47,28 @@ class Engine:
             from . import posefit
             self._fitter = posefit.BatchFitter(self.dev, num_objs, num_frags, model_store, K, fit_params,
                                                max_correspondences, seed, min_obj_conf=min_obj_conf,
-                                               min_frag_rel_conf=min_frag_rel_conf)
+                                               min_frag_rel_conf=min_frag_rel_conf, mparams=multi_params)
 
-    def _fit(self, out, after_extract=None, K=None):
-        poses = self._fitter.fit(out, after_extract, K).clone()      # the fitter's record buffer is reused by the next batch
+    def _fit(self, out, after_extract=None, K=None, num_instances=None):
+        poses = self._fitter.fit(out, after_extract, K, num_instances).clone()   # the record buffer is reused by the next batch
         out['poses'] = poses
+        if self._fitter.multi is not None:
+            out['multi'] = self._fitter.multi                        # Progressive-X problems: every instance (BatchFitter.fit_maps)
         if self.post_fit is not None:
             out['poses_all'] = self.post_fit(poses)
 
-    def run_device(self, images_dev, K=None):
+    def run_device(self, images_dev, K=None, num_instances=None):
         """images_dev [B,H,W,3] f32 CUDA; K = this batch's camera intrinsics, [3,3] or [B,3,3] (default: the K given
         at construction -- the reference reads K per image, scripts/infer.py:376-377).  Returns a dict of CUDA tensors:
         model.predict's outputs for 'cnn', plus 'poses' [B,O,16] f64 pose records for the full path (pipelined: valid
-        after join() / out['ready'])."""
+        after join() / out['ready']).  num_instances [B,J]: instance bound per (image, object slot) as in
+        scripts/infer.py:462-468 (0 = skip, 1 = GC-RANSAC, 2.. = Progressive-X, -1 = all); out['multi'] then holds every
+        instance of the Progressive-X problems."""
         out = self.net.predict(images_dev, lazy_loc=self.lazy_loc)
         if self._fitter is None:
             return out
         if not self.pipelined:
-            self._fit(out, K=K)
+            self._fit(out, K=K, num_instances=num_instances)
             return out
         main = torch.cuda.current_stream(self.dev)
         done_cnn = torch.cuda.Event()
@@ -81,7 +85,7 @@ class Engine:
             for t in maps:
                 t.record_stream(self._side)
             ev_maps = torch.cuda.Event()
-            self._fit(out, after_extract=lambda: ev_maps.record(self._side), K=K)
+            self._fit(out, after_extract=lambda: ev_maps.record(self._side), K=K, num_instances=num_instances)
             ev = torch.cuda.Event()
             ev.record(self._side)
         self._inflight.append((maps, ev_maps))

@@ -110,9 +110,12 @@ class BatchFitter:
     (record layout: include/epos_b200.h EPOS_POSE_RECORD_DOUBLES)."""
 
     def __init__(self, device, num_objs, num_frags, model_store, K, params=None, max_correspondences=4096, seed=0,
-                 obj_ids=None, output_scale=0.25, min_obj_conf=0.1, min_frag_rel_conf=0.5):
+                 obj_ids=None, output_scale=0.25, min_obj_conf=0.1, min_frag_rel_conf=0.5, mparams=None):
         self.dev = torch.device(device)
         self.params = params or default_params()
+        self.mparams = mparams or multi_params()
+        self._multi_fitter = None
+        self.multi = None                 # result of the Progressive-X problems of the last batch (see fit_maps)
         nmax = _lib.lib().epos_fit_max_points()
         if max_correspondences is None or max_correspondences > nmax:
             raise ValueError('this build keeps the point set in shared memory: max_correspondences must be <= %d '
@@ -160,7 +163,12 @@ class BatchFitter:
         """Stream key of problem (image b, slot j) in batch n: seed * 2^32 + n * P + b * J + j."""
         return self._base + (self.seed << 32) + self.batch_index * (B * self.J)
 
-    def fit_maps(self, obj_conf, frag_conf, frag_loc, after_extract=None, K=None, lazy_loc=None):
+    def fit_maps(self, obj_conf, frag_conf, frag_loc, after_extract=None, K=None, lazy_loc=None, num_instances=None):
+        """num_instances [B, J] (host ints; None = 1 everywhere) is the `num_instances` of scripts/infer.py:462-468 per
+        (image, object slot): 0 = object not annotated (skipped), 1 = GC-RANSAC + final LM, 2 .. = Progressive-X with
+        that instance bound, -1 = all instances (DETECTION).  Records [B, J, 16]; for Progressive-X problems the record
+        holds the first instance and record[14] the number of instances, all of them are in self.multi =
+        {'index': [(b, j), ...], 'poses' [Pm, MAXI, 12], 'scores' [Pm, MAXI], 'counts' [Pm], 'labeling'} (device)."""
         B = obj_conf.shape[0]
         self._prepare(B, K)
         bc = self.extract(obj_conf, frag_conf, frag_loc, lazy_loc=lazy_loc)
@@ -169,15 +177,38 @@ class BatchFitter:
             after_extract()                       # the head maps are no longer needed from here on
         seeds = self.seeds_for(B)
         self.batch_index += 1
-        poses, lab = self._fitter.fit(bc.coord_2d.view(-1, 2), bc.coord_3d.view(-1, 3), bc.offsets, bc.counts,
+        counts = bc.counts
+        self.multi = None
+        midx = None
+        if num_instances is not None:
+            ni = np.ascontiguousarray(num_instances, np.int32).reshape(-1)
+            if ni.size != B * self.J:
+                raise ValueError('num_instances should be [B, J] = [%d, %d]' % (B, self.J))
+            if ((ni < -1)).any():
+                raise ValueError('num_instances entries should be -1, 0 or positive')
+            if (ni != 1).any():
+                nid = torch.from_numpy(ni).to(self.dev)
+                counts = torch.where(nid == 1, counts, torch.zeros_like(counts))
+                midx = np.nonzero((ni != 1) & (ni != 0))[0]
+        poses, lab = self._fitter.fit(bc.coord_2d.view(-1, 2), bc.coord_3d.view(-1, 3), bc.offsets, counts,
                                       self._Kdev, seeds, self._poses, self._labeling)
+        if midx is not None and midx.size:
+            if self._multi_fitter is None or self._multi_fitter.P < midx.size:
+                self._multi_fitter = MultiPoseFitter(self.dev, max(int(midx.size), 4), self.params, self.mparams)
+            it = torch.from_numpy(midx.astype(np.int64)).to(self.dev)
+            rec, mlab, mposes, mscores, mcounts = self._multi_fitter.fit(
+                bc.coord_2d.view(-1, 2), bc.coord_3d.view(-1, 3), bc.offsets[it].contiguous(), bc.counts[it].contiguous(),
+                self._Kdev[it].contiguous(), seeds[it].contiguous(), nid[it].contiguous())
+            poses.index_copy_(0, it, rec)
+            self.multi = {'index': [(int(i) // self.J, int(i) % self.J) for i in midx], 'poses': mposes, 'scores': mscores,
+                          'counts': mcounts, 'labeling': mlab}
         return poses.view(B, self.J, 16)
 
-    def fit(self, predictions, after_extract=None, K=None):
+    def fit(self, predictions, after_extract=None, K=None, num_instances=None):
         from . import model
         return self.fit_maps(predictions[model.PRED_OBJ_CONF], predictions[model.PRED_FRAG_CONF],
                              predictions.get(model.PRED_FRAG_LOC), after_extract, K,
-                             lazy_loc=predictions.get(model.LAZY_FRAG_LOC))
+                             lazy_loc=predictions.get(model.LAZY_FRAG_LOC), num_instances=num_instances)
 
 
 def find6DPoses(x1y1, x2y2z2, K, threshold=4.0, max_model_number=-1, conf=0.5, proposal_engine_conf=1.0,

@@ -74,11 +74,13 @@ def rodrigues(rv):
 
 
 def planted_maps(B, num_objs, num_frags, store, K, seed=0, objs_per_image=None, outlier_frac=0.3, loc_noise=0.02,
-                 h=120, w=160, output_scale=0.25):
+                 h=120, w=160, output_scale=0.25, instances_per_object=1):
     """Model outputs with known poses.  Returns (obj_conf [B,h,w,O+1], frag_conf [B,h,w,O,F], frag_loc [B,h,w,O,F,3],
     gt) with gt[b] = {obj_id: (R, t)}.  Each visible object is the 100 mm sphere of `store` at t_z in [500, 1200] mm;
     inside its silhouette obj_conf = 0.9, frag_conf = 0.8 on the true fragment, frag_loc = (X - centre)/size + noise;
-    `outlier_frac` of the silhouette pixels get a random fragment and random local coordinates instead."""
+    `outlier_frac` of the silhouette pixels get a random fragment and random local coordinates instead.
+    instances_per_object > 1 plants that many spheres per visible object (later ones overwrite earlier ones where they
+    overlap); gt[b][obj_id] is then a LIST of (R, t)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     O, F = num_objs, num_frags
     obj_conf = np.zeros((B, h, w, O + 1), np.float32)
@@ -96,7 +98,7 @@ def planted_maps(B, num_objs, num_frags, store, K, seed=0, objs_per_image=None, 
         g = {}
         n_vis = len(ids) if objs_per_image is None else min(objs_per_image, len(ids))
         vis = list(rng.choice(ids, size=n_vis, replace=False)) if n_vis < len(ids) else list(ids)
-        for oid in vis:
+        for oid in [o for o in vis for _ in range(instances_per_object)]:
             tz = rng.uniform(500.0, 1200.0)
             cu, cv = rng.uniform(0.2, 0.8) * w / output_scale, rng.uniform(0.2, 0.8) * h / output_scale
             t = tz * (Kinv @ np.array([cu, cv, 1.0]))
@@ -126,6 +128,9 @@ def planted_maps(B, num_objs, num_frags, store, K, seed=0, objs_per_image=None, 
             frag_conf[b, yy, xx, oid - 1, :] = 0.2 / (F - 1) if F > 1 else 1.0
             frag_conf[b, yy, xx, oid - 1, f] = 0.8 if F > 1 else 1.0
             frag_loc[b, yy, xx, oid - 1, f, :] = loc.astype(np.float32)
-            g[int(oid)] = (R, t)
+            if instances_per_object == 1:
+                g[int(oid)] = (R, t)
+            else:
+                g.setdefault(int(oid), []).append((R, t))
         gt.append(g)
     return obj_conf, frag_conf, frag_loc, gt
