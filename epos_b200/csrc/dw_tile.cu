@@ -9,6 +9,7 @@
 // strip's 4+2r input columns are read once per filter row (LDS.128, 8 lanes cover the 128 B of a pixel: conflict-free)
 // and reused across the 3 horizontal taps; the 9 taps of the lane's channels live in registers.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -16,10 +17,10 @@ namespace epos {
 
 constexpr int DT_TW = 16;          // tile width (output pixels)
 constexpr int DT_SLAB = 32;        // channels per CTA
-constexpr int DT_THREADS = 256;    // 8 channel groups x (4 strips per row x 8 rows per pass)
+constexpr int DT_THREADS = 256;    // 8 channel groups x (4 strips per row x 8 rows per pass); three CTAs per SM
 
 template <int R>
-__global__ void __launch_bounds__(DT_THREADS) dwconv3x3_tile_kernel(
+__global__ void __launch_bounds__(DT_THREADS, 3) dwconv3x3_tile_kernel(
     const __grid_constant__ CUtensorMap tmap, const float* __restrict__ w, const float* __restrict__ bias,
     float* __restrict__ y_f32, uint16_t* __restrict__ y_split, int ldy_split, long long plane_stride, int H, int W, int C,
     int TH,
@@ -242,12 +243,17 @@ int dwconv3x3_tiled(const float* x, int ldx, const float* w, const float* bias, 
       return launch_dw_rows(x, ldx, w, bias, y_f32, y_split, ldy_split, B, H, W, C, rate, relu_in, relu_out, stream);
     return EPOS_ERR_UNSUPPORTED;
   }
-  // tile height: a multiple of 4 in [8, 24] with the least padded rows (ties: the taller tile)
+  // tile height: a multiple of 4 in [8, 24] that loads the fewest rows in total (tiles x (TH + 2 rate): halo and padded
+  // rows both count), among the heights whose haloed tile leaves room for THREE CTAs per SM (the kernel is built for
+  // 3 x 256 threads, 80 registers: a CTA waits for its TMA box before it computes, so the latency is hidden by the
+  // other resident CTAs -- measured on B200: 2 -> 3 CTAs per SM takes the 60x80x728 layer from 53 to 46 us)
   int TH = 8, best = 1 << 30;
   for (int t = 8; t <= 24; t += 4) {
-    const int waste = ceil_div(H, t) * t - H;
-    if (waste <= best) { best = waste; TH = t; }
+    if (t > 8 && (t + 2 * rate) * (DT_TW + 2 * rate) * DT_SLAB * 4 + 128 > 74 * 1024) break;
+    const int rows = ceil_div(H, t) * (t + 2 * rate);
+    if (rows <= best) { best = rows; TH = t; }
   }
+  if (const char* e = getenv("EPOS_DW_TH")) { const int t = atoi(e); if (t >= 4 && t <= 32 && t % 4 == 0) TH = t; }   // developer A/B
   if ((long long)ceil_div(H, TH) * B > 65535 || ceil_div(W, DT_TW) > 65535) return EPOS_ERR_UNSUPPORTED;
   CUtensorMap map;
   int rc = make_dw_map(&map, x, ldx, B, H, W, C, TH, rate);

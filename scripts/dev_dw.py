@@ -9,13 +9,14 @@ shapes = [(8, 60, 80, 728, 1, 2), (8, 60, 80, 2048, 1, 12), (8, 120, 160, 256, 2
 for (B, H, W, C, stride, rate) in shapes:
     Ho, Wo = (H, W) if stride == 1 else ((H - 1) // 2 + 1, (W - 1) // 2 + 1)
     nb = 3
-    xs = [torch.randn(B * H * W, C, device=dev) for _ in range(nb)]
+    LDX = (C + 31) // 32 * 32          # the network keeps f32 activations with 128-byte aligned rows (728 -> 736)
+    xs = [torch.randn(B * H * W, LDX, device=dev) for _ in range(nb)]
     LDY = (C + 15) // 16 * 16
     ys = [torch.empty(2, B * Ho * Wo, LDY, dtype=torch.bfloat16, device=dev) for _ in range(nb)]
     w = torch.randn(9, C, device=dev); b = torch.randn(C, device=dev)
     s = torch.cuda.current_stream().cuda_stream
     def run(i):
-        _lib.check(lib.epos_dwconv3x3(xs[i % nb].data_ptr(), C, w.data_ptr(), b.data_ptr(), None, ys[i % nb].data_ptr(), LDY, B, H, W, C, stride, rate, 1, 0, s), 'dw')
+        _lib.check(lib.epos_dwconv3x3(xs[i % nb].data_ptr(), LDX, w.data_ptr(), b.data_ptr(), None, ys[i % nb].data_ptr(), LDY, B, H, W, C, stride, rate, 1, 0, s), 'dw')
     for i in range(3): run(i)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -24,4 +25,4 @@ for (B, H, W, C, stride, rate) in shapes:
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / n * 1e3
     bytes_ = (B * H * W * C * 4 + B * Ho * Wo * C * 4)
-    print('variant %s  B%d %dx%dx%d s%d r%d: %.1f us  %.0f GB/s (alg)' % (os.environ.get('EPOS_DW_VARIANT', 'default'), B, H, W, C, stride, rate, us, bytes_ / us / 1e3))
+    print('TH %s variant %s  B%d %dx%dx%d s%d r%d: %.1f us  %.0f GB/s (alg)' % (os.environ.get('EPOS_DW_TH', 'auto'), os.environ.get('EPOS_DW_VARIANT', 'default'), B, H, W, C, stride, rate, us, bytes_ / us / 1e3))
