@@ -28,6 +28,34 @@ _DTYPES = {1: np.float32, 2: np.float64, 3: np.int32, 4: np.uint8, 5: np.int16, 
            17: np.uint16, 19: np.float16, 22: np.uint32, 23: np.uint64}
 
 
+# CRC-32C (Castagnoli, reflected polynomial 0x82F63B78) as used by LevelDB tables and the tensor bundle, and LevelDB's
+# "masked" form stored in files (leveldb/util/crc32c.h: rotate right by 15, add 0xa282ead8).
+_CRC_TABLE = []
+for _i in range(256):
+    _c = _i
+    for _ in range(8):
+        _c = (_c >> 1) ^ 0x82F63B78 if _c & 1 else _c >> 1
+    _CRC_TABLE.append(_c)
+_CRC_VERIFY_LIMIT = 1 << 20          # tensor payloads above this size are checked only with verify_data=True (pure Python)
+
+
+def crc32c(data, crc=0):
+    c = crc ^ 0xFFFFFFFF
+    tab = _CRC_TABLE
+    for b in bytes(data):
+        c = tab[(c ^ b) & 0xFF] ^ (c >> 8)
+    return c ^ 0xFFFFFFFF
+
+
+def mask_crc(crc):
+    return ((((crc >> 15) | (crc << 17)) & 0xFFFFFFFF) + 0xA282EAD8) & 0xFFFFFFFF
+
+
+def unmask_crc(masked):
+    rot = (masked - 0xA282EAD8) & 0xFFFFFFFF
+    return ((rot >> 17) | (rot << 15)) & 0xFFFFFFFF
+
+
 def _varint(buf, pos):
     result, shift = 0, 0
     while True:
@@ -115,6 +143,11 @@ def _read_block(data, offset, size):
     blk = data[offset:offset + size]
     if size < 4:
         raise ValueError('short block')
+    # block trailer: masked crc32c over the block contents and the compression-type byte (table/format.cc).  Writers
+    # that do not checksum leave the field zero; anything else must match.
+    stored = struct.unpack('<I', data[offset + size + 1:offset + size + 5])[0]
+    if stored != 0 and unmask_crc(stored) != crc32c(data[offset:offset + size + 1]):
+        raise ValueError('table block checksum mismatch at offset %d (corrupt checkpoint index)' % offset)
     n_restarts = struct.unpack('<I', blk[-4:])[0]
     limit = size - 4 - 4 * n_restarts
     if limit < 0:
@@ -163,8 +196,10 @@ def list_variables(prefix):
     return [(k, e['shape'], _DTYPES.get(e['dtype'])) for k, e in sorted(entries.items())]
 
 
-def load_checkpoint(prefix, names=None):
-    """Reads the tensors of the checkpoint `prefix` (all of them, or those in `names`) into {name: numpy array}."""
+def load_checkpoint(prefix, names=None, verify_data=False):
+    """Reads the tensors of the checkpoint `prefix` (all of them, or those in `names`) into {name: numpy array}.
+    The masked crc32c the bundle stores per tensor (BundleEntryProto.crc32c) is verified for payloads up to 1 MB, for
+    every tensor with verify_data=True (pure-Python CRC: about 1 MB/s)."""
     entries, header = read_index(prefix + '.index')
     n = header['num_shards']
     wanted = sorted(entries) if names is None else list(names)
@@ -188,6 +223,9 @@ def load_checkpoint(prefix, names=None):
             count = int(np.prod(e['shape'])) if e['shape'] else 1
             if len(raw) != e['size'] or e['size'] != count * np.dtype(dt).itemsize:
                 raise ValueError('size mismatch for %r: %d bytes for shape %s' % (name, e['size'], (e['shape'],)))
+            if e['crc32c'] not in (None, 0) and (verify_data or len(raw) <= _CRC_VERIFY_LIMIT):
+                if unmask_crc(e['crc32c']) != crc32c(raw):
+                    raise ValueError('tensor %r: data checksum mismatch (corrupt checkpoint shard)' % name)
             out[name] = np.frombuffer(raw, dtype=np.dtype(dt).newbyteorder('<')).reshape(e['shape']).astype(dt)
     finally:
         for f in files.values():
