@@ -234,6 +234,59 @@ __global__ void __launch_bounds__(256, 3) dwconv3x3_kernel(const float* __restri
   }
 }
 
+// Input side of the inference path (datagen.py:424-476, _parse_and_preprocess): the decoded uint8 image is resized to
+// (new_w, new_h) with misc.resize_image_tf (misc.py:75-91) -- tf.image.resize_area(align_corners=True) when the image is
+// not enlarged (in_h >= new_h), tf.image.resize_bilinear(align_corners=True) otherwise -- then cropped at
+// (off_y, off_x) to crop_h x crop_w, as float32 in [0, 255].  One thread per output pixel, the three channels together.
+// resize_area (TensorFlow 1.12 core/kernels/resize_area_op.cc, restated): scale = (in - 1) / (out - 1) with
+// align_corners (in / out when out == 1); output pixel y averages the input span [y scale, (y + 1) scale): source row i
+// has weight (i < y scale ? (i + 1 > (y+1) scale ? scale : i + 1 - y scale) : (i + 1 > (y+1) scale ? (y+1) scale - i : 1)),
+// rows beyond the image are clamped to the last row; the sum is divided by scale_y scale_x.
+__global__ void __launch_bounds__(256) preprocess_u8_kernel(const uint8_t* __restrict__ src, int in_h, int in_w,
+                                                            long long src_pitch, float* __restrict__ dst, int new_h,
+                                                            int new_w, int off_y, int off_x, int crop_h, int crop_w,
+                                                            int area) {
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
+  if (ox >= crop_w || oy >= crop_h) return;
+  const int y = oy + off_y, x = ox + off_x;                    // position in the resized image
+  float r = 0.f, g = 0.f, b = 0.f;
+  if (y >= 0 && y < new_h && x >= 0 && x < new_w) {
+    const float sy = (new_h > 1) ? (float)(in_h - 1) / (float)(new_h - 1) : (float)in_h / (float)new_h;
+    const float sx = (new_w > 1) ? (float)(in_w - 1) / (float)(new_w - 1) : (float)in_w / (float)new_w;
+    if (!area) {
+      const float fy = y * sy, fx = x * sx;
+      const int y0 = (int)floorf(fy), x0 = (int)floorf(fx);
+      const int y1 = min(y0 + 1, in_h - 1), x1 = min(x0 + 1, in_w - 1);
+      const float ly = fy - y0, lx = fx - x0;
+      const uint8_t* p00 = src + y0 * src_pitch + 3 * x0; const uint8_t* p01 = src + y0 * src_pitch + 3 * x1;
+      const uint8_t* p10 = src + y1 * src_pitch + 3 * x0; const uint8_t* p11 = src + y1 * src_pitch + 3 * x1;
+      float* o[3] = {&r, &g, &b};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float top = (float)p00[c] + ((float)p01[c] - (float)p00[c]) * lx;
+        const float bot = (float)p10[c] + ((float)p11[c] - (float)p10[c]) * lx;
+        *o[c] = top + (bot - top) * ly;
+      }
+    } else {
+      const float in_y = y * sy, in_y1 = (y + 1) * sy, in_x = x * sx, in_x1 = (x + 1) * sx;
+      const int ys = (int)floorf(in_y), ye = (int)ceilf(in_y1), xs = (int)floorf(in_x), xe = (int)ceilf(in_x1);
+      const float norm = 1.0f / (sy * sx);
+      for (int i = ys; i < ye; ++i) {
+        const float wy = i < in_y ? (i + 1 > in_y1 ? sy : i + 1 - in_y) : (i + 1 > in_y1 ? in_y1 - i : 1.0f);
+        const uint8_t* row = src + (long long)min(max(i, 0), in_h - 1) * src_pitch;
+        for (int j = xs; j < xe; ++j) {
+          const float wx = j < in_x ? (j + 1 > in_x1 ? sx : j + 1 - in_x) : (j + 1 > in_x1 ? in_x1 - j : 1.0f);
+          const uint8_t* px = row + 3 * min(max(j, 0), in_w - 1);
+          const float wgt = wy * wx * norm;
+          r += (float)px[0] * wgt; g += (float)px[1] * wgt; b += (float)px[2] * wgt;
+        }
+      }
+    }
+  }
+  float* o = dst + ((long long)oy * crop_w + ox) * 3;
+  o[0] = r; o[1] = g; o[2] = b;
+}
+
 // slim.max_pool2d(3, stride 2, 'SAME') (net_resnet_v1_beta.py:187): TF pads total = max((ceil(n/2)-1)*2+3-n, 0), before =
 // floor(total/2) (0/1 for even n, 1/1 for odd n); padded taps never win the max.
 __global__ void __launch_bounds__(256) maxpool3x3_s2_kernel(const float* __restrict__ x, float* __restrict__ y_f32,
@@ -628,6 +681,33 @@ int epos_pwconv_simt(const float* a, int lda, const float* w, const float* bias,
   dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
   pwconv_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, lda, w, bias, bias_group_rows, residual, ldr, d, ldd, M,
                                                             N, K, relu);
+  EPOS_LAUNCH_CHECK();
+  return EPOS_OK;
+}
+
+int epos_preprocess_u8(const uint8_t* src, int in_h, int in_w, size_t src_pitch, int max_height_before_crop, int crop_h,
+                       int crop_w, int off_y, int off_x, const double* K_in, float* dst, double* K_out, void* stream) {
+  EPOS_CHECK_ARG(src && dst && in_h > 0 && in_w > 0 && src_pitch >= (size_t)3 * in_w && max_height_before_crop > 0);
+  EPOS_CHECK_ARG(crop_h > 0 && crop_w > 0);
+  // datagen.py:441-444: new height = min(max_height_before_crop, height), the width follows the same scale (truncated)
+  const int new_h = in_h < max_height_before_crop ? in_h : max_height_before_crop;
+  const float scale = (float)new_h / (float)in_h;
+  const int new_w = (int)((float)in_w * scale);
+  EPOS_CHECK_ARG(new_w > 0);
+  if (off_y < 0 || off_x < 0 || off_y + crop_h > new_h || off_x + crop_w > new_w) {
+    set_error("epos_preprocess_u8: crop %dx%d at (%d,%d) does not fit the resized image %dx%d (datagen.py:451-459 requires it)",
+              crop_w, crop_h, off_x, off_y, new_w, new_h);
+    return EPOS_ERR_INVALID_ARG;
+  }
+  if (K_in && K_out) {                                          // datagen.py:461-467 (float32 arithmetic in the reference)
+    const float fx = (float)K_in[0] * scale, fy = (float)K_in[4] * scale;
+    const float cx = (float)K_in[2] * scale - (float)off_x, cy = (float)K_in[5] * scale - (float)off_y;
+    const double Ko[9] = {fx, 0.0, cx, 0.0, fy, cy, 0.0, 0.0, 1.0};
+    for (int i = 0; i < 9; ++i) K_out[i] = Ko[i];
+  }
+  dim3 grid(ceil_div(crop_w, 256), crop_h);
+  preprocess_u8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, in_h, in_w, (long long)src_pitch, dst, new_h, new_w, off_y,
+                                                              off_x, crop_h, crop_w, in_h >= new_h ? 1 : 0);
   EPOS_LAUNCH_CHECK();
   return EPOS_OK;
 }

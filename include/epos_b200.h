@@ -137,6 +137,17 @@ int epos_resize_bilinear(const float* x, float* y, int ldy, int B, int Hi, int W
  * argmax as int64 (model.py:683). */
 int epos_softmax_rows(float* x, int64_t* labels, size_t rows, int n, void* stream);
 
+/* Input side (datagen.py:424-476 _parse_and_preprocess, misc.py:75-91 resize_image_tf, misc.py:110-147 crop_image): a
+ * decoded uint8 RGB image src [in_h][src_pitch bytes] (device) is resized so that its height is
+ * min(max_height_before_crop, in_h) -- tf.image.resize_area(align_corners=True) when not enlarged, resize_bilinear
+ * otherwise -- and cropped at (off_y, off_x) to dst [crop_h][crop_w][3] f32 in [0,255] (the layout model.predict takes).
+ * K_in / K_out [9] (HOST, row-major; may be NULL): the intrinsics follow the image, f' = f s, c' = c s - offset with
+ * s = new_h / in_h (datagen.py:461-467).  The reference draws the crop offset uniformly (datagen.py:451-455); the
+ * caller passes it (for a 640x480 source it is 0).  Image file decoding stays on the host. */
+int epos_preprocess_u8(const uint8_t* src, int in_h, int in_w, size_t src_pitch, int max_height_before_crop,
+                       int crop_h, int crop_w, int off_y, int off_x, const double* K_in, float* dst, double* K_out,
+                       void* stream);
+
 /* ---- correspondences: replaces corresp.establish_many_to_many (epos_lib/corresp.py:9-101) and the
  * top-K selection of scripts/infer.py:425-440 ------------------------------------------------------ */
 
