@@ -22,7 +22,7 @@ class Engine:
 
     def __init__(self, weights, num_objs, num_frags, device, stages=STAGES_CNN, model_store=None, K=None,
                  fit_params=None, max_correspondences=4096, seed=0, min_obj_conf=0.1, min_frag_rel_conf=0.5,
-                 model_options=None, pipelined=False, post_fit=None, lazy_loc=True, multi_params=None):
+                 model_options=None, pipelined=False, post_fit=None, lazy_loc=True, multi_params=None, graphs=False):
         self.dev = torch.device(device)
         self.net = model.EposNet(weights, num_objs, num_frags, self.dev, model_options=model_options)
         self.O, self.F = num_objs, num_frags
@@ -43,6 +43,13 @@ class Engine:
         self._inflight = []                      # (maps kept alive, event after corresp) of batches still on the side stream
         self._last_fit = None                    # event after the most recent fit
         self._pending_host = None                # (pinned result, event) of the previous run_host call
+        # graphs=True: the per-batch pipeline is captured once per input shape into CUDA graphs (two buffer sets: the CNN
+        # of batch i+1 writes set (i+1) % 2 while correspondences / pose fitting of batch i read set i % 2) and replayed;
+        # the host then issues ~4 launches per batch instead of ~170 kernel launches and ~200 allocations
+        self.graphs = bool(graphs)
+        self._gsets = {}                         # (B, H, W) -> [GraphSet, GraphSet]
+        self._gturn = 0
+        self.graph_launches = 0                  # kernel launches replayed through graphs (bench.py's gpu_launches)
         if stages == STAGES_FULL:
             from . import posefit
             self._fitter = posefit.BatchFitter(self.dev, num_objs, num_frags, model_store, K, fit_params,
@@ -57,6 +64,106 @@ class Engine:
         if self.post_fit is not None:
             out['poses_all'] = self.post_fit(poses)
 
+    # ---- CUDA-graph mode -------------------------------------------------------------------------------------
+    def _capture(self, shape, K):
+        """Two buffer sets for input shape (B, H, W, 3): static input, CNN graph (main stream) and, for the full path, a
+        post-processing graph (correspondences + pose fitting; side stream)."""
+        lib = _lib.lib()
+        B = shape[0]
+        bi0 = 0
+        if self._fitter is not None:
+            self._fitter._prepare(B, K)
+            bi0 = self._fitter.batch_index
+        side = self._side if self._side is not None else torch.cuda.Stream(device=self.dev)
+        self._side = side
+        warm = torch.zeros(shape, dtype=torch.float32, device=self.dev)
+        # eager warm-up on the capture stream: one-time initialisation (kernel attributes, scheduler ring, TMA encoder)
+        cap = torch.cuda.Stream(device=self.dev)
+        cap.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(cap):
+            out = self.net.predict(warm, lazy_loc=self.lazy_loc)
+            if self._fitter is not None:
+                self._fitter.fit(out)
+        cap.synchronize()
+        sets = []
+        pool = None
+        for s in range(2):
+            gs = {'x': torch.zeros(shape, dtype=torch.float32, device=self.dev)}
+            g = torch.cuda.CUDAGraph()
+            l0 = lib.epos_launch_count()
+            with torch.cuda.graph(g, pool=pool, stream=cap, capture_error_mode='thread_local'):
+                gs['out'] = self.net.predict(gs['x'], lazy_loc=self.lazy_loc)
+            gs['cnn'] = g
+            gs['cnn_launches'] = int(lib.epos_launch_count() - l0)
+            pool = g.pool()                      # the two CNN graphs replay in order on one stream: shared private pool
+            gs['post'] = None
+            gs['post_launches'] = 0
+            if self._fitter is not None:
+                gp = torch.cuda.CUDAGraph()
+                l0 = lib.epos_launch_count()
+                with torch.cuda.graph(gp, stream=cap, capture_error_mode='thread_local'):
+                    gs['poses'] = self._fitter.fit(gs['out']).clone()
+                gs['post'] = gp
+                gs['post_launches'] = int(lib.epos_launch_count() - l0)
+            gs['ev_cnn'] = torch.cuda.Event()
+            gs['ev_post'] = torch.cuda.Event()
+            sets.append(gs)
+        # the warm-up and the captures advanced the host-side counter only; the device-side batch counter restarts here
+        if self._fitter is not None:
+            self._fitter.batch_index = bi0
+            with torch.cuda.stream(cap):
+                self._fitter._batch_dev.fill_(bi0)
+        torch.cuda.current_stream(self.dev).wait_stream(cap)
+        return sets
+
+    def _run_graph(self, images, K=None, from_host=False):
+        """One batch through the captured graphs.  images: device tensor, or pinned host tensor with from_host=True
+        (copied straight into the static input on the copy stream)."""
+        shape = tuple(images.shape)
+        key = shape[:3]
+        if key not in self._gsets:
+            self._gsets[key] = self._capture(shape, K)
+        gs = self._gsets[key][self._gturn % 2]
+        self._gturn += 1
+        main = torch.cuda.current_stream(self.dev)
+        if self._fitter is not None:
+            self._fitter._prepare(shape[0], K)   # refreshes the intrinsics of this batch if they changed (outside the graph)
+        main.wait_event(gs['ev_post'])           # batch i-2 has finished reading this set's head maps / poses
+        if from_host and self._copy is not None:
+            with torch.cuda.stream(self._copy):
+                self._copy.wait_event(gs['ev_cnn'])          # the CNN of batch i-2 has consumed the static input
+                self._copy.wait_event(gs['ev_post'])
+                gs['x'].copy_(images, non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(self._copy)
+            main.wait_event(ev_in)
+        else:
+            gs['x'].copy_(images, non_blocking=True)
+        gs['cnn'].replay()
+        gs['ev_cnn'].record(main)
+        self.graph_launches += gs['cnn_launches']
+        out = dict(gs['out'])
+        if gs['post'] is None:
+            gs['ev_post'].record(main)
+            return out
+        post_stream = self._side if self.pipelined else main
+        with torch.cuda.stream(post_stream):
+            post_stream.wait_event(gs['ev_cnn'])
+            gs['post'].replay()
+            self._fitter.batch_index += 1
+            self.graph_launches += gs['post_launches']
+            out['poses'] = gs['poses']
+            if self.post_fit is not None:
+                out['poses_all'] = self.post_fit(gs['poses'])
+            gs['ev_post'].record(post_stream)
+        self._last_fit = gs['ev_post']
+        out['ready'] = gs['ev_post']
+        return out
+
+    def launch_count(self):
+        """Kernels of this library launched so far, including those replayed through CUDA graphs."""
+        return int(_lib.lib().epos_launch_count()) + self.graph_launches
+
     def run_device(self, images_dev, K=None, num_instances=None):
         """images_dev [B,H,W,3] f32 CUDA; K = this batch's camera intrinsics, [3,3] or [B,3,3] (default: the K given
         at construction -- the reference reads K per image, scripts/infer.py:376-377).  Returns a dict of CUDA tensors:
@@ -64,6 +171,8 @@ class Engine:
         after join() / out['ready']).  num_instances [B,J]: instance bound per (image, object slot) as in
         scripts/infer.py:462-468 (0 = skip, 1 = GC-RANSAC, 2.. = Progressive-X, -1 = all); out['multi'] then holds every
         instance of the Progressive-X problems."""
+        if self.graphs and num_instances is None:
+            return self._run_graph(images_dev, K)
         out = self.net.predict(images_dev, lazy_loc=self.lazy_loc)
         if self._fitter is None:
             return out
@@ -107,6 +216,24 @@ class Engine:
         Serial engine: returns this batch's result.  Pipelined engine: the D2H of this batch is queued behind its pose
         fitting on the side stream and the call returns the PREVIOUS batch's result (None on the first call); flush()
         returns the last one -- the host always holds batch i while the GPU works on batch i+1."""
+        if self.graphs:
+            out = self._run_graph(images_pinned, K, from_host=True)
+            r = self.result_tensor(out)
+            if not self.pipelined:
+                if result_pinned is None:
+                    return r.cpu()
+                result_pinned.copy_(r, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                return result_pinned
+            prev = self.flush()
+            buf = torch.empty(r.shape, dtype=r.dtype).pin_memory() if result_pinned is None else result_pinned
+            with torch.cuda.stream(self._side):
+                buf.copy_(r, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._side)
+                out['ready'].record(self._side)      # the next user of this buffer set also waits for the read-back
+            self._pending_host = (buf, ev)
+            return prev
         if self.pipelined:
             # the copy engine brings batch i+1 in while the SMs are still busy with batch i
             main = torch.cuda.current_stream(self.dev)

@@ -132,6 +132,7 @@ class BatchFitter:
         self._Khost = None
         self._P = 0
         self.batch_index = 0
+        self._batch_dev = None
 
     def _prepare(self, B, K=None):
         """Buffers for B images and the intrinsics of this batch.  The reference reads K per image
@@ -146,7 +147,10 @@ class BatchFitter:
             self._Khost = None
             self._poses = torch.empty((P, 16), dtype=torch.float64, device=self.dev)
             self._labeling = torch.empty((P * self.extract.cap,), dtype=torch.int32, device=self.dev)
-            self._base = torch.arange(P, dtype=torch.int64, device=self.dev)
+            self._base = torch.arange(P, dtype=torch.int64, device=self.dev) + (self.seed << 32)
+        if self._batch_dev is None:
+            # the batch counter of the stream keys lives on the device so that a captured CUDA graph advances it itself
+            self._batch_dev = torch.full((1,), self.batch_index, dtype=torch.int64, device=self.dev)
         K = self.K if K is None else np.asarray(K, np.float64)
         if K is None:
             raise ValueError('camera intrinsics K are required ([3,3] or [B,3,3])')
@@ -160,8 +164,11 @@ class BatchFitter:
             self._Kdev.copy_(torch.from_numpy(rows), non_blocking=False)
 
     def seeds_for(self, B):
-        """Stream key of problem (image b, slot j) in batch n: seed * 2^32 + n * P + b * J + j."""
-        return self._base + (self.seed << 32) + self.batch_index * (B * self.J)
+        """Stream key of problem (image b, slot j) in batch n: seed * 2^32 + n * P + b * J + j.  Advances the device-side
+        batch counter (graph-capturable: no host value is baked in)."""
+        seeds = self._base + self._batch_dev * (B * self.J)
+        self._batch_dev += 1
+        return seeds
 
     def fit_maps(self, obj_conf, frag_conf, frag_loc, after_extract=None, K=None, lazy_loc=None, num_instances=None):
         """num_instances [B, J] (host ints; None = 1 everywhere) is the `num_instances` of scripts/infer.py:462-468 per

