@@ -126,8 +126,6 @@ class Engine:
         gs = self._gsets[key][self._gturn % 2]
         self._gturn += 1
         main = torch.cuda.current_stream(self.dev)
-        if self._fitter is not None:
-            self._fitter._prepare(shape[0], K)   # refreshes the intrinsics of this batch if they changed (outside the graph)
         main.wait_event(gs['ev_post'])           # batch i-2 has finished reading this set's head maps / poses
         if from_host and self._copy is not None:
             with torch.cuda.stream(self._copy):
@@ -149,6 +147,8 @@ class Engine:
         post_stream = self._side if self.pipelined else main
         with torch.cuda.stream(post_stream):
             post_stream.wait_event(gs['ev_cnn'])
+            # intrinsics of this batch (outside the graph, on the stream of the fit: ordered behind the previous batch's fit)
+            self._fitter._prepare(shape[0], K)
             gs['post'].replay()
             self._fitter.batch_index += 1
             self.graph_launches += gs['post_launches']

@@ -161,7 +161,10 @@ class BatchFitter:
         if self._Khost is None or not np.array_equal(self._Khost, K):
             self._Khost = np.array(K, np.float64)
             rows = np.ascontiguousarray(np.repeat(self._Khost.reshape(B, 9), self.J, axis=0))
-            self._Kdev.copy_(torch.from_numpy(rows), non_blocking=False)
+            # asynchronous, ordered on the CURRENT stream behind the fit of the previous batch (which may still read the old
+            # values); the pinned staging buffer is kept alive until the next change
+            self._Kpin = torch.from_numpy(rows).pin_memory()
+            self._Kdev.copy_(self._Kpin, non_blocking=True)
 
     def seeds_for(self, B):
         """Stream key of problem (image b, slot j) in batch n: seed * 2^32 + n * P + b * J + j.  Advances the device-side
