@@ -66,6 +66,8 @@ def parse_args():
     ap.add_argument('--cpu-images', type=int, default=3, help='images in the cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--serial', action='store_true', help='no CNN / pose-fitting overlap (single stream)')
+    ap.add_argument('--no-graphs', dest='graphs', action='store_false', default=True,
+                    help='launch every kernel from Python instead of replaying the captured CUDA graphs')
     ap.add_argument('--secondary', dest='secondary', action='store_true', default=None,
                     help='also time BASELINE configs[3] (ResNet-50-beta, 8/GPU) and configs[4] (30x256, 2000 iterations, '
                          '16/GPU) for a few steps each (default: on when no workload flag is given)')
@@ -225,7 +227,7 @@ class Cfg:
         self.backbone, self.max_iters, self.steps, self.warmup = backbone, max_iters, steps, warmup
 
 
-def measure(cfg, ctx, serial=False, want_roofline=True):
+def measure(cfg, ctx, serial=False, want_roofline=True, graphs=True):
     """Builds the engine for `cfg`, times `value` (device-resident inputs) and `e2e` (host buffers) over exactly
     cfg.steps steps after cfg.warmup warm-up steps, max over ranks; rank 0 also measures the rooflines of the two
     dominant kernels (tcgen05 GEMM: tensor; fit_kernel: HBM on algorithmic bytes).  Returns a dict (rank 0) / None."""
@@ -254,7 +256,7 @@ def measure(cfg, ctx, serial=False, want_roofline=True):
         fit_params.max_iters = cfg.max_iters
     eng = engine.Engine(w, O, F, dev, stages=engine.STAGES_FULL if kind == 'full' else engine.STAGES_CNN,
                         model_store=store, K=K, seed=1234 + rank, max_correspondences=MAX_CORR, model_options=opts,
-                        fit_params=fit_params, pipelined=not serial,
+                        fit_params=fit_params, pipelined=not serial, graphs=graphs,
                         post_fit=(lambda poses: edist.all_gather_poses(poses, world, group=side_group)) if world > 1 else None)
     del w
 
@@ -283,7 +285,7 @@ def measure(cfg, ctx, serial=False, want_roofline=True):
         out = eng.run_device(dev_batches[i % NROT])
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    l0 = lib.epos_launch_count()
+    l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(cfg.steps):
@@ -291,7 +293,7 @@ def measure(cfg, ctx, serial=False, want_roofline=True):
     eng.join()                         # the timed region ends when the last batch's pose records (and all-gather) are done
     e1.record()
     barrier()
-    launches = int(lib.epos_launch_count() - l0)
+    launches = int(eng.launch_count() - l0)          # kernels replayed through CUDA graphs included
     clocks = sampler.stop() if sampler else None
     ms = max_over_ranks(e0.elapsed_time(e1))
     value = world * B * cfg.steps / (ms * 1e-3)
@@ -330,6 +332,7 @@ def measure(cfg, ctx, serial=False, want_roofline=True):
         eng.net.gemm_events = []
         nat = max(1, min(cfg.steps, 5))
         was_pipelined, eng.pipelined = eng.pipelined, False       # kernel timed alone: no pose-fitting CTAs beside it
+        was_graphs, eng.graphs = eng.graphs, False                # per-launch events need eager launches
         post_fit, eng.post_fit = eng.post_fit, None               # rank 0 only: no collective in this pass
         fit_ms = fit_bytes = prep_ms = 0.0
         if kind == 'full':
@@ -345,7 +348,7 @@ def measure(cfg, ctx, serial=False, want_roofline=True):
         torch.cuda.synchronize()
         if kind == 'full':
             _lib.check(lib.epos_fit_enable_timing(0), 'epos_fit_enable_timing')
-        eng.pipelined, eng.post_fit = was_pipelined, post_fit
+        eng.pipelined, eng.post_fit, eng.graphs = was_pipelined, post_fit, was_graphs
         evs, eng.net.gemm_events = eng.net.gemm_events, None
         gemm_ms = sum(a.elapsed_time(b) for a, b, _, _, _ in evs)
         gemm_flop = sum(2.0 * m * n * k for _, _, m, n, k in evs)
@@ -405,6 +408,8 @@ def measure(cfg, ctx, serial=False, want_roofline=True):
                           'parallelism': 'image-sharded dp%d' % world,
                           'pipeline': 'pose fitting of batch i on a side stream under the CNN of batch i+1'
                                       if eng.pipelined else 'serial',
+                          'launch': 'CUDA graphs (CNN graph + post-processing graph per buffer set, replayed)'
+                                    if eng.graphs else 'eager (one ctypes launch per kernel)',
                           'parity_pin': 'pose: reference golden vectors (pnp16 / pose6dscene / tless / cv2 / BK max-flow); '
                                         'CNN: Slim conv2d_same / atrous vectors only (the reference holds no network-level '
                                         'vector; TF-1.12 not installable)'}}
@@ -434,16 +439,17 @@ def run_ours(args, kind):
     side_group = dist.new_group(backend='nccl') if world > 1 else None
     ctx = {'world': world, 'rank': rank, 'local': local, 'dev': dev, 'lib': _lib.lib(), 'side_group': side_group}
     B, O, F = args.batch, args.objs, args.frags
-    primary = measure(Cfg(kind, B, O, F, args.backbone, args.max_iters, args.steps, args.warmup), ctx, serial=args.serial)
+    primary = measure(Cfg(kind, B, O, F, args.backbone, args.max_iters, args.steps, args.warmup), ctx, serial=args.serial,
+                      graphs=args.graphs)
 
     # ---- the other multi-GPU configs of BASELINE.json at their per-GPU shapes (short runs, same timing rules) ----
     secondary = None
     if args.secondary and kind == 'full':
-        sw, ss = max(3, min(args.warmup, 3)), max(3, min(args.steps, 6))
+        sw, ss = max(3, min(args.warmup, 3)), max(3, min(args.steps, 10))
         secondary = {}
         for name, cfg in (('configs[3]', Cfg('full', 8, 21, 64, 'resnet_v1_50_beta', 400, ss, sw)),
                           ('configs[4]', Cfg('full', 16, 30, 256, 'xception_65', 2000, ss, sw))):
-            r = measure(cfg, ctx, serial=args.serial)
+            r = measure(cfg, ctx, serial=args.serial, graphs=args.graphs)
             if rank == 0:
                 r['metric'], r['unit'], r['n_gpus'] = 'images/sec', 'images/s', world
                 secondary[name] = r
