@@ -747,6 +747,13 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const CUten
   return EPOS_OK;
 }
 
+// K block of a launch: 64 bf16 everywhere; EPOS_GEMM_BK=32 (developer switch) halves it for the pointwise 256-column tiles
+static int gemm_bk_for(int bn, int conv) {
+  static int env = -1;
+  if (env < 0) { const char* e = getenv("EPOS_GEMM_BK"); env = e ? atoi(e) : 64; }
+  return (env == 32 && bn == 256 && !conv) ? 32 : GEMM_BK;
+}
+
 // W maps, epilogue descriptor and dispatch on the N tile shared by the pointwise and the 3x3 entry points.
 // K block = 64 bf16 (128-byte swizzle, 2 smem stages at BLOCK_N = 256).  A 32-wide K block (64-byte swizzle, 4 stages)
 // was measured 4-15 % slower on B200: the main loop is bound by L2->SM throughput, not by pipeline depth.
@@ -769,11 +776,14 @@ static int run_gemm(const CUtensorMap& ma, const uint16_t* w_split, int ldw, con
   if (pair_env < 0) { const char* e = getenv("EPOS_GEMM_PAIR"); pair_env = e ? atoi(e) : 1; }
   const long long m_tiles = cg.enabled ? (long long)(M / (cg.H * cg.W)) * cg.tiles_x * cg.tiles_y : ceil_div(M, BLOCK_M);
   const bool pair = pair_env && bn == 256 && m_tiles >= 2 && (K >= 1024 || pair_env == 2);
+  // developer A/B (scripts/dev_gemm.py): EPOS_GEMM_BK=32 runs the 256-column tiles with a 32-wide K block (64-byte swizzle,
+  // twice the pipeline depth); the caller's A map must then be built with the same K block (epos_pwconv_gemm does)
+  const int bk = gemm_bk_for(bn, cg.enabled);
   CUtensorMap mw, mw64;
-  int rc = make_map(&mw, w_split, N, K, ldw, (size_t)N * ldw, pair ? bn / 2 : bn, GEMM_BK, 2);
+  int rc = make_map(&mw, w_split, N, K, ldw, (size_t)N * ldw, pair ? bn / 2 : bn, bk, 2);
   if (rc) return rc;
-  rc = pair ? make_map(&mw64, w_split, N, K, ldw, (size_t)N * ldw, 32, GEMM_BK, 2)
-            : make_map(&mw64, w_split, N, K, ldw, (size_t)N * ldw, bn < 64 ? bn : 64, GEMM_BK, 1);
+  rc = pair ? make_map(&mw64, w_split, N, K, ldw, (size_t)N * ldw, 32, bk, 2)
+            : make_map(&mw64, w_split, N, K, ldw, (size_t)N * ldw, bn < 64 ? bn : 64, bk, 1);
   if (rc) return rc;
   GemmEpilogue ep;
   ep.bias = bias; ep.residual = residual; ep.d_f32 = d_f32; ep.d_split = d_split;
@@ -783,6 +793,10 @@ static int run_gemm(const CUtensorMap& ma, const uint16_t* w_split, int ldw, con
     // fused softmax needs whole 64-column groups per piece and the aligned fast path; f32 output only
     EPOS_CHECK_ARG(d_f32 && !d_split && !residual && bias_group_rows == 0 && (N % 64) == 0 && (ldd % 4) == 0 &&
                    (reinterpret_cast<uintptr_t>(d_f32) & 15) == 0 && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0));
+  }
+  if (bk == 32) {
+    if (pair) return launch_gemm<256, 32, true>(ma, mw, mw64, ep, cg, M, N, K, s, dbg);
+    return launch_gemm<256, 32, false>(ma, mw, mw64, ep, cg, M, N, K, s, dbg);
   }
   if (pair) return launch_gemm<256, GEMM_BK, true>(ma, mw, mw64, ep, cg, M, N, K, s, dbg);
   switch (bn) {
@@ -825,7 +839,8 @@ extern "C" int epos_pwconv_gemm(const uint16_t* a_split, int lda, size_t a_plane
   EPOS_CHECK_ARG(lda >= K && (lda % 8) == 0 && (K % 8) == 0 && (a_plane_stride % 8) == 0);
   EPOS_CHECK_ARG((reinterpret_cast<uintptr_t>(a_split) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_split) & 15) == 0);
   CUtensorMap ma;
-  int rc = make_map(&ma, a_split, M, K, lda, a_plane_stride, BLOCK_M, GEMM_BK, 2);
+  const int bn_ = N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
+  int rc = make_map(&ma, a_split, M, K, lda, a_plane_stride, BLOCK_M, gemm_bk_for(bn_, 0), 2);
   if (rc) return rc;
   ConvGeom cg = {};
   return run_gemm(ma, w_split, ldw, bias, bias_group_rows, residual, ldr, d_f32, ldd, d_split, ldd_split, d_plane_stride, cg,
