@@ -10,6 +10,7 @@
 //            then a shared-memory bitonic sort of the K survivors
 //   phase 3  rows: coord_2d = (x + 0.5, y + 0.5) / output_scale (misc.py:14-26), coord_3d = centre[f] +
 //            f32(loc * size[f]) (corresp.py:70-78), conf = obj_conf * frag_conf
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace epos {
@@ -344,6 +345,348 @@ __global__ void __launch_bounds__(CT, 1) corresp_kernel(CorrArgs a) {
   if (!a.frag_loc) { __syncthreads(); lazy_loc_rows(a, b, obj_id, seg_base, n); }
 }
 
+
+// =====================================================================================================
+// Grid-wide pipeline (default).  The single-CTA-per-segment kernel above leaves the GPU to a handful of CTAs: the heavy
+// segments (tens of thousands of candidate rows, radix select over several passes) run on ONE SM each while the other
+// 140 idle, and all J CTAs of an image re-scan obj_conf with an (O+1)-float stride.  Here every stage is spread over the
+// whole grid and obj_conf is read once per image:
+//   rows     thread per pixel: the pixel's obj_conf row once; for every object slot above tau_a the F-float frag_conf row
+//            -> row max and number of selected fragments, dense per (segment, pixel)
+//   scan     CTA per segment: exclusive scan of the counts = emission offsets (row-major pixel, then fragment), totals,
+//            top-K decision
+//   emit     thread per (segment, pixel): rows of the segments that keep everything
+//   hist/pick (x6, top-K segments only) radix select of the max_corr largest 64-bit keys (conf bits << 32 | emission
+//            index) with per-CTA shared-memory histograms merged into a global one; later digits stop early as before
+//   gather   survivors (key >= K-th key) -> per-segment list;  sort   CTA per segment: bitonic sort, rows in descending order
+//   loc      (lazy localisation head) warp per emitted row over all segments
+// Results are bit-identical to the kernel above (same keys, same order).
+// =====================================================================================================
+struct SegState {
+  unsigned long long prefix, maskbits;
+  int need, tie_count, topk, done, sel_count, total, pad0, pad1;
+};
+
+struct Corr2 {
+  CorrArgs a;
+  unsigned int* cnt;        // [S][HW+1] selected fragments per (segment, pixel)
+  unsigned int* off;        // [S][HW+1] exclusive scan; off[HW] = total
+  float* rmax;              // [S][HW+1]
+  unsigned int* hist;       // [S][2048]
+  SegState* state;          // [S]
+  unsigned long long* sel_keys;   // [S][SORT_MAX]
+  unsigned int* sel_payload;      // [S][SORT_MAX]
+};
+
+__global__ void __launch_bounds__(128) corr2_rows_kernel(Corr2 c) {
+  __shared__ int s_ids[64];
+  const CorrArgs& a = c.a;
+  const int HW = a.h * a.w, b = blockIdx.y;
+  for (int j = threadIdx.x; j < a.J; j += 128) s_ids[j] = a.obj_ids[j];
+  __syncthreads();
+  const int p = blockIdx.x * 128 + threadIdx.x;
+  if (p >= HW) return;
+  const float* oc = a.obj_conf + ((size_t)b * HW + p) * (a.O + 1);
+  const bool vec = (a.F % 4 == 0);
+  for (int j = 0; j < a.J; ++j) {
+    const int obj_id = s_ids[j];
+    const size_t si = ((size_t)b * a.J + j) * (HW + 1) + p;
+    unsigned int n = 0;
+    if (obj_id >= 1 && obj_id <= a.O && __ldg(oc + obj_id) > a.min_obj_conf) {
+      const float* row = a.frag_conf + (((size_t)b * HW + p) * a.O + (obj_id - 1)) * a.F;
+      float mx = -INFINITY;
+      if (vec) {
+        for (int f = 0; f < a.F; f += 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(row + f));
+          mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+        }
+      } else {
+        for (int f = 0; f < a.F; ++f) mx = fmaxf(mx, __ldg(row + f));
+      }
+      const float thr = __fmul_rn(mx, a.min_rel);
+      if (vec) {
+        for (int f = 0; f < a.F; f += 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(row + f));
+          n += (v.x > thr) + (v.y > thr) + (v.z > thr) + (v.w > thr);
+        }
+      } else {
+        for (int f = 0; f < a.F; ++f) n += (__ldg(row + f) > thr);
+      }
+      c.rmax[si] = mx;
+    }
+    c.cnt[si] = n;
+  }
+}
+
+__global__ void __launch_bounds__(CT, 1) corr2_scan_kernel(Corr2 c) {
+  __shared__ int scan_sh[CW + 1];
+  const CorrArgs& a = c.a;
+  const int seg = blockIdx.x, tid = threadIdx.x, HW = a.h * a.w;
+  const unsigned int* cnt = c.cnt + (size_t)seg * (HW + 1);
+  unsigned int* off = c.off + (size_t)seg * (HW + 1);
+  const int per = (HW + CT - 1) / CT;
+  const int lo = min(tid * per, HW), hi = min(lo + per, HW);
+  int s = 0;
+  for (int i = lo; i < hi; ++i) s += (int)cnt[i];
+  int total;
+  int base = block_scan_excl(s, scan_sh, &total);
+  for (int i = lo; i < hi; ++i) { off[i] = (unsigned int)base; base += (int)cnt[i]; }
+  for (int i = tid; i < 2048; i += CT) c.hist[(size_t)seg * 2048 + i] = 0u;
+  if (tid == 0) {
+    off[HW] = (unsigned int)total;
+    const bool topk = a.max_corr > 0 && total > a.max_corr;
+    const int n = topk ? (a.max_corr < a.cap ? a.max_corr : a.cap) : (total < a.cap ? total : a.cap);
+    a.counts[seg] = n;
+    if (a.totals) a.totals[seg] = total;
+    SegState st;
+    st.prefix = 0ULL; st.maskbits = 0ULL; st.need = a.max_corr; st.tie_count = 0; st.topk = topk ? 1 : 0; st.done = 0;
+    st.sel_count = 0; st.total = total; st.pad0 = st.pad1 = 0;
+    c.state[seg] = st;
+  }
+}
+
+// visits the selected fragments of (segment, pixel): fn(f, e, vfrag)
+template <class Fn>
+__device__ __forceinline__ void corr2_candidates(const Corr2& c, int b, int obj_id, int seg, int p, Fn fn) {
+  const CorrArgs& a = c.a;
+  const int HW = a.h * a.w;
+  const size_t si = (size_t)seg * (HW + 1) + p;
+  if (c.cnt[si] == 0) return;
+  unsigned int e = c.off[si];
+  const float thr = __fmul_rn(c.rmax[si], a.min_rel);
+  const float* row = a.frag_conf + (((size_t)b * HW + p) * a.O + (obj_id - 1)) * a.F;
+  if (a.F % 4 == 0) {
+    for (int f = 0; f < a.F; f += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(row + f));
+      if (v.x > thr) fn(f, e++, v.x);
+      if (v.y > thr) fn(f + 1, e++, v.y);
+      if (v.z > thr) fn(f + 2, e++, v.z);
+      if (v.w > thr) fn(f + 3, e++, v.w);
+    }
+  } else {
+    for (int f = 0; f < a.F; ++f) {
+      const float v = __ldg(row + f);
+      if (v > thr) fn(f, e++, v);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) corr2_emit_kernel(Corr2 c) {
+  const CorrArgs& a = c.a;
+  const int seg = blockIdx.y, HW = a.h * a.w;
+  if (c.state[seg].topk) return;
+  const int p = blockIdx.x * 128 + threadIdx.x;
+  if (p >= HW) return;
+  const int b = seg / a.J, obj_id = a.obj_ids[seg % a.J];
+  if (obj_id < 1 || obj_id > a.O) return;
+  const size_t seg_base = (size_t)seg * a.cap;
+  float vobj = 0.f;
+  bool have = false;
+  corr2_candidates(c, b, obj_id, seg, p, [&](int f, unsigned int e, float vf) {
+    if (!have) { vobj = __ldg(a.obj_conf + ((size_t)b * HW + p) * (a.O + 1) + obj_id); have = true; }
+    if ((int)e < a.cap) write_row(a, b, obj_id, seg_base + e, p, f, vobj, vf);
+  });
+}
+
+__constant__ int c2_shifts[6] = {53, 42, 32, 21, 10, 0};
+__constant__ int c2_widths[6] = {11, 11, 10, 11, 11, 10};
+
+__global__ void __launch_bounds__(256) corr2_hist_kernel(Corr2 c, int d) {
+  __shared__ unsigned int sh[2048];
+  const CorrArgs& a = c.a;
+  const int seg = blockIdx.y, HW = a.h * a.w;
+  const SegState st = c.state[seg];
+  if (!st.topk || st.done) return;
+  for (int i = threadIdx.x; i < 2048; i += 256) sh[i] = 0u;
+  __syncthreads();
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  const int b = seg / a.J, obj_id = a.obj_ids[seg % a.J];
+  const int sh_ = c2_shifts[d], wd = c2_widths[d];
+  if (p < HW && obj_id >= 1 && obj_id <= a.O) {
+    float vobj = 0.f;
+    bool have = false;
+    corr2_candidates(c, b, obj_id, seg, p, [&](int, unsigned int e, float vf) {
+      if (!have) { vobj = __ldg(a.obj_conf + ((size_t)b * HW + p) * (a.O + 1) + obj_id); have = true; }
+      const unsigned long long key = make_key(vobj, vf, e);
+      if ((key & st.maskbits) == st.prefix) atomicAdd(&sh[(unsigned int)(key >> sh_) & ((1u << wd) - 1u)], 1u);
+    });
+  }
+  __syncthreads();
+  unsigned int* gh = c.hist + (size_t)seg * 2048;
+  for (int i = threadIdx.x; i < 2048; i += 256)
+    if (sh[i]) atomicAdd(&gh[i], sh[i]);
+}
+
+__global__ void __launch_bounds__(CT, 1) corr2_pick_kernel(Corr2 c, int d) {
+  __shared__ int scan_sh[CW + 1];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_need;
+  const int seg = blockIdx.x, tid = threadIdx.x;
+  SegState* stp = c.state + seg;
+  const SegState st = *stp;
+  if (!st.topk || st.done) return;
+  unsigned int* hist = c.hist + (size_t)seg * 2048;
+  const int sh_ = c2_shifts[d], wd = c2_widths[d];
+  if (tid == 0) { s_prefix = st.prefix; s_need = st.need; }
+  int cb[4];
+  int csum = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { cb[q] = (int)hist[2047 - 4 * tid - q]; csum += cb[q]; }
+  int tot2;
+  int above = block_scan_excl(csum, scan_sh, &tot2);
+  const int need = st.need;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (above < need && need <= above + cb[q]) {
+      s_prefix = st.prefix | ((unsigned long long)(2047 - 4 * tid - q) << sh_);
+      s_need = need - above;
+    }
+    above += cb[q];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    stp->prefix = s_prefix; stp->need = s_need;
+    stp->maskbits = st.maskbits | (((1ULL << wd) - 1ULL) << sh_);
+    if (d == 2) {
+      // rows whose confidence equals the K-th one: if all of them are needed the index digits are not (ties are all kept)
+      const int ties = (int)hist[(unsigned int)(s_prefix >> sh_) & ((1u << wd) - 1u)];
+      stp->tie_count = ties;
+      if (s_need == ties) stp->done = 1;
+    }
+    if (d == 5) stp->done = 1;
+  }
+  __syncthreads();
+  for (int i = tid; i < 2048; i += CT) hist[i] = 0u;
+}
+
+__global__ void __launch_bounds__(256) corr2_gather_kernel(Corr2 c) {
+  const CorrArgs& a = c.a;
+  const int seg = blockIdx.y, HW = a.h * a.w;
+  const SegState st = c.state[seg];
+  if (!st.topk) return;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  const int b = seg / a.J, obj_id = a.obj_ids[seg % a.J];
+  if (p >= HW || obj_id < 1 || obj_id > a.O) return;
+  const unsigned long long kth = st.prefix;
+  float vobj = 0.f;
+  bool have = false;
+  corr2_candidates(c, b, obj_id, seg, p, [&](int f, unsigned int e, float vf) {
+    if (!have) { vobj = __ldg(a.obj_conf + ((size_t)b * HW + p) * (a.O + 1) + obj_id); have = true; }
+    const unsigned long long key = make_key(vobj, vf, e);
+    if (key >= kth) {
+      const int slot = atomicAdd(&c.state[seg].sel_count, 1);
+      if (slot < SORT_MAX) {
+        c.sel_keys[(size_t)seg * SORT_MAX + slot] = key;
+        c.sel_payload[(size_t)seg * SORT_MAX + slot] = ((unsigned int)p << 9) | (unsigned int)f;
+      }
+    }
+  });
+}
+
+__global__ void __launch_bounds__(CT, 1) corr2_sort_kernel(Corr2 c) {
+  extern __shared__ unsigned char smem_raw[];
+  const CorrArgs& a = c.a;
+  const int seg = blockIdx.x, tid = threadIdx.x, HW = a.h * a.w;
+  const SegState st = c.state[seg];
+  if (!st.topk) return;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
+  unsigned int* payload = reinterpret_cast<unsigned int*>(smem_raw + SORT_MAX * 8);
+  const int nsel = st.sel_count < SORT_MAX ? st.sel_count : SORT_MAX;
+  for (int i = tid; i < SORT_MAX; i += CT) {
+    keys[i] = i < nsel ? c.sel_keys[(size_t)seg * SORT_MAX + i] : 0ULL;
+    payload[i] = i < nsel ? c.sel_payload[(size_t)seg * SORT_MAX + i] : 0u;
+  }
+  __syncthreads();
+  for (int k = 2; k <= SORT_MAX; k <<= 1)
+    for (int jj = k >> 1; jj > 0; jj >>= 1) {
+      for (int i = tid; i < SORT_MAX; i += CT) {
+        const int l = i ^ jj;
+        if (l > i) {
+          const bool desc = (i & k) == 0;
+          const unsigned long long ki = keys[i], kl = keys[l];
+          if (desc ? (ki < kl) : (ki > kl)) {
+            keys[i] = kl; keys[l] = ki;
+            const unsigned int t = payload[i]; payload[i] = payload[l]; payload[l] = t;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  const int b = seg / a.J, obj_id = a.obj_ids[seg % a.J];
+  const int n = a.counts[seg];
+  const size_t seg_base = (size_t)seg * a.cap;
+  for (int i = tid; i < n; i += CT) {
+    const unsigned int pl = payload[i];
+    const int p = (int)(pl >> 9), f = (int)(pl & 511u);
+    const float vo = __ldg(a.obj_conf + ((size_t)b * HW + p) * (a.O + 1) + obj_id);
+    const float vf = __ldg(a.frag_conf + (((size_t)b * HW + p) * a.O + (obj_id - 1)) * a.F + f);
+    write_row(a, b, obj_id, seg_base + i, p, f, vo, vf);
+  }
+}
+
+// lazy localisation head over the emitted rows of every segment: CW warps per CTA, grid (row chunks, segments)
+__global__ void __launch_bounds__(CT) corr2_loc_kernel(Corr2 c, int rows_per_cta) {
+  const CorrArgs& a = c.a;
+  const int seg = blockIdx.y;
+  const int n = a.counts[seg];
+  const int r0 = blockIdx.x * rows_per_cta;
+  if (r0 >= n) return;
+  const int b = seg / a.J, obj_id = a.obj_ids[seg % a.J];
+  const int r1 = min(n, r0 + rows_per_cta);
+  // lazy_loc_rows walks rows [0, n) of a segment with the CTA's warps: give it the sub-range as its own "segment"
+  lazy_loc_rows(a, b, obj_id, (size_t)seg * a.cap + r0, r1 - r0);
+}
+
+static size_t corr2_extra_bytes(int S) { return (size_t)S * (2048 * 4 + sizeof(SegState) + SORT_MAX * 12) + 1024; }
+
+static int corresp2_launch(const CorrArgs& a, void* ws_aligned, cudaStream_t stream) {
+  const int S = a.B * a.J, HW = a.h * a.w;
+  Corr2 c;
+  c.a = a;
+  unsigned char* p = reinterpret_cast<unsigned char*>(ws_aligned);
+  c.cnt = reinterpret_cast<unsigned int*>(p); p += (size_t)S * (HW + 1) * 4;
+  c.off = reinterpret_cast<unsigned int*>(p); p += (size_t)S * (HW + 1) * 4;
+  c.rmax = reinterpret_cast<float*>(p); p += (size_t)S * (HW + 1) * 4;
+  p += (size_t)S * (HW + 1) * 4;                                   // (fourth plane of the v1 layout: unused)
+  p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 255) & ~(uintptr_t)255);
+  c.hist = reinterpret_cast<unsigned int*>(p); p += (size_t)S * 2048 * 4;
+  c.sel_keys = reinterpret_cast<unsigned long long*>(p); p += (size_t)S * SORT_MAX * 8;
+  c.sel_payload = reinterpret_cast<unsigned int*>(p); p += (size_t)S * SORT_MAX * 4;
+  c.state = reinterpret_cast<SegState*>(p);
+  EPOS_CHECK_ARG(a.J <= 64 && S <= 65535);
+  corr2_rows_kernel<<<dim3(ceil_div(HW, 128), a.B), 128, 0, stream>>>(c);
+  EPOS_LAUNCH_CHECK();
+  corr2_scan_kernel<<<S, CT, 0, stream>>>(c);
+  EPOS_LAUNCH_CHECK();
+  corr2_emit_kernel<<<dim3(ceil_div(HW, 128), S), 128, 0, stream>>>(c);
+  EPOS_LAUNCH_CHECK();
+  if (a.max_corr > 0) {
+    for (int d = 0; d < 6; ++d) {
+      corr2_hist_kernel<<<dim3(ceil_div(HW, 256), S), 256, 0, stream>>>(c, d);
+      EPOS_LAUNCH_CHECK();
+      corr2_pick_kernel<<<S, CT, 0, stream>>>(c, d);
+      EPOS_LAUNCH_CHECK();
+    }
+    corr2_gather_kernel<<<dim3(ceil_div(HW, 256), S), 256, 0, stream>>>(c);
+    EPOS_LAUNCH_CHECK();
+    const size_t smem = (size_t)SORT_MAX * 12;
+    static std::atomic<int> attr[EPOS_MAX_DEVICES];
+    const int dslot = device_slot();
+    if (!attr[dslot].load(std::memory_order_acquire)) {
+      EPOS_CUDA(cudaFuncSetAttribute(corr2_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr[dslot].store(1, std::memory_order_release);
+    }
+    corr2_sort_kernel<<<S, CT, smem, stream>>>(c);
+    EPOS_LAUNCH_CHECK();
+  }
+  if (!a.frag_loc) {
+    const int rows_per_cta = 4 * CW;
+    corr2_loc_kernel<<<dim3(ceil_div(a.cap, rows_per_cta), S), CT, 0, stream>>>(c, rows_per_cta);
+    EPOS_LAUNCH_CHECK();
+  }
+  return EPOS_OK;
+}
+
 }  // namespace epos
 
 using namespace epos;
@@ -352,7 +695,7 @@ extern "C" {
 
 size_t epos_corresp_workspace_bytes(int B, int J, int h, int w) {
   if (B <= 0 || J <= 0 || h <= 0 || w <= 0) return 0;
-  return (size_t)B * J * ((size_t)h * w + 1) * 16 + 256;
+  return (size_t)B * J * ((size_t)h * w + 1) * 16 + 512 + corr2_extra_bytes(B * J);
 }
 
 static int corresp_launch(const float* obj_conf, const float* frag_conf, const float* frag_loc, const uint16_t* feat, int ldf,
@@ -381,6 +724,10 @@ static int corresp_launch(const float* obj_conf, const float* frag_conf, const f
   a.counts = counts; a.totals = totals;
   a.feat = feat; a.ldf = ldf; a.feat_plane = (long long)feat_plane; a.w_loc = w_loc; a.b_loc = b_loc; a.feat_c = feat_c;
   a.ws = reinterpret_cast<unsigned int*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  // grid-wide pipeline by default; EPOS_CORRESP_V1=1 selects the one-CTA-per-segment kernel (developer A/B)
+  static int v1 = -1;
+  if (v1 < 0) { const char* e = getenv("EPOS_CORRESP_V1"); v1 = e ? atoi(e) : 0; }
+  if (!v1) return corresp2_launch(a, a.ws, (cudaStream_t)stream);
   const size_t smem = 2048 * 4 + (size_t)SORT_MAX * 12;
   static std::atomic<int> attr[EPOS_MAX_DEVICES];
   const int dslot = device_slot();
