@@ -30,7 +30,9 @@ with open(os.path.join(pr, 'launches_%s.csv' % tag), 'w') as f:
 pat = re.compile(r'dram__bytes_(read|write)\.sum$|dram__bytes_(read|write)\.sum\.per_second|gpu__dram_throughput\.avg\.pct|'
                  r'sm__pipe_tensor.*cycles_active.*pct|sm__inst_executed_pipe_tensor|sm__warps_active\.avg\.pct|launch__registers_per_thread|'
                  r'gpu__time_duration\.sum|sm__throughput\.avg\.pct|launch__grid_size|launch__block_size|l1tex__t_bytes.*sum$|lts__t_bytes\.sum$|'
-                 r'smsp__cycles_active\.avg|sm__cycles_elapsed\.max|launch__occupancy_limit|smsp__warp_issue_stalled.*pct|sm__pipe_fp64|sm__inst_executed\.sum$')
+                 r'smsp__cycles_active\.avg|sm__cycles_elapsed\.max|launch__occupancy_limit|smsp__warp_issue_stalled.*pct|sm__pipe_fp64|sm__inst_executed\.sum$|'
+                 r'l1tex__m_xbar2l1tex_read_bytes|lts__throughput\.avg\.pct|sm__mem_tensor_cycles_active|l1tex__data_pipe_lsu_wavefronts_mem_shared\.sum$|'
+                 r'l1tex__throughput\.avg\.pct|lts__t_sector_hit_rate\.pct|smsp__inst_executed_pipe_fp64|sm__inst_executed_pipe_fp64')
 for fn in sorted(os.listdir(go)):
     if fn.endswith('_%s.ncu-rep' % tag):
         out = subprocess.run(['ncu', '-i', os.path.join(go, fn), '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
