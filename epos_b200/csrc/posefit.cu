@@ -6,19 +6,20 @@
 // updates, the LO trigger (iteration > 20 on a new best), the cumulative budget of 9 graph cuts and the coverage exit
 // all depend on the order of hypotheses.  The kernels keep that order exactly while evaluating hypotheses in parallel:
 //
-//   prep     points (u_n, v_n, x, y, z), dense pixel ids, k-nearest neighbour graph (f32, 5-D), reverse adjacency
-//   main     persistent per problem: 16 RANSAC passes at a time, ONE WARP PER PASS (sample -> Kneip P3P -> score every
-//            solution over all N points with ballot counting and a per-warp pixel bitset), then an in-order replay of
-//            the chunk applies the reference's update / early-out / LO-trigger / termination rules
-//   cut      graph-cut labeling (GCRANSAC.h:812-920): f64 preflow-push in waves + reverse BFS = nodes that can still
-//            reach the sink, which is what the reference's BK max-flow labels SINK (graph.h:112-115,478-488)
-//   trials   the <= 20 inner fits of graphCutLocalOptimization (GCRANSAC.h:737-792), one warp per trial
-//            (sample 21 inliers -> DLT + LM -> score), replayed in order
-//   final    iterated least squares, final non-minimal fit, final LM refinement (GCRANSAC.h:480-521,
-//            progressivex_python.cpp:257-312), pose record + labeling
+//   prep_kernel   points (u_n, v_n, x, y, z), dense pixel ids, k-nearest neighbour graph (f32, 5-D), reverse adjacency
+//   fit_kernel    ONE PERSISTENT CTA PER PROBLEM runs the whole state machine, re-carving its shared memory per phase:
+//     main     80 RANSAC passes at a time: a thread per pass samples until a valid sample gives an admissible Kneip P3P pose,
+//              a warp per pass scores every solution over all N points (ballot counting, per-warp pixel bitset), then an
+//              in-order replay of the chunk applies the reference's update / early-out / LO-trigger / termination rules
+//     cut      graph-cut labeling (GCRANSAC.h:812-920): f64 preflow-push in waves + reverse BFS = nodes that can still
+//              reach the sink, which is what the reference's BK max-flow labels SINK (graph.h:112-115,478-488)
+//     trials   the <= 20 inner fits of graphCutLocalOptimization (GCRANSAC.h:737-792), one warp per trial
+//              (sample 21 inliers -> DLT + LM -> score), replayed in order
+//     final    iterated least squares, final non-minimal fit, final LM refinement (GCRANSAC.h:480-521,
+//              progressivex_python.cpp:257-312), pose record + labeling
+//   progx_kernel  the same phases inside the Progressive-X outer loop (multi-instance problems; see further down)
 //
-// The host launches a FIXED schedule (prep, 11 x [main, cut, trials], final): a problem uses a slot only when its
-// state says so, nothing is read back, so the whole sequence is CUDA-graph capturable.
+// Two launches per batch (prep, fit), nothing is read back: the sequence is CUDA-graph capturable (engine.py).
 #include "common.cuh"
 #include "pose_fit.cuh"
 
