@@ -398,11 +398,35 @@ def test_pipelined_engine_equals_serial_engine():
         assert np.array_equal(a, b)
 
 
+def _engine_records(w, O, F, store, K, imgs, Ks, pipelined, graphs):
+    """Pose records of every batch through run_device (read one batch at a time) and then through run_host / flush."""
+    from epos_b200 import engine
+    eng = engine.Engine(w, O, F, DEV, stages=engine.STAGES_FULL, model_store=store, K=K, max_correspondences=1024,
+                        seed=4, pipelined=pipelined, graphs=graphs)
+    recs = []
+    for im, k in zip(imgs, Ks):
+        o = eng.run_device(im.to(DEV), K=k)
+        eng.join()
+        torch.cuda.synchronize()
+        recs.append(o['poses'].cpu().numpy().copy())
+    host = []
+    for im, k in zip(imgs, Ks):
+        r = eng.run_host(im.pin_memory(), K=k)
+        if r is not None:
+            host.append(r.numpy().copy())
+    last = eng.flush() if pipelined else None
+    if last is not None:
+        host.append(last.numpy().copy())
+    assert len(host) == len(imgs)
+    torch.cuda.synchronize()
+    return recs, host, eng
+
+
 @pytest.mark.parametrize('pipelined', [False, True])
 def test_graph_engine_equals_eager_engine(pipelined):
     """graphs=True replays the per-batch pipeline from CUDA graphs (two buffer sets, device-side stream-key counter).
-    Every pose record must be bit-identical to the eager engine's, batch after batch, through run_device and run_host,
-    and a change of the intrinsics between batches must take effect."""
+    Every pose record must be bit-identical to the serial eager engine's, batch after batch, through run_device and
+    run_host, back to back without host synchronisation, and a change of the intrinsics between batches must take effect."""
     from epos_b200 import engine, synthetic, weights as W
     O, F, B = 3, 16, 2
     w = W.random_init(O, F, seed=2, bn='random', logits_std=0.5)
@@ -411,43 +435,24 @@ def test_graph_engine_equals_eager_engine(pipelined):
     K2 = K.copy(); K2[0, 0] *= 1.1; K2[1, 1] *= 1.1
     imgs = [torch.from_numpy(W.synthetic_images(B, seed=20 + i, height=160, width=224)) for i in range(5)]
     Ks = [None, None, K2, K2, None]
-    res = {}
-    for graphs in (False, True):
-        eng = engine.Engine(w, O, F, DEV, stages=engine.STAGES_FULL, model_store=store, K=K, max_correspondences=1024,
-                            seed=4, pipelined=pipelined, graphs=graphs)
-        outs = [eng.run_device(im.to(DEV), K=k) for im, k in zip(imgs, Ks)]
-        recs = []
-        for o in outs:                       # graph mode reuses two buffer sets: read each record before its set is reused
-            pass
-        eng.join()
-        torch.cuda.synchronize()
-        # records of the last two batches are still in their buffer sets; earlier ones are re-run one at a time
+    ref_dev, ref_host, _ = _engine_records(w, O, F, store, K, imgs, Ks, pipelined=False, graphs=False)
+    assert sum(float(r[..., 14].sum()) for r in ref_dev) >= 1
+    assert not np.array_equal(ref_dev[1], ref_dev[2])                  # K2 changes the poses
+    for graphs in ((False, True) if pipelined else (True,)):
+        dev, host, eng = _engine_records(w, O, F, store, K, imgs, Ks, pipelined=pipelined, graphs=graphs)
+        for i, (a, b) in enumerate(zip(ref_dev, dev)):
+            assert a.shape == (B, O, 16) and np.array_equal(a, b), ('run_device', 'graphs' if graphs else 'eager', i)
+        for i, (a, b) in enumerate(zip(ref_host, host)):
+            assert np.array_equal(a, b), ('run_host', 'graphs' if graphs else 'eager', i, np.abs(a - b).max())
+        if graphs:
+            assert eng.launch_count() > 0 and eng.graph_launches > 100
+        # back-to-back run_device calls (no host synchronisation in between): the last record is still the right one
         eng2 = engine.Engine(w, O, F, DEV, stages=engine.STAGES_FULL, model_store=store, K=K, max_correspondences=1024,
                              seed=4, pipelined=pipelined, graphs=graphs)
-        for im, k in zip(imgs, Ks):
-            o = eng2.run_device(im.to(DEV), K=k)
-            eng2.join()
-            torch.cuda.synchronize()
-            recs.append(o['poses'].cpu().numpy().copy())
-        assert np.array_equal(outs[-1]['poses'].cpu().numpy(), recs[-1])
-        host = []
-        for im, k in zip(imgs, Ks):
-            r = eng2.run_host(im.pin_memory(), K=k)
-            if r is not None:
-                host.append(r.numpy().copy())
-        last = eng2.flush()
-        if last is not None:
-            host.append(last.numpy().copy())
-        assert len(host) == len(imgs)
-        res[graphs] = (recs, host)
-        if graphs:
-            assert eng2.launch_count() > 0 and eng2.graph_launches > 100
-    for a, b in zip(res[False][0], res[True][0]):
-        assert a.shape == (B, O, 16) and np.array_equal(a, b)
-    for a, b in zip(res[False][1], res[True][1]):
-        assert np.array_equal(a, b)
-    assert sum(float(r[..., 14].sum()) for r in res[False][0]) >= 1
-    assert not np.array_equal(res[False][0][1], res[False][0][2])
+        outs = [eng2.run_device(im.to(DEV), K=k) for im, k in zip(imgs, Ks)]
+        eng2.join()
+        torch.cuda.synchronize()
+        assert np.array_equal(outs[-1]['poses'].cpu().numpy(), ref_dev[-1]), ('back to back', graphs)
 
 
 def test_graph_engine_cnn_only():
