@@ -95,7 +95,11 @@ class Engine:
                 gs['out'] = self.net.predict(gs['x'], lazy_loc=self.lazy_loc)
             gs['cnn'] = g
             gs['cnn_launches'] = int(lib.epos_launch_count() - l0)
-            pool = g.pool()                      # the two CNN graphs replay in order on one stream: shared private pool
+            # Serial engine: the two CNN graphs replay strictly one after the other, so they may share a private pool.
+            # Pipelined engine: they must NOT -- with a shared pool the outputs of set 1 can be placed in blocks that
+            # were intermediates of set 0's graph, and set 0's next replay would overwrite them while the side stream is
+            # still post-processing set 1.
+            pool = None if self.pipelined else g.pool()
             gs['post'] = None
             gs['post_launches'] = 0
             if self._fitter is not None:
