@@ -101,111 +101,6 @@ __global__ void __launch_bounds__(DT_THREADS, 3) dwconv3x3_tile_kernel(
   }
 }
 
-// Persistent variant: a CTA walks over tiles (slab fastest) with TWO shared-memory buffers; the TMA box of the tile after
-// next is requested as soon as a buffer has been consumed, so a CTA always has one load in flight while it computes
-// (the one-tile kernel above leaves a CTA idle from launch until its box lands).  Two CTAs per SM.
-template <int R>
-__global__ void __launch_bounds__(DT_THREADS, 2) dwconv3x3_tile_persist_kernel(
-    const __grid_constant__ CUtensorMap tmap, const float* __restrict__ w, const float* __restrict__ bias,
-    float* __restrict__ y_f32, uint16_t* __restrict__ y_split, int ldy_split, long long plane_stride, int H, int W, int C,
-    int TH, int tiles_y, int tiles_x, int slabs, int total, int buf_bytes, int relu_in, int relu_out) {
-  constexpr int IW = DT_TW + 2 * R;
-  extern __shared__ __align__(128) uint8_t dt_smem[];
-  uint8_t* base = dt_smem + ((128u - (smem_u32(dt_smem) & 127u)) & 127u);
-  __shared__ uint64_t bar[2];
-  const uint32_t tile_bytes = (uint32_t)((TH + 2 * R) * IW * DT_SLAB * 4);
-  auto issue = [&](int t, int s) {
-    const int slab = t % slabs;
-    int q = t / slabs;
-    const int tx = q % tiles_x;
-    q /= tiles_x;
-    const int ty = q % tiles_y, b = q / tiles_y;
-    mbar_expect_tx(&bar[s], tile_bytes);
-    tma_load_4d(base + (size_t)s * buf_bytes, &tmap, &bar[s], slab * DT_SLAB, tx * DT_TW - R, ty * TH - R, b);
-  };
-  if (threadIdx.x == 0) {
-    mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int s = 0; s < 2; ++s) {
-      const int t = (int)blockIdx.x + s * (int)gridDim.x;
-      if (t < total) issue(t, s);
-    }
-  }
-  const int cg = threadIdx.x & 7, sx = (threadIdx.x >> 3) & 3, sy = threadIdx.x >> 5;
-  const float in_floor = relu_in ? 0.f : -INFINITY;
-  const float out_floor = relu_out ? 0.f : -INFINITY;
-  __syncthreads();
-  int k = 0;
-  for (int t = blockIdx.x; t < total; t += gridDim.x, ++k) {
-    const int s = k & 1;
-    const uint32_t phase = (uint32_t)(k >> 1) & 1u;
-    const int slab = t % slabs;
-    int q = t / slabs;
-    const int x0 = (q % tiles_x) * DT_TW;
-    q /= tiles_x;
-    const int y0 = (q % tiles_y) * TH, b = q / tiles_y;
-    const int c = slab * DT_SLAB + cg * 4;
-    const bool c_ok = c < C;
-    float4 wk[9];
-    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c_ok) {
-#pragma unroll
-      for (int i = 0; i < 9; ++i) wk[i] = __ldg(reinterpret_cast<const float4*>(w + (size_t)i * C + c));
-      bb = __ldg(reinterpret_cast<const float4*>(bias + c));
-    } else {
-#pragma unroll
-      for (int i = 0; i < 9; ++i) wk[i] = bb;
-    }
-    const float4* tile = reinterpret_cast<const float4*>(base + (size_t)s * buf_bytes);
-    mbar_wait(&bar[s], phase);
-    for (int row = sy; row < TH; row += 8) {
-      float4 acc[4] = {bb, bb, bb, bb};
-#pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        const float4* rp = tile + ((row + ky * R) * IW + sx * 4) * 8 + cg;
-#pragma unroll
-        for (int col = 0; col < 4 + 2 * R; ++col) {
-          float4 v = rp[col * 8];
-          v.x = fmaxf(v.x, in_floor); v.y = fmaxf(v.y, in_floor); v.z = fmaxf(v.z, in_floor); v.w = fmaxf(v.w, in_floor);
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const int p = col - kx * R;
-            if (p >= 0 && p < 4) {
-              const float4 ww = wk[ky * 3 + kx];
-              acc[p].x = fmaf(v.x, ww.x, acc[p].x); acc[p].y = fmaf(v.y, ww.y, acc[p].y);
-              acc[p].z = fmaf(v.z, ww.z, acc[p].z); acc[p].w = fmaf(v.w, ww.w, acc[p].w);
-            }
-          }
-        }
-      }
-      const int oy = y0 + row;
-      if (!c_ok || oy >= H) continue;
-      const long long pix0 = ((long long)b * H + oy) * W + x0 + sx * 4;
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        if (x0 + sx * 4 + p >= W) break;
-        float4 a = acc[p];
-        a.x = fmaxf(a.x, out_floor); a.y = fmaxf(a.y, out_floor); a.z = fmaxf(a.z, out_floor); a.w = fmaxf(a.w, out_floor);
-        const long long o = (pix0 + p) * C + c;
-        if (y_f32) *reinterpret_cast<float4*>(y_f32 + o) = a;
-        const long long os = (pix0 + p) * ldy_split + c;
-        if (y_split) {
-          uint2 hi, lo;
-          split_bf16x2(a.x, a.y, hi.x, lo.x);
-          split_bf16x2(a.z, a.w, hi.y, lo.y);
-          *reinterpret_cast<uint2*>(y_split + os) = hi;
-          *reinterpret_cast<uint2*>(y_split + plane_stride + os) = lo;
-        }
-      }
-    }
-    __syncthreads();                            // every thread has finished reading buffer s
-    if (threadIdx.x == 0) {
-      const int t2 = t + 2 * (int)gridDim.x;
-      if (t2 < total) issue(t2, s);
-    }
-  }
-}
-
 // Large dilation rates (ASPP: 12 / 24 / 36 on a 60 x 80 map).  With rate r the rows y = ry (mod r) form an independent
 // problem: a tap of such a row lies in a row of the same class, r pixels to the side.  A CTA therefore owns one row class
 // of one image and one 32-channel slab: every input value is read from HBM exactly once (the register-strip kernel
@@ -319,37 +214,9 @@ static int make_dw_map(CUtensorMap* map, const float* x, int ldx, int B, int H, 
   return EPOS_OK;
 }
 
-static int dw_persist_mode() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("EPOS_DW_PERSIST"); v = e ? atoi(e) : 0; }
-  return v;
-}
-
 template <int R>
 static int launch_dw_tile(const CUtensorMap& map, const float* w, const float* bias, float* y_f32, uint16_t* y_split,
                           int ldy_split, int B, int H, int W, int C, int TH, int relu_in, int relu_out, cudaStream_t stream) {
-  if (dw_persist_mode()) {
-    const int buf = ((TH + 2 * R) * (DT_TW + 2 * R) * DT_SLAB * 4 + 127) & ~127;
-    const int smem_p = 2 * buf + 128;
-    static std::atomic<int> attr_p[EPOS_MAX_DEVICES];
-    const int ds = device_slot();
-    if (smem_p > attr_p[ds].load(std::memory_order_acquire)) {
-      EPOS_CUDA(cudaFuncSetAttribute(dwconv3x3_tile_persist_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
-      attr_p[ds].store(smem_p, std::memory_order_release);
-    }
-    const int tiles_y = ceil_div(H, TH), tiles_x = ceil_div(W, DT_TW), slabs = ceil_div(C, DT_SLAB);
-    const long long total = (long long)slabs * tiles_x * tiles_y * B;
-    if (total < (1LL << 30)) {
-      int sms = 148;
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ds);
-      const int ctas_per_sm = smem_p <= 112 * 1024 ? 2 : 1;
-      const int grid = (int)(total < (long long)sms * ctas_per_sm ? total : (long long)sms * ctas_per_sm);
-      dwconv3x3_tile_persist_kernel<R><<<grid, DT_THREADS, smem_p, stream>>>(map, w, bias, y_f32, y_split, ldy_split,
-          (long long)B * H * W * ldy_split, H, W, C, TH, tiles_y, tiles_x, slabs, (int)total, buf, relu_in, relu_out);
-      EPOS_LAUNCH_CHECK();
-      return EPOS_OK;
-    }
-  }
   const int smem = (TH + 2 * R) * (DT_TW + 2 * R) * DT_SLAB * 4 + 128;
   static std::atomic<int> attr[EPOS_MAX_DEVICES];
   const int dslot = device_slot();
@@ -382,7 +249,7 @@ int dwconv3x3_tiled(const float* x, int ldx, const float* w, const float* bias, 
   // other resident CTAs -- measured on B200: 2 -> 3 CTAs per SM takes the 60x80x728 layer from 53 to 46 us)
   int TH = 8, best = 1 << 30;
   for (int t = 8; t <= 24; t += 4) {
-    if (t > 8 && (t + 2 * rate) * (DT_TW + 2 * rate) * DT_SLAB * 4 + 128 > (dw_persist_mode() ? 55 : 74) * 1024) break;
+    if (t > 8 && (t + 2 * rate) * (DT_TW + 2 * rate) * DT_SLAB * 4 + 128 > 74 * 1024) break;
     const int rows = ceil_div(H, t) * (t + 2 * rate);
     if (rows <= best) { best = rows; TH = t; }
   }
