@@ -97,7 +97,6 @@ class EposNet:
         self.keep_f32 = keep_f32
         self.impl = 'tcgen05'            # 'simt' = fp32 validation path (needs keep_f32=True)
         self.end_points = {}
-        self.end_points_split = {}
         self.gemm_events = None          # bench.py: list collecting (start, stop, M, N, K) per tcgen05 GEMM launch
         self._prepare(weights)
 
@@ -222,8 +221,8 @@ class EposNet:
             ldd = (N + 31) // 32 * 32 if (pad_f32 and N >= 64) else N
             d_f32 = torch.empty((M, ldd), dtype=torch.float32, device=self.dev)
         if out_split and d_split is None:
-            ldd_split = (N + 15) // 16 * 16      # 32-byte aligned bf16 rows, as split() / dwconv() produce them
-            d_split = torch.empty((2, M, ldd_split), dtype=torch.bfloat16, device=self.dev)
+            d_split = torch.empty((2, M, N), dtype=torch.bfloat16, device=self.dev)
+            ldd_split = N
         plane = 0 if d_split is None else d_split.stride(0)
         if self.impl == 'simt':
             # fp32 validation path: reconstruct A from the split planes, run the SIMT GEMM, then split.
@@ -348,13 +347,9 @@ class EposNet:
         return d
 
     # -- network --------------------------------------------------------------------------------------
-    def xception_module(self, x, B, H, W, cin, base, depths, skip, stride, rate, relu_inside, xs=None, split_out=()):
-        """x: f32 [B*H*W, cin] (xs: its split-bf16 form when the producer emitted it).  net_xception.py:198-323.
-        split_out: indices of the separable convs whose GEMM also writes the split-bf16 form of its output (for a
-        following 1x1 shortcut conv at stride 1, the ASPP branches or the decoder skip), saving a conversion pass.
-        Returns (out f32, h, w, c, split form of the output or None)."""
+    def xception_module(self, x, B, H, W, cin, base, depths, skip, stride, rate, relu_inside):
+        """x: f32 [B*H*W, cin].  net_xception.py:198-323."""
         r, c, h, w = x, cin, H, W
-        rs = None
         for i in range(3):
             s = stride if i == 2 else 1
             a, ho, wo = self.dwconv(r, B, h, w, c, r.shape[1], self.p['%s/dw%d' % (base, i)], s, rate,
@@ -363,18 +358,14 @@ class EposNet:
             g = self.p['%s/pw%d' % (base, i)]
             res = None
             if i == 2 and skip == 'conv':
-                if xs is None or stride != 1:
-                    xs = self.split(x, B, H, W, cin, x.shape[1], subsample=stride)
+                xs = self.split(x, B, H, W, cin, x.shape[1], subsample=stride)
                 res, _ = self.gemm(xs, self.p[base + '/shortcut'], M, relu=False)
             elif i == 2 and skip == 'sum':
                 res = x
-            r, rs = self.gemm(a, g, M, relu=relu_inside, residual=res, out_split=i in split_out)
+            r, _ = self.gemm(a, g, M, relu=relu_inside, residual=res)
             c, h, w = depths[i], ho, wo
-            name = '%s/separable_conv%d_pointwise' % (base.replace(XC + '/', ''), i + 1)
-            self.end_points[name] = (r, h, w, c)
-            if rs is not None:
-                self.end_points_split[name] = rs
-        return r, h, w, c, rs
+            self.end_points['%s/separable_conv%d_pointwise' % (base.replace(XC + '/', ''), i + 1)] = (r, h, w, c)
+        return r, h, w, c
 
     def forward_features(self, images):
         """images [B,H,W,3] f32 cuda in [0,255] -> decoder features (split-bf16 [2,M,256]) and (B,h,w)."""
@@ -382,7 +373,6 @@ class EposNet:
         B, H, W, _ = images.shape
         images = images.contiguous()
         self.end_points = {}
-        self.end_points_split = {}
         if self.variant == 'resnet_v1_50_beta':
             x, xs, h, w, c = self.resnet_features(images)
             return self.aspp_decoder(x, xs, B, H, W, h, w, c, RESNET_END_POINT)
@@ -394,30 +384,17 @@ class EposNet:
         x, h, w, c = c2, H1, W1, 64
         target = self.opts.encoder_output_stride // 2              # net_xception.py:455-458
         current_stride, rate = 1, 1
-        units_flat = []                                            # (base, depths, skip, stride, rate, relu_inside)
         for scope, depths, skip, units in XCEPTION65_BLOCKS:
             stride = _BLOCK_STRIDES[scope]
             for u in range(1, units + 1):
                 base = '%s/%s/unit_%d/xception_module' % (XC, scope, u)
                 if current_stride == target:                       # net_xception.py:374-385
-                    units_flat.append((base, depths, skip, 1, rate, scope in _RELU_INSIDE))
+                    x, h, w, c = self.xception_module(x, B, h, w, c, base, depths, skip, 1, rate, scope in _RELU_INSIDE)
                     rate *= stride
                 else:
-                    units_flat.append((base, depths, skip, stride, 1, scope in _RELU_INSIDE))
+                    x, h, w, c = self.xception_module(x, B, h, w, c, base, depths, skip, stride, 1, scope in _RELU_INSIDE)
                     current_stride *= stride
-        xs = None
-        for k, (base, depths, skip, stride, rate_, relu_in) in enumerate(units_flat):
-            split_out = set()
-            # the split-bf16 form of a unit's output is wanted by a stride-1 shortcut conv of the next unit and by ASPP
-            nxt = units_flat[k + 1] if k + 1 < len(units_flat) else None
-            if nxt is None or (nxt[2] == 'conv' and nxt[3] == 1):
-                split_out.add(2)
-            for i in range(3):                                     # ... and by the decoder's skip projection
-                if '%s/separable_conv%d_pointwise' % (base.replace(XC + '/', ''), i + 1) == DECODER_END_POINT:
-                    split_out.add(i)
-            x, h, w, c, xs = self.xception_module(x, B, h, w, c, base, depths, skip, stride, rate_, relu_in, xs=xs,
-                                                  split_out=split_out)
-        return self.aspp_decoder(x, xs, B, H, W, h, w, c, DECODER_END_POINT)
+        return self.aspp_decoder(x, None, B, H, W, h, w, c, DECODER_END_POINT)
 
     def aspp_decoder(self, x, xs, B, H, W, h, w, c, end_point):
         """ASPP + decoder on backbone features x (f32 [B*h*w, c]; xs = its split form if already available)."""
@@ -449,9 +426,7 @@ class EposNet:
             raise NotImplementedError('skip feature %dx%d != decoder size %dx%d' % (sh, sw, dh_, dw_))
         Md = B * dh_ * dw_
         dcat = torch.empty((Md, 320), dtype=torch.float32, device=self.dev)       # 304 channels, 128-byte aligned rows
-        ss = self.end_points_split.get(end_point)
-        if ss is None:
-            ss = self.split(skip, B, sh, sw, sc, skip.shape[1])
+        ss = self.split(skip, B, sh, sw, sc, skip.shape[1])
         self.gemm(ss, p['feature_projection0'], Md, relu=True, d_f32=dcat[:, 256:], ldd=320)
         _lib.check(lib.epos_resize_bilinear(aspp.data_ptr(), dcat.data_ptr(), 320, B, h, w, dh_, dw_, 256, self._s()),
                    'epos_resize_bilinear')
