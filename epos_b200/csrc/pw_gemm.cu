@@ -303,6 +303,13 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if constexpr (PAIR) {
             const uint32_t fb = full_addr + (uint32_t)stage * 8u;
+            // developer switches (scripts/dev_gemm.py): 256 = the peer loads nothing, 512 = the leader loads nothing,
+            // 1024 = nobody loads (pure barrier protocol rate)
+            if ((dbg & 1024) || ((dbg & 256) && rank == 1) || ((dbg & 512) && rank == 0)) {
+              mbar_expect_tx_cluster(fb, 0);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              continue;
+            }
             mbar_expect_tx_cluster(fb, Cfg::A_BYTES + (full ? Cfg::B_BYTES : 2 * Cfg::B_BOX_BYTES));
             if (cg.enabled) {
               const int tap = kb / cg.cpb, c0 = (kb - tap * cg.cpb) * BLOCK_K;
