@@ -32,6 +32,12 @@ struct WarpGroup {
   __device__ __forceinline__ int lane() const { return rank; }
 };
 
+// A warp working on MORE points than it has lanes: same interface as WarpGroup, but a distinct type so that the generic
+// (lane-strided) lm_eval applies instead of the one-point-per-lane specialisation.  Used for the final fits on a few dozen
+// to a few hundred inliers, where a single warp without block barriers beats the whole CTA with two barriers per
+// reduction.
+struct WarpGroupN : WarpGroup {};
+
 struct CtaGroup {
   int rank, size;
   double* sh;            // FIT_SCRATCH_DOUBLES doubles

@@ -578,7 +578,20 @@ __device__ __noinline__ void phase_main(const Workspace& ws, const epos_fit_para
   unsigned char* rest = load_points(smem_raw, ws, p, N, &sp, pts_loaded);
   unsigned int* bits = reinterpret_cast<unsigned int*>(rest) + warp * (NMAX / 32);
   double* best_model = reinterpret_cast<double*>(rest + WARPS * (NMAX / 32) * 4);
+  // the replay's view of the chunk: the small per-pass fields staged in shared memory (the replay is a dependent chain of
+  // reads; from the L2-resident records it cost ~2000 cycles per pass, i.e. a quarter of the main phase)
+  double* s_val = best_model + 12;                                 // [CHUNK][4]
+  int* s_inl = reinterpret_cast<int*>(s_val + CHUNK * 4);          // [CHUNK][4]
+  int* s_nm = s_inl + CHUNK * 4;                                   // [CHUNK]
+  int* s_fails = s_nm + CHUNK;                                     // [CHUNK]
   PassRecord* recs = ws.recs + (size_t)p * CHUNK;                  // global (L2): hypotheses do not depend on the state
+  auto stage_chunk = [&]() {
+    if (tid < CHUNK) {
+      const PassRecord* rc = recs + tid;
+      s_nm[tid] = rc->nm; s_fails[tid] = rc->fails;
+      for (int m = 0; m < 4; ++m) { s_inl[tid * 4 + m] = rc->inl[m]; s_val[tid * 4 + m] = rc->val[m]; }
+    }
+  };
   // state (identical in every thread)
   unsigned long long iter = st->iter, max_iteration = st->max_iteration;
   const unsigned long long seed = st->seed;
@@ -592,6 +605,7 @@ __device__ __noinline__ void phase_main(const Workspace& ws, const epos_fit_para
   const double sq_trunc = st->sq_trunc;
   const unsigned long long max_iters = (unsigned long long)prm.max_iters, min_iters = (unsigned long long)prm.min_iters;
   if (tid < 12) best_model[tid] = st->best_model[tid];
+  if (pass < chunk_base + chunk_n) stage_chunk();                  // records of a chunk interrupted by an LO round
   __syncthreads();
   bool ended = false, to_lo = false;
   long long t_sample = 0, t_score = 0, t_replay = 0, n_scored = 0;
@@ -639,7 +653,9 @@ __device__ __noinline__ void phase_main(const Workspace& ws, const epos_fit_para
         }
       }
       __syncthreads();
-      if (tid == 0) { int sc = 0; for (int k = 0; k < CHUNK; ++k) sc += recs[k].nm; n_scored += sc; }
+      stage_chunk();
+      __syncthreads();
+      if (tid == 0) { int sc = 0; for (int k = 0; k < CHUNK; ++k) sc += s_nm[k]; n_scored += sc; }
       t_score += clock64() - t0; t0 = clock64();
     }
     // ---- in-order replay (every thread runs the same scalar code on the same records) ----
@@ -652,14 +668,14 @@ __device__ __noinline__ void phase_main(const Workspace& ws, const epos_fit_para
       bool do_lo = false;
       ++iter;
       const PassRecord* rc = recs + k;
-      iter += (unsigned long long)rc->fails;
-      const int nm = rc->nm;
+      iter += (unsigned long long)s_fails[k];
+      const int nm = s_nm[k];
       for (int m = 0; m < nm; ++m) {
-        int s_inl = rc->inl[m];
-        double s_val = rc->val[m];
-        if (s_inl + 1 < best_inl) { s_inl = 0; s_val = 0.0; }     // early-out of getScore, scoring_function.h:257-259
-        if (best_value < s_val) {
-          best_value = s_val; best_inl = s_inl;
+        int c_inl = s_inl[k * 4 + m];
+        double c_val = s_val[k * 4 + m];
+        if (c_inl + 1 < best_inl) { c_inl = 0; c_val = 0.0; }     // early-out of getScore, scoring_function.h:257-259
+        if (best_value < c_val) {
+          best_value = c_val; best_inl = c_inl;
           __syncthreads();
           if (tid < 12) best_model[tid] = rc->models[12 * m + tid];
           __syncthreads();
@@ -1041,16 +1057,19 @@ __device__ __noinline__ void phase_final(const Workspace& ws, const epos_fit_par
   g.rank = tid; g.size = THREADS; g.sh = fit_sh; g.part = part;
   WarpGroup wg;
   wg.rank = tid & 31; wg.size = 32; wg.sh = fit_sh;
-  // Non-minimal fit on an index list: small lists (the no-consensus case) are fitted by warp 0 alone, which avoids a
-  // block barrier per reduction; large lists use the whole CTA.
+  WarpGroupN wgn;
+  wgn.rank = tid & 31; wgn.size = 32; wgn.sh = fit_sh;
+  constexpr int WARP_N_MAX = 512;      // above this the whole CTA fits (block reductions); below, warp 0 alone
+  // Non-minimal fit on an index list: short lists (the no-consensus case: a few dozen inliers) are fitted by warp 0 alone,
+  // which avoids two block barriers per reduction; long lists use the whole CTA.
   auto fit_list = [&](const unsigned short* list, int n, double* m2) -> bool {
     PointView v;
     v.un = sp.un; v.vn = sp.vn; v.x = sp.x; v.y = sp.y; v.z = sp.z; v.idx = list; v.n = n;
-    if (n > WARP_FIT_MAX) return fit_nonminimal_group(g, v, m2);
+    if (n > WARP_N_MAX) return fit_nonminimal_group(g, v, m2);
     __syncthreads();
     if (tid < 32) {
       double mm[12];
-      const bool ok = fit_nonminimal_group(wg, v, mm);
+      const bool ok = n > WARP_FIT_MAX ? fit_nonminimal_group(wgn, v, mm) : fit_nonminimal_group(wg, v, mm);
       if (tid == 0) { bcast[12] = ok ? 1.0 : 0.0; for (int i = 0; i < 12; ++i) bcast[i] = ok ? mm[i] : 0.0; }
     }
     __syncthreads();
@@ -1147,12 +1166,12 @@ __device__ __noinline__ void phase_final(const Workspace& ws, const epos_fit_par
     matrix_to_rodrigues(R, param);
     param[3] = best_model[3]; param[4] = best_model[7]; param[5] = best_model[11];
     pv.idx = listA; pv.n = nA;
-    if (nA > WARP_FIT_MAX) {
+    if (nA > WARP_N_MAX) {
       lm_refine_group(g, pv, param);
     } else {
       __syncthreads();
       if (tid < 32) {
-        lm_refine_group(wg, pv, param);
+        if (nA > WARP_FIT_MAX) lm_refine_group(wgn, pv, param); else lm_refine_group(wg, pv, param);
         if (tid == 0) for (int i = 0; i < 6; ++i) bcast[i] = param[i];
       }
       __syncthreads();
@@ -2086,7 +2105,7 @@ fit_kernel(Workspace ws, epos_fit_params prm, const int* __restrict__ offsets, d
 constexpr size_t SMEM_POINTS = 5 * NMAX * 8 + NMAX * 2;
 constexpr size_t SMEM_PREP = 5 * NMAX * 4 + 8192 * 8 + 64 * 4 + 8192 * 2 + 64;
 static_assert(sizeof(PassRecord) <= 464 && CHUNK == 80, "workspace_layout reserves 80 x 464 bytes of pass records");
-constexpr size_t SMEM_MAIN = SMEM_POINTS + WARPS * (NMAX / 32) * 4 + 12 * 8 + 64;
+constexpr size_t SMEM_MAIN = SMEM_POINTS + WARPS * (NMAX / 32) * 4 + 12 * 8 + CHUNK * (4 * 8 + 4 * 4 + 4 + 4) + 64;
 constexpr size_t SMEM_CUT = SMEM_CUT_DYN;
 static_assert(FIT_SCRATCH_DOUBLES * 8 >= (NMAX / 32) * 4, "bitset must fit in the fit scratch");
 constexpr size_t SMEM_TRIALS = SMEM_POINTS + MAX_TRIALS * sizeof(TrialRecord) +
