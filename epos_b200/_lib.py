@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libepos_b200.so')
+LIB_PATH = os.environ.get('EPOS_B200_LIB') or os.path.join(_HERE, 'csrc', 'libepos_b200.so')   # override: developer A/B builds
 _lib = None
 
 vp, i32, i64, u64, f32, f64, sz = C.c_void_p, C.c_int, C.c_longlong, C.c_ulonglong, C.c_float, C.c_double, C.c_size_t

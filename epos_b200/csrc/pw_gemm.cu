@@ -266,8 +266,10 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int pub = id < pm.num_pieces ? id : -1;
           sched_ids[sslot] = pub;
           if constexpr (PAIR) {
-            st_cluster_u32(mapa_u32(const_cast<int*>(&sched_ids[sslot]), 1), (uint32_t)pub);
-            mbar_arrive_cluster(mapa_u32(&sched_full[sslot], 1));     // release.cluster: publishes the index to the peer
+            // the peer's copy of the index travels with its own completion count (st.async + complete_tx)
+            const uint32_t peer_bar = mapa_u32(&sched_full[sslot], 1);
+            mbar_expect_tx_cluster(peer_bar, 4);
+            st_async_cluster_u32(mapa_u32(const_cast<int*>(&sched_ids[sslot]), 1), (uint32_t)pub, peer_bar);
           }
           mbar_arrive(&sched_full[sslot]);                            // release: publishes the index to the consumers
           if (++sslot == SCHED_DEPTH) { sslot = 0; sphase ^= 1; }
@@ -276,9 +278,12 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           id = id_next;
         } else {
           // peer CTA of a pair: a consumer of the leader's piece queue
-          mbar_wait_cluster(&sched_full[sslot], sphase);
+          mbar_wait(&sched_full[sslot], sphase);
           const int got = sched_ids[sslot];
-          mbar_arrive_cluster(mapa_u32(&sched_empty[sslot], 0));
+          // the arrive is predicated on the value read: a remote arrive does not wait for an earlier LDS of the same
+          // thread, and the leader overwrites the slot as soon as the last consumer has signalled (seen on B200: a
+          // consumer read the NEXT round's index)
+          if (got >= -1) mbar_arrive_cluster(mapa_u32(&sched_empty[sslot], 0));
           if (++sslot == SCHED_DEPTH) { sslot = 0; sphase ^= 1; }
           if (got < 0) break;
           pm.decode(got, m0, n0, n_cols);
@@ -362,7 +367,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       while (true) {
         mbar_wait(&sched_full[sslot], sphase);
         const int id = sched_ids[sslot];
-        mbar_arrive(&sched_empty[sslot]);
+        if (id >= -1) mbar_arrive(&sched_empty[sslot]);
         if (++sslot == SCHED_DEPTH) { sslot = 0; sphase ^= 1; }
         if (id < 0) break;
         pm.decode(id, m0, n0, n_cols);
@@ -442,10 +447,15 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t sphase = 0;
     int m0, n0, n_cols;
     while (true) {
-      if constexpr (PAIR) mbar_wait_cluster(&sched_full[sslot], sphase); else mbar_wait(&sched_full[sslot], sphase);
-      const int id = sched_ids[sslot];
-      __syncwarp();
+      // lane 0 takes the index and hands it to the warp; its "slot consumed" signal is predicated on the value (see the
+      // producer: the signal must not overtake the read)
+      int id = 0;
       if (lane == 0) {
+        mbar_wait(&sched_full[sslot], sphase);
+        id = sched_ids[sslot];
+      }
+      id = __shfl_sync(0xffffffffu, id, 0);
+      if (lane == 0 && id >= -1) {
         if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(&sched_empty[sslot], 0)); else mbar_arrive(&sched_empty[sslot]);
       }
       if (++sslot == SCHED_DEPTH) { sslot = 0; sphase ^= 1; }
@@ -775,14 +785,14 @@ static int run_gemm(const CUtensorMap& ma, const uint16_t* w_split, int ldw, con
   const int bn = N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
   const char* de = getenv("EPOS_GEMM_DEBUG");   // developer A/B switches (scripts/dev_gemm.py); 0 in production
   const int dbg = de ? atoi(de) : 0;
-  // CTA pairs (cta_group::2, 256 x 256 tiles, each CTA holds half of the W tile).  Measured on B200 (scripts/dev_gemm.py,
-  // profiles/gemm_ab_r01h.log): 3-4 % faster than single CTAs on the deep-K layers (K >= 1024: exit flow, ASPP), 5-8 %
-  // slower on K = 728 and on the K = 256 heads, where the per-tile hand-shakes between the two SMs are not amortised.
-  // EPOS_GEMM_PAIR = 0 / 2 forces single CTAs / pairs wherever BLOCK_N = 256.
+  // CTA pairs (cta_group::2, 256 x 256 tiles, each CTA holds half of the W tile) wherever BLOCK_N = 256.  Measured on B200
+  // (scripts/dev_gemm.py, profiles/gemm_ab_r02c.log): 38400x728x728 112.7 -> 92.8 us, decoder 81 -> 72, heads -6 %, the
+  // MMA-bound deep-K layers unchanged.  (Until round 2 the remote arrives were .release.cluster = a MEMBAR.ALL.GPU per
+  // pipeline stage, which made pairs slower than single CTAs on every K < 1024 layer.)  EPOS_GEMM_PAIR = 0 forces single CTAs.
   static int pair_env = -1;
   if (pair_env < 0) { const char* e = getenv("EPOS_GEMM_PAIR"); pair_env = e ? atoi(e) : 1; }
   const long long m_tiles = cg.enabled ? (long long)(M / (cg.H * cg.W)) * cg.tiles_x * cg.tiles_y : ceil_div(M, BLOCK_M);
-  const bool pair = pair_env && bn == 256 && m_tiles >= 2 && (K >= 1024 || pair_env == 2);
+  const bool pair = pair_env && bn == 256 && m_tiles >= 2;
   // developer A/B (scripts/dev_gemm.py): EPOS_GEMM_BK=32 runs the 256-column tiles with a 32-wide K block (64-byte swizzle,
   // twice the pipeline depth); the caller's A map must then be built with the same K block (epos_pwconv_gemm does)
   const int bk = gemm_bk_for(bn, cg.enabled);

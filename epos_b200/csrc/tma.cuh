@@ -55,7 +55,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
-    if (!done && ++spins > (1ull << 26)) __trap();   // turn a protocol bug into an error, not a hang
+    if (!done) {
+      ++spins;
+#ifdef EPOS_MBAR_DEBUG
+      if (spins == (1ull << 22))                     // -DEPOS_MBAR_DEBUG: every stuck waiter reports once, well before the first trap
+        printf("[mbar_wait] block %d thread %d barrier smem 0x%x parity %u\n", (int)blockIdx.x, (int)threadIdx.x, addr, parity);
+#endif
+      if (spins > (1ull << 26)) __trap();            // turn a protocol bug into an error, not a hang
+    }
   } while (!done);
 }
 
@@ -89,31 +96,21 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Remote arrives carry no data of their own (the payload travels by TMA / st.async with complete_tx on the same
+// barrier, or is a "slot free" signal), so they use the default .release.cta form as CUTLASS's ClusterBarrier does:
+// the .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of every arrive, which stalls
+// the producer for about a microsecond per pipeline stage while loads are in flight.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
-               : "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void st_cluster_u32(uint32_t cluster_addr, uint32_t v) {
-  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
-}
-// wait with cluster-scope acquire: the data published before the (remote) arrive was written by the peer CTA
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  unsigned long long spins = 0;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (!done && ++spins > (1ull << 26)) __trap();
-  } while (!done);
+// 4-byte store into the peer's shared memory whose completion is counted (complete_tx) on the peer's mbarrier: data and
+// signal travel together, no cluster-scope fence on either side
+__device__ __forceinline__ void st_async_cluster_u32(uint32_t cluster_addr, uint32_t v, uint32_t bar_cluster_addr) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];"
+               ::"r"(cluster_addr), "r"(v), "r"(bar_cluster_addr) : "memory");
 }
 // TMA loads of a CTA pair: the completion is signalled on an mbarrier that may live in the peer CTA (cluster address)
 __device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1,

@@ -21,7 +21,12 @@ SHAPES = [  # M, N, K, residual, f32 out, split out, name
 flags = [int(a) for a in sys.argv[1:]] or [0, 1, 2, 6, 8, 16]
 only = os.environ.get('SHAPES')
 if os.environ.get('CUSTOM'):
-    SHAPES = [tuple(int(v) for v in c.split('x')) + (False, True, False, c) for c in os.environ['CUSTOM'].split(',')]
+    # CUSTOM=MxNxK[:rfs] (r = residual, f = f32 output, s = split-bf16 output; default f)
+    SHAPES = []
+    for c in os.environ['CUSTOM'].split(','):
+        dims, _, fl = c.partition(':')
+        fl = fl or 'f'
+        SHAPES.append(tuple(int(v) for v in dims.split('x')) + ('r' in fl, 'f' in fl, 's' in fl, c))
 
 
 def split(t):
