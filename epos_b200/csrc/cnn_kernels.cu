@@ -19,57 +19,81 @@ void set_error(const char* fmt, ...) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// conv1_1: preprocessing + 3x3 s2 conv (pad 1/1, VALID) + bias + ReLU.  8 threads per output pixel,
-// 4 output channels each (Cout = 32).
+// conv1_1: preprocessing + 3x3 s2 conv (pad 1/1, VALID) + bias + ReLU.  One thread per output pixel and
+// 32-channel half: the 27 input values are loaded once (not once per 4-channel group), the filter bank is
+// read from shared memory as warp-wide broadcasts, and a thread writes 128 (f32) / 64 + 64 (split) contiguous bytes.
 // ------------------------------------------------------------------------------------------------
 template <int COUT>
-__global__ void __launch_bounds__(256) conv3x3_rgb_s2_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(128) conv3x3_rgb_s2_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ bias, float* __restrict__ y,
                                                              uint16_t* __restrict__ y_split, long long plane_stride,
                                                              int B, int H, int W, int Ho, int Wo) {
-  __shared__ float sw[27 * COUT];
-  __shared__ float sb[COUT];
+  __shared__ __align__(16) float sw[27 * COUT];
+  __shared__ __align__(16) float sb[COUT];
   for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) sw[i] = w[i];
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias[i];
   __syncthreads();
-  constexpr int G = COUT / 4;
-  const long long total = (long long)B * Ho * Wo * G;
+  constexpr int HALVES = COUT / 32;
+  const long long total = (long long)B * Ho * Wo * HALVES;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % G);
-    long long p = idx / G;
+    // the half index is the slowest so that a warp covers 32 consecutive pixels of one half
+    long long p = idx % ((long long)B * Ho * Wo);
+    const int c0 = (int)(idx / ((long long)B * Ho * Wo)) * 32;
+    const long long pix = p;
     const int ox = (int)(p % Wo);
     p /= Wo;
     const int oy = (int)(p % Ho);
     const int b = (int)(p / Ho);
-    float acc[4] = {sb[g * 4 + 0], sb[g * 4 + 1], sb[g * 4 + 2], sb[g * 4 + 3]};
+    float v[27];
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int iy = oy * 2 - 1 + ky;
-      if (iy < 0 || iy >= H) continue;
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
         const int ix = ox * 2 - 1 + kx;
-        if (ix < 0 || ix >= W) continue;
-        const float* px = x + (((long long)b * H + iy) * W + ix) * 3;
+        const bool in = iy >= 0 && iy < H && ix >= 0 && ix < W;
+        const float* px = x + (((long long)b * H + (in ? iy : 0)) * W + (in ? ix : 0)) * 3;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float v = (2.0f / 255.0f) * __ldg(px + c) - 1.0f;   // feature.py:171-174
-          const float* ww = sw + ((ky * 3 + kx) * 3 + c) * COUT + g * 4;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[j] = fmaf(v, ww[j], acc[j]);
-        }
+        for (int c = 0; c < 3; ++c)                                  // feature.py:171-174; zero padding AFTER the scaling
+          v[(ky * 3 + kx) * 3 + c] = in ? (2.0f / 255.0f) * __ldg(px + c) - 1.0f : 0.f;
       }
     }
-    float4 o = make_float4(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
-    const long long off = (((long long)b * Ho + oy) * Wo + ox) * COUT + g * 4;
-    if (y) *reinterpret_cast<float4*>(y + off) = o;
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = sb[c0 + j];
+    // same accumulation order as before (taps in ky, kx, c order), so results are unchanged bit for bit
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+      const float4* ww = reinterpret_cast<const float4*>(sw + t * COUT + c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 q = ww[j];
+        acc[4 * j + 0] = fmaf(v[t], q.x, acc[4 * j + 0]);
+        acc[4 * j + 1] = fmaf(v[t], q.y, acc[4 * j + 1]);
+        acc[4 * j + 2] = fmaf(v[t], q.z, acc[4 * j + 2]);
+        acc[4 * j + 3] = fmaf(v[t], q.w, acc[4 * j + 3]);
+      }
+    }
+    const long long off = pix * COUT + c0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
+    if (y) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(y + off + 4 * j) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+    }
     if (y_split) {
-      uint2 hi, lo;
-      split_bf16x2(o.x, o.y, hi.x, lo.x);
-      split_bf16x2(o.z, o.w, hi.y, lo.y);
-      *reinterpret_cast<uint2*>(y_split + off) = hi;
-      *reinterpret_cast<uint2*>(y_split + plane_stride + off) = lo;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {                                  // 8 channels = 16 bytes per plane and store
+        uint4 hi, lo;
+        split_bf16x2(acc[8 * j + 0], acc[8 * j + 1], hi.x, lo.x);
+        split_bf16x2(acc[8 * j + 2], acc[8 * j + 3], hi.y, lo.y);
+        split_bf16x2(acc[8 * j + 4], acc[8 * j + 5], hi.z, lo.z);
+        split_bf16x2(acc[8 * j + 6], acc[8 * j + 7], hi.w, lo.w);
+        *reinterpret_cast<uint4*>(y_split + off + 8 * j) = hi;
+        *reinterpret_cast<uint4*>(y_split + plane_stride + off + 8 * j) = lo;
+      }
     }
   }
 }
@@ -554,12 +578,12 @@ int epos_conv3x3_rgb_s2(const float* x, const float* w, const float* bias, float
                         int W, int Cout, void* stream) {
   EPOS_CHECK_ARG(x && w && bias && (y || y_split) && B > 0 && H > 0 && W > 0);
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-  const long long total = (long long)B * Ho * Wo * (Cout / 4);
+  const long long total = (long long)B * Ho * Wo * (Cout / 32);
   const long long plane = (long long)B * Ho * Wo * Cout;
   if (Cout == 32) {
-    conv3x3_rgb_s2_kernel<32><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, y_split, plane, B, H, W, Ho, Wo);
+    conv3x3_rgb_s2_kernel<32><<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>(x, w, bias, y, y_split, plane, B, H, W, Ho, Wo);
   } else if (Cout == 64) {
-    conv3x3_rgb_s2_kernel<64><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, y_split, plane, B, H, W, Ho, Wo);
+    conv3x3_rgb_s2_kernel<64><<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>(x, w, bias, y, y_split, plane, B, H, W, Ho, Wo);
   } else {
     set_error("epos_conv3x3_rgb_s2: Cout=%d unsupported (32, 64)", Cout);
     return EPOS_ERR_UNSUPPORTED;

@@ -179,12 +179,127 @@ __global__ void __launch_bounds__(DT_THREADS) dwconv3x3_rows_kernel(
   }
 }
 
+// The same row-class kernel with the load phase handed to the TMA unit: one cp.async.bulk.tensor.4d per row of the class
+// (box = 32 channels x W pixels; a traversal stride over H would do it in one copy, but elementStrides are limited to 8)
+// on one mbarrier.  No registers or issue slots are spent on the copy, so the resident CTAs of an SM overlap one CTA's
+// arithmetic with the others' loads; ReLU on the input moves to the tap read.
+constexpr int DR_MAX_ROWS = 5;     // rows of a class a thread keeps in registers
+
+__global__ void __launch_bounds__(DT_THREADS) dwconv3x3_rows_tma_kernel(
+    const __grid_constant__ CUtensorMap tmap, const float* __restrict__ w, const float* __restrict__ bias,
+    float* __restrict__ y_f32, uint16_t* __restrict__ y_split, int ldy_split, long long plane_stride, int H, int W, int C,
+    int rate, int relu_in, int relu_out) {
+  extern __shared__ __align__(128) uint8_t dt_smem[];
+  float4* tile = reinterpret_cast<float4*>(dt_smem + ((128u - (smem_u32(dt_smem) & 127u)) & 127u));
+  __shared__ uint64_t bar;
+  const int slab = blockIdx.x, ry = blockIdx.y, b = blockIdx.z;
+  const int Hs = (H - ry + rate - 1) / rate;          // rows ry, ry + r, ... of this class
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&bar, (uint32_t)(Hs * W * DT_SLAB * 4));
+    for (int i = 0; i < Hs; ++i) tma_load_4d(tile + (size_t)i * W * 8, &tmap, &bar, slab * DT_SLAB, 0, ry + i * rate, b);
+  }
+  const int cg = threadIdx.x & 7;
+  const int c = slab * DT_SLAB + cg * 4;
+  const bool c_ok = c < C;
+  const float in_floor = relu_in ? 0.f : -INFINITY;
+  const float out_floor = relu_out ? 0.f : -INFINITY;
+  float4 wk[9];
+  float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int t = 0; t < 9; ++t) wk[t] = c_ok ? __ldg(reinterpret_cast<const float4*>(w + (size_t)t * C + c)) : bb;
+  if (c_ok) bb = __ldg(reinterpret_cast<const float4*>(bias + c));
+  __syncthreads();                                   // the barrier is initialised before anyone polls it
+  mbar_wait(&bar, 0);
+  if (!c_ok) return;
+  // A thread owns one column (and 4 channels) of the class and walks its rows: an input value feeds the outputs of the
+  // rows above, at and below it, so the 9 taps of an output cost 3 shared-memory reads instead of 9.
+  for (int item = threadIdx.x; item < W * 8; item += DT_THREADS) {
+    const int xx = item >> 3;
+    float4 acc[DR_MAX_ROWS];
+#pragma unroll
+    for (int i = 0; i < DR_MAX_ROWS; ++i) acc[i] = bb;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xs = xx + (kx - 1) * rate;
+      if (xs < 0 || xs >= W) continue;
+#pragma unroll
+      for (int ii = 0; ii < DR_MAX_ROWS; ++ii) {
+        if (ii < Hs) {
+          float4 v = tile[(ii * W + xs) * 8 + cg];
+          v.x = fmaxf(v.x, in_floor); v.y = fmaxf(v.y, in_floor); v.z = fmaxf(v.z, in_floor); v.w = fmaxf(v.w, in_floor);
+          if (ii + 1 < DR_MAX_ROWS) {                  // row below: this value is its ky = 0 tap
+            const float4 ww = wk[kx];
+            acc[ii + 1].x = fmaf(v.x, ww.x, acc[ii + 1].x); acc[ii + 1].y = fmaf(v.y, ww.y, acc[ii + 1].y);
+            acc[ii + 1].z = fmaf(v.z, ww.z, acc[ii + 1].z); acc[ii + 1].w = fmaf(v.w, ww.w, acc[ii + 1].w);
+          }
+          {
+            const float4 ww = wk[3 + kx];
+            acc[ii].x = fmaf(v.x, ww.x, acc[ii].x); acc[ii].y = fmaf(v.y, ww.y, acc[ii].y);
+            acc[ii].z = fmaf(v.z, ww.z, acc[ii].z); acc[ii].w = fmaf(v.w, ww.w, acc[ii].w);
+          }
+          if (ii >= 1) {                               // row above: its ky = 2 tap
+            const float4 ww = wk[6 + kx];
+            acc[ii - 1].x = fmaf(v.x, ww.x, acc[ii - 1].x); acc[ii - 1].y = fmaf(v.y, ww.y, acc[ii - 1].y);
+            acc[ii - 1].z = fmaf(v.z, ww.z, acc[ii - 1].z); acc[ii - 1].w = fmaf(v.w, ww.w, acc[ii - 1].w);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < DR_MAX_ROWS; ++i) {
+      if (i < Hs) {
+        float4 a = acc[i];
+        a.x = fmaxf(a.x, out_floor); a.y = fmaxf(a.y, out_floor); a.z = fmaxf(a.z, out_floor); a.w = fmaxf(a.w, out_floor);
+        const long long pix = ((long long)b * H + ry + i * rate) * W + xx;
+        if (y_f32) *reinterpret_cast<float4*>(y_f32 + pix * C + c) = a;
+        if (y_split) {
+          uint2 hi, lo;
+          split_bf16x2(a.x, a.y, hi.x, lo.x);
+          split_bf16x2(a.z, a.w, hi.y, lo.y);
+          *reinterpret_cast<uint2*>(y_split + pix * ldy_split + c) = hi;
+          *reinterpret_cast<uint2*>(y_split + plane_stride + pix * ldy_split + c) = lo;
+        }
+      }
+    }
+  }
+}
+
 static int launch_dw_rows(const float* x, int ldx, const float* w, const float* bias, float* y_f32, uint16_t* y_split,
                           int ldy_split, int B, int H, int W, int C, int rate, int relu_in, int relu_out, cudaStream_t stream) {
   const int hs_max = ceil_div(H, rate);
   const int smem = hs_max * W * DT_SLAB * 4;
   static std::atomic<int> attr[EPOS_MAX_DEVICES];
   const int dslot = device_slot();
+  // TMA path: one box {32 channels, W, 1, 1} per row of the class; box extents are limited to 256
+  static int use_tma = -1;
+  if (use_tma < 0) { const char* e = getenv("EPOS_DW_ROWS_TMA"); use_tma = e ? atoi(e) : 1; }   // developer A/B
+  PFN_encodeTiled enc = get_encode();
+  if (use_tma && enc && W <= 256 && hs_max <= DR_MAX_ROWS && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (ldx % 4) == 0) {
+    CUtensorMap map;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)W * ldx * 4, (cuuint64_t)H * W * ldx * 4};
+    cuuint32_t box[4] = {(cuuint32_t)DT_SLAB, (cuuint32_t)W, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS) {
+      static std::atomic<int> attr_t[EPOS_MAX_DEVICES];
+      const int smem_t = smem + 128;
+      if (smem_t > attr_t[dslot].load(std::memory_order_acquire)) {
+        EPOS_CUDA(cudaFuncSetAttribute(dwconv3x3_rows_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_t));
+        attr_t[dslot].store(smem_t, std::memory_order_release);
+      }
+      dim3 grid(ceil_div(C, DT_SLAB), rate < H ? rate : H, B);
+      dwconv3x3_rows_tma_kernel<<<grid, DT_THREADS, smem_t, stream>>>(map, w, bias, y_f32, y_split, ldy_split,
+                                                                      (long long)B * H * W * ldy_split, H, W, C, rate,
+                                                                      relu_in, relu_out);
+      EPOS_LAUNCH_CHECK();
+      return EPOS_OK;
+    }
+  }
   if (smem > attr[dslot].load(std::memory_order_acquire)) {
     EPOS_CUDA(cudaFuncSetAttribute(dwconv3x3_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr[dslot].store(smem, std::memory_order_release);

@@ -117,7 +117,8 @@ def test_pw_gemm_grouped_bias_and_slices(env):
     (64, 24, 32, 1, 1, True, False), (128, 24, 32, 2, 1, True, False), (728, 15, 20, 1, 2, True, False),
     (1024, 15, 20, 1, 4, False, True), (2048, 15, 20, 1, 12, False, True), (304, 30, 40, 1, 1, False, True),
     (256, 9, 11, 2, 1, True, False), (2048, 15, 20, 1, 36, False, True),
-    (728, 60, 80, 1, 2, True, False), (132, 50, 33, 1, 4, True, True), (20, 17, 19, 1, 1, False, False)])
+    (728, 60, 80, 1, 2, True, False), (132, 50, 33, 1, 4, True, True), (20, 17, 19, 1, 1, False, False),
+    (2048, 60, 80, 1, 24, True, True), (100, 60, 80, 1, 12, True, False), (64, 31, 45, 1, 6, False, False)])
 def test_dwconv(env, C, H, W, stride, rate, relu_in, relu_out):
     from epos_b200 import _lib
     from oracle import cnn
@@ -240,6 +241,32 @@ def test_entry_convs(env):
     torch.cuda.synchronize()
     assert rel_err(c1.cpu().numpy(), r1.permute(0, 2, 3, 1).numpy()) < 1e-5
     assert rel_err(c2.cpu().numpy(), r2.permute(0, 2, 3, 1).numpy()) < 1e-5
+
+
+@pytest.mark.parametrize('cout,H,W', [(32, 64, 96), (64, 37, 51), (32, 480, 640)])
+def test_stem_conv_split_output(env, cout, H, W):
+    """conv1_1 (3x3 stride 2 on the raw image, preprocessing fused): f32 and split-bf16 outputs, both widths, odd sizes."""
+    from epos_b200 import _lib, weights as Wt
+    import torch.nn.functional as F
+    lib, dev = env
+    B = 2
+    img = torch.from_numpy(Wt.synthetic_images(B, seed=H + cout, height=H, width=W)).to(dev)
+    g = torch.Generator(device='cpu').manual_seed(cout)
+    k = (torch.randn(3, 3, 3, cout, generator=g) * 0.3).to(dev)
+    b = torch.randn(cout, generator=g).to(dev)
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty(B, Ho, Wo, cout, device=dev)
+    ys = torch.empty(2, B, Ho, Wo, cout, dtype=torch.bfloat16, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.epos_conv3x3_rgb_s2(img.data_ptr(), k.data_ptr(), b.data_ptr(), y.data_ptr(), ys.data_ptr(), B, H, W, cout, s), 'c1')
+    torch.cuda.synchronize()
+    x = ((2.0 / 255.0) * img.double() - 1.0).permute(0, 3, 1, 2)
+    ref = F.relu(F.conv2d(F.pad(x, (1, 1, 1, 1)), k.double().permute(3, 2, 0, 1), b.double(), stride=2))
+    ref = ref.permute(0, 2, 3, 1)[:, :Ho, :Wo]
+    assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+    rec = ys[0].float() + ys[1].float()
+    assert float((rec - y).abs().max()) <= 2e-5 * float(y.abs().max())
+    assert torch.equal(ys[0], y.to(torch.bfloat16))
 
 
 def test_resize_mean_softmax(env):
