@@ -65,6 +65,7 @@ struct ProbState {
   long long t_sample, t_score, t_replay, t_total;   // main_kernel clock64() accumulators (profiling aid)
   long long t_cut, t_trials, t_final, t_fit;        // other kernels; t_fit = non-minimal fits inside trials (warp 0)
   long long n_scored_main, n_scored_lo, n_scored_final;   // models scored over all N points (roofline accounting)
+  long long pts_skipped;                                  // points the early-out of the main loop did not visit
   long long pad2;
 };
 
@@ -217,7 +218,7 @@ prep_kernel(Workspace ws, const double* __restrict__ c2d, const double* __restri
     st->lo_value = 0.0; st->lo_inl = 0; st->used_pixels = 0; st->chunk_base = 0; st->chunk_n = 0;
     st->t_sample = st->t_score = st->t_replay = st->t_total = 0;
     st->t_cut = st->t_trials = st->t_final = st->t_fit = 0;
-    st->n_scored_main = st->n_scored_lo = st->n_scored_final = 0;
+    st->n_scored_main = st->n_scored_lo = st->n_scored_final = 0; st->pts_skipped = 0;
     st->seed = seeds[p];
     st->max_iteration = iteration_bound(1.0 /* set below */, 1, N > 0 ? N : 1);
     for (int i = 0; i < 12; ++i) { st->best_model[i] = 0.0; st->lo_model[i] = 0.0; }
@@ -488,9 +489,12 @@ __device__ __forceinline__ bool is_inlier(double un, double vn, double x, double
 // cpref != NULL (Progressive-X): *val_out = pixels - (shared support)^2, shared = sum_i min(cpref_i, max(0, 1 - r_i^2/T))
 // over the inliers (scoring_function_with_compound_model.h:216-263).  Summation order as defined by the oracle: point i
 // goes to the partial sum of lane i mod 32 in ascending order, then a butterfly over the lanes.
-__device__ inline void score_warp(const SmemPoints& sp, int N, const double* model, double sq_trunc, unsigned int* bits,
-                                  int lane, int* inl_out, int* pix_out, const double* __restrict__ cpref = nullptr,
-                                  double* val_out = nullptr) {
+// floor_inl > 0: the caller will discard any model with inliers + 1 < floor_inl (the early-out of getScore,
+// scoring_function.h:257-259, as the replay applies it); scoring stops as soon as the count cannot reach that bound any
+// more and reports zero inliers -- which the replay turns into the same decision.  Returns the points NOT visited.
+__device__ inline int score_warp(const SmemPoints& sp, int N, const double* model, double sq_trunc, unsigned int* bits,
+                                 int lane, int* inl_out, int* pix_out, const double* __restrict__ cpref = nullptr,
+                                 double* val_out = nullptr, int floor_inl = 0) {
   double m[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) m[k] = model[k];
@@ -521,6 +525,12 @@ __device__ inline void score_warp(const SmemPoints& sp, int N, const double* mod
       }
       inl += __popc(__ballot_sync(0xffffffffu, in[u]));
     }
+    const int left = N - base - 128;                 // points not visited yet (warp-uniform, like inl)
+    if (left > 0 && inl + left + 1 < floor_inl) {
+      *inl_out = 0; *pix_out = 0;
+      if (val_out) *val_out = 0.0;
+      return left;
+    }
   }
   __syncwarp();
   int px = 0;
@@ -538,6 +548,7 @@ __device__ inline void score_warp(const SmemPoints& sp, int N, const double* mod
     }
     *val_out = v;
   }
+  return 0;
 }
 
 // thread 0 only: end of graphCutLocalOptimization (GCRANSAC.h:799-808) + the caller's bookkeeping (:418-427)
@@ -592,7 +603,8 @@ __device__ __noinline__ void phase_main(const Workspace& ws, const epos_fit_para
       for (int m = 0; m < 4; ++m) { s_inl[tid * 4 + m] = rc->inl[m]; s_val[tid * 4 + m] = rc->val[m]; }
     }
   };
-  // state (identical in every thread)
+  // state (identical in every thread; the replay's results travel through rs)
+  __shared__ struct { unsigned long long iter, max_iteration; double best_value, coverage; int pass, best_inl, lo_runs, gc_count, flags; } rs;
   unsigned long long iter = st->iter, max_iteration = st->max_iteration;
   const unsigned long long seed = st->seed;
   int pass = st->pass, best_inl = st->best_inl, lo_runs = st->lo_runs, gc_count = st->gc_count;
@@ -608,7 +620,7 @@ __device__ __noinline__ void phase_main(const Workspace& ws, const epos_fit_para
   if (pass < chunk_base + chunk_n) stage_chunk();                  // records of a chunk interrupted by an LO round
   __syncthreads();
   bool ended = false, to_lo = false;
-  long long t_sample = 0, t_score = 0, t_replay = 0, n_scored = 0;
+  long long t_sample = 0, t_score = 0, t_replay = 0, n_scored = 0, n_skipped = 0;   // n_skipped: per warp
   const long long t_begin = clock64();
   while (true) {
     long long t0 = clock64();
@@ -648,7 +660,7 @@ __device__ __noinline__ void phase_main(const Workspace& ws, const epos_fit_para
         for (int m = 0; m < nm; ++m) {
           int inl, px;
           double val;
-          score_warp(sp, N, rc->models + 12 * m, sq_trunc, bits, lane, &inl, &px, cpref, &val);
+          n_skipped += score_warp(sp, N, rc->models + 12 * m, sq_trunc, bits, lane, &inl, &px, cpref, &val, best_inl);
           if (lane == 0) { rc->inl[m] = inl; rc->pix[m] = px; rc->val[m] = val; }
         }
       }
@@ -658,8 +670,45 @@ __device__ __noinline__ void phase_main(const Workspace& ws, const epos_fit_para
       if (tid == 0) { int sc = 0; for (int k = 0; k < CHUNK; ++k) sc += s_nm[k]; n_scored += sc; }
       t_score += clock64() - t0; t0 = clock64();
     }
-    // ---- in-order replay (every thread runs the same scalar code on the same records) ----
-    for (int k = pass - chunk_base; k < chunk_n; ++k) {
+    // ---- in-order replay: warp 0 walks the chunk's records (scalar code, every lane the same), the other 19 warps wait;
+    // run by all warps it cost 20x the issue slots for the same dependent chain (0.59 of the main phase's 2.9 Mcycles) ----
+    if (warp == 0) {
+    // Most passes change nothing but the iteration count.  Lane l looks at pass k0 + l: it tests, against the state at the
+    // start of the batch, whether the loop would stop before the pass or a model of the pass would be accepted; the
+    // passes before the first such lane only advance the counters, that pass then runs the scalar code below.
+    int k = pass - chunk_base;
+    while (k < chunk_n && !ended && !to_lo) {
+      const int kl = k + lane;
+      const bool have = kl < chunk_n;
+      const unsigned long long step = have ? 1ull + (unsigned long long)s_fails[kl] : 0ull;
+      unsigned long long incl = step;                              // inclusive prefix sum of the iteration steps
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const unsigned long long it0 = iter + incl - step;           // iteration count when pass kl starts
+      bool event = false;
+      if (have) {
+        const unsigned long long lim = max_iteration < max_iters ? max_iteration : max_iters;
+        if (!(min_iters > it0 || it0 < lim)) event = true;
+        if (min_iters < it0 && (it0 > max_iteration || it0 > max_iters || prm.min_coverage < coverage)) event = true;
+        const int nm = s_nm[kl];
+        for (int m = 0; m < nm; ++m) {
+          const double cv = s_inl[kl * 4 + m] + 1 < best_inl ? 0.0 : s_val[kl * 4 + m];
+          if (best_value < cv) event = true;
+        }
+      }
+      const unsigned int evm = __ballot_sync(0xffffffffu, event);
+      const int nb = chunk_n - k < 32 ? chunk_n - k : 32;          // passes in this batch
+      const int f = evm ? __ffs(evm) - 1 : nb;                     // uneventful passes at the head of the batch
+      if (f > 0) {
+        iter += __shfl_sync(0xffffffffu, incl, f - 1);
+        pass += f; k += f;
+      }
+      if (!evm) continue;
+      // ---- pass k: the sequential code ----
+      {
       const unsigned long long lim = max_iteration < max_iters ? max_iteration : max_iters;
       if (!(min_iters > iter || iter < lim)) { ended = true; break; }
       if (min_iters < iter) {
@@ -676,25 +725,35 @@ __device__ __noinline__ void phase_main(const Workspace& ws, const epos_fit_para
         if (c_inl + 1 < best_inl) { c_inl = 0; c_val = 0.0; }     // early-out of getScore, scoring_function.h:257-259
         if (best_value < c_val) {
           best_value = c_val; best_inl = c_inl;
-          __syncthreads();
-          if (tid < 12) best_model[tid] = rc->models[12 * m + tid];
-          __syncthreads();
+          if (lane < 12) best_model[lane] = rc->models[12 * m + lane];
           do_lo = iter > (unsigned long long)prm.min_iters_before_lo && best_inl > 3;
           max_iteration = iteration_bound(1.0, best_inl, N);
           coverage = (double)best_value / (double)used_pixels;
         }
       }
-      ++pass;
+      ++pass; ++k;
       if (do_lo) {
         lo_runs += 2;                                               // GCRANSAC.h:409 and :702
         if (gc_count + 1 < prm.max_graph_cuts) { to_lo = true; break; }
         ++gc_count;                                                 // budget exhausted: the while at :710 exits at once
       }
+      }
     }
+    if (lane == 0) {
+      rs.iter = iter; rs.max_iteration = max_iteration; rs.best_value = best_value; rs.coverage = coverage;
+      rs.pass = pass; rs.best_inl = best_inl; rs.lo_runs = lo_runs; rs.gc_count = gc_count;
+      rs.flags = (ended ? 1 : 0) | (to_lo ? 2 : 0);
+    }
+    }
+    __syncthreads();
+    iter = rs.iter; max_iteration = rs.max_iteration; best_value = rs.best_value; coverage = rs.coverage;
+    pass = rs.pass; best_inl = rs.best_inl; lo_runs = rs.lo_runs; gc_count = rs.gc_count;
+    ended = rs.flags & 1; to_lo = rs.flags & 2;
     __syncthreads();
     t_replay += clock64() - t0;
     if (ended || to_lo) break;
   }
+  if (lane == 0 && n_skipped) atomicAdd(reinterpret_cast<unsigned long long*>(&st->pts_skipped), (unsigned long long)n_skipped);
   if (tid == 0) {
     st->t_sample += t_sample; st->t_score += t_score; st->t_replay += t_replay; st->t_total += clock64() - t_begin;
     st->n_scored_main += n_scored;
@@ -2137,7 +2196,7 @@ int epos_fit_max_points(void) { return NMAX; }
 // Profiling / debugging aid: copies per-problem counters out of a workspace after epos_fit_poses (synchronises).
 // out [P][EPOS_FIT_DEBUG_COLS] i64: N, used_pixels, iterations, passes, graph_cuts, lo_runs, phase, best_inliers,
 //                  clocks (sample+P3P, scoring, replay, main total, cut, trials, final, trial fits),
-//                  models scored over all N points in main / LO trials / final, reserved.
+//                  models scored over all N points in main / LO trials / final, points the early-out skipped.
 int epos_fit_debug_state(const void* workspace, int P, long long* out) {
   EPOS_CHECK_ARG(workspace && out && P > 0);
   Workspace ws;
@@ -2152,7 +2211,7 @@ int epos_fit_debug_state(const void* workspace, int P, long long* out) {
     o[5] = h[i].lo_runs; o[6] = h[i].phase; o[7] = h[i].best_inl; o[8] = h[i].t_sample; o[9] = h[i].t_score;
     o[10] = h[i].t_replay; o[11] = h[i].t_total; o[12] = h[i].t_cut; o[13] = h[i].t_trials; o[14] = h[i].t_final;
     o[15] = h[i].t_fit;
-    o[16] = h[i].n_scored_main; o[17] = h[i].n_scored_lo; o[18] = h[i].n_scored_final; o[19] = 0;
+    o[16] = h[i].n_scored_main; o[17] = h[i].n_scored_lo; o[18] = h[i].n_scored_final; o[19] = h[i].pts_skipped;
   }
   free(h);
   return EPOS_OK;

@@ -57,9 +57,10 @@ class PoseFitter:
 
     def algorithmic_bytes(self, P):
         """SURVEY.md 8d RANSAC figure for the last fit: every model scored over a problem's N points reads
-        N x 40 B (u_n, v_n, x, y, z in f64) + N x 8 B (pixel id)."""
+        N x 40 B (u_n, v_n, x, y, z in f64) + N x 8 B (pixel id); points the main loop's early-out never visited
+        (column 19) are not counted."""
         d = self.debug_state(P)
-        return float((d[:, 0] * (d[:, 16] + d[:, 17] + d[:, 18])).sum()) * 48.0
+        return float((d[:, 0] * (d[:, 16] + d[:, 17] + d[:, 18]) - d[:, 19]).sum()) * 48.0
 
 
 def multi_params(max_model_number_for_pearl=5, min_point_number=6, confidence=0.5, max_tanimoto_similarity=0.9):

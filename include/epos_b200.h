@@ -240,7 +240,7 @@ int epos_fit_max_points(void);
  * then clock64() totals: main phase sampling+P3P, scoring, replay, whole; cut, trials, final phases; fits inside trials
  * (warp 0); then the number of models scored over all N points in the main loop / the LO trials / the final phase
  * (the "hypotheses" of SURVEY.md 8d's algorithmic-bytes figure: each costs N x 40 B of points + N x 8 B of pixel ids),
- * one reserved column. */
+ * then the number of points the main loop's early-out did not visit (to be subtracted from models x N). */
 #define EPOS_FIT_DEBUG_COLS 20
 int epos_fit_debug_state(const void* workspace, int P, long long* out);
 
