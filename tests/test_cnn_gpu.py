@@ -94,6 +94,34 @@ def test_pw_gemm_balanced_pieces_cover_everything(env):
         assert bool(torch.isnan(buf[M:]).all()) and bool(torch.isnan(buf[:, N:]).all()), (M, N, K)
 
 
+@pytest.mark.parametrize('M,N,K,reps', [(153600, 256, 64, 12), (38400, 728, 128, 4), (9000, 512, 200, 4)])
+def test_pw_gemm_pair_three_outputs_repeated(env, M, N, K, reps):
+    """CTA-pair GEMM with the slowest epilogue (residual + f32 + split-bf16 outputs) on short-K shapes, launched
+    repeatedly: the case in which a consumer's "slot consumed" signal once overtook its read of the piece queue
+    (the kernel then hung on 100 % of the launches of 153600 x 256 x 64).  Every launch must finish and be exact."""
+    from epos_b200 import _lib
+    lib, dev = env
+    g = torch.Generator(device='cpu').manual_seed(N + K)
+    a = torch.randn(M, K, generator=g).to(dev)
+    w = (torch.randn(N, K, generator=g) * 0.1).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    res = torch.randn(M, N, generator=g).to(dev)
+    ref = (a[:4096].double() @ w.double().T + bias.double() + res[:4096].double()).clamp_min(0)
+    a_s, w_s = split(a), split(w)
+    s = torch.cuda.current_stream().cuda_stream
+    for it in range(reps):
+        d = torch.full((M, N), float('nan'), device=dev)
+        ds = torch.zeros((2, M, N), dtype=torch.bfloat16, device=dev)
+        _lib.check(lib.epos_pwconv_gemm(a_s.data_ptr(), K, a_s.stride(0), w_s.data_ptr(), K, bias.data_ptr(), 0,
+                                        res.data_ptr(), N, d.data_ptr(), N, ds.data_ptr(), N, ds.stride(0),
+                                        M, N, K, 1, s), 'gemm')
+        torch.cuda.synchronize()
+        assert not bool(torch.isnan(d).any()), it
+        assert rel_err(d[:4096].cpu().numpy(), ref.cpu().numpy()) < 2e-5, it
+        assert torch.equal(ds[0], d.to(torch.bfloat16)), it
+        assert float((ds[0][-4096:].float() + ds[1][-4096:].float() - d[-4096:]).abs().max()) <= 2e-5 * float(d.abs().max())
+
+
 def test_pw_gemm_grouped_bias_and_slices(env):
     """per-image bias rows (image-pooling fold) and strided output slices (concat buffers)."""
     from epos_b200 import _lib
