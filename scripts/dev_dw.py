@@ -16,7 +16,7 @@ for (B, H, W, C, stride, rate) in shapes:
     w = torch.randn(9, C, device=dev); b = torch.randn(C, device=dev)
     s = torch.cuda.current_stream().cuda_stream
     def run(i):
-        _lib.check(lib.epos_dwconv3x3(xs[i % nb].data_ptr(), LDX, w.data_ptr(), b.data_ptr(), None, ys[i % nb].data_ptr(), LDY, B, H, W, C, stride, rate, 1, 0, s), 'dw')
+        _lib.check(lib.epos_dwconv3x3(xs[i % nb].data_ptr(), LDX, w.data_ptr(), b.data_ptr(), None, ys[i % nb].data_ptr(), LDY, B, H, W, C, stride, rate, int(os.environ.get('RELU_IN', '1')), 0, s), 'dw')
     for i in range(3): run(i)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
