@@ -551,6 +551,85 @@ __device__ inline int score_warp(const SmemPoints& sp, int N, const double* mode
   return 0;
 }
 
+// Two models in one sweep over the points (the solutions of a P3P sample come in pairs more often than not): a point
+// is read from shared memory once and tested against both -- the single-model sweep is bound as much by its 40 B per
+// point of shared-memory reads as by the FP64 pipe.  Same per-point arithmetic, same counting and summation order per
+// model as score_warp; bitsA / bitsB: two per-warp bitsets.  Returns the points not visited (both models, when neither can
+// reach floor_inl any more).
+__device__ inline int score_warp2(const SmemPoints& sp, int N, const double* modelA, const double* modelB, double sq_trunc,
+                                  unsigned int* bitsA, unsigned int* bitsB, int lane, int* inl_out, int* pix_out,
+                                  const double* __restrict__ cpref, double* val_out, int floor_inl) {
+  double ma[12], mb[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) { ma[k] = modelA[k]; mb[k] = modelB[k]; }
+  for (int k = lane; k < NMAX / 32; k += 32) { bitsA[k] = 0u; bitsB[k] = 0u; }
+  __syncwarp();
+  int inlA = 0, inlB = 0;
+  double sharedA = 0.0, sharedB = 0.0;
+  for (int base = 0; base < N; base += 64) {
+    bool ia[2], ib[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = base + u * 32 + lane;
+      ia[u] = ib[u] = false;
+      if (i < N) {
+        const double un = sp.un[i], vn = sp.vn[i], x = sp.x[i], y = sp.y[i], z = sp.z[i];
+        ia[u] = is_inlier(un, vn, x, y, z, ma, sq_trunc);
+        ib[u] = is_inlier(un, vn, x, y, z, mb, sq_trunc);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = base + u * 32 + lane;
+      if (ia[u] || ib[u]) {
+        const unsigned int pid = sp.pix[i];
+        if (ia[u]) atomicOr(&bitsA[pid >> 5], 1u << (pid & 31));
+        if (ib[u]) atomicOr(&bitsB[pid >> 5], 1u << (pid & 31));
+        if (cpref) {
+          const double c = cpref[i];
+          if (ia[u]) {
+            double pref = 1.0 - sq_residual(sp.un[i], sp.vn[i], sp.x[i], sp.y[i], sp.z[i], ma) / sq_trunc;
+            if (!(pref > 0.0)) pref = 0.0;
+            sharedA += c < pref ? c : pref;
+          }
+          if (ib[u]) {
+            double pref = 1.0 - sq_residual(sp.un[i], sp.vn[i], sp.x[i], sp.y[i], sp.z[i], mb) / sq_trunc;
+            if (!(pref > 0.0)) pref = 0.0;
+            sharedB += c < pref ? c : pref;
+          }
+        }
+      }
+      inlA += __popc(__ballot_sync(0xffffffffu, ia[u]));
+      inlB += __popc(__ballot_sync(0xffffffffu, ib[u]));
+    }
+    const int left = N - base - 64;
+    if (left > 0 && inlA + left + 1 < floor_inl && inlB + left + 1 < floor_inl) {
+      inl_out[0] = inl_out[1] = 0; pix_out[0] = pix_out[1] = 0; val_out[0] = val_out[1] = 0.0;
+      return 2 * left;
+    }
+  }
+  __syncwarp();
+  int pxA = 0, pxB = 0;
+  for (int k = lane; k < NMAX / 32; k += 32) { pxA += __popc(bitsA[k]); pxB += __popc(bitsB[k]); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    pxA += __shfl_xor_sync(0xffffffffu, pxA, o);
+    pxB += __shfl_xor_sync(0xffffffffu, pxB, o);
+  }
+  inl_out[0] = inlA; inl_out[1] = inlB; pix_out[0] = pxA; pix_out[1] = pxB;
+  double vA = (double)pxA, vB = (double)pxB;
+  if (cpref) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sharedA += __shfl_xor_sync(0xffffffffu, sharedA, o);
+      sharedB += __shfl_xor_sync(0xffffffffu, sharedB, o);
+    }
+    vA -= sharedA * sharedA; vB -= sharedB * sharedB;
+  }
+  val_out[0] = vA; val_out[1] = vB;
+  return 0;
+}
+
 // thread 0 only: end of graphCutLocalOptimization (GCRANSAC.h:799-808) + the caller's bookkeeping (:418-427)
 __device__ inline void finalize_lo(ProbState* st, const epos_fit_params& prm) {
   if (st->best_value < st->lo_value) {
@@ -588,7 +667,8 @@ __device__ __noinline__ void phase_main(const Workspace& ws, const epos_fit_para
   SmemPoints sp;
   unsigned char* rest = load_points(smem_raw, ws, p, N, &sp, pts_loaded);
   unsigned int* bits = reinterpret_cast<unsigned int*>(rest) + warp * (NMAX / 32);
-  double* best_model = reinterpret_cast<double*>(rest + WARPS * (NMAX / 32) * 4);
+  unsigned int* bits2 = bits + WARPS * (NMAX / 32);                 // second per-warp bitset (two models per sweep)
+  double* best_model = reinterpret_cast<double*>(rest + 2 * WARPS * (NMAX / 32) * 4);
   // the replay's view of the chunk: the small per-pass fields staged in shared memory (the replay is a dependent chain of
   // reads; from the L2-resident records it cost ~2000 cycles per pass, i.e. a quarter of the main phase)
   double* s_val = best_model + 12;                                 // [CHUNK][4]
@@ -657,7 +737,18 @@ __device__ __noinline__ void phase_main(const Workspace& ws, const epos_fit_para
       for (int k = warp; k < CHUNK; k += WARPS) {
         PassRecord* rc = recs + k;
         const int nm = rc->nm;
-        for (int m = 0; m < nm; ++m) {
+        int m = 0;
+        for (; m + 1 < nm; m += 2) {                                 // two solutions per sweep over the points
+          int inl[2], px[2];
+          double val[2];
+          n_skipped += score_warp2(sp, N, rc->models + 12 * m, rc->models + 12 * (m + 1), sq_trunc, bits, bits2, lane, inl, px,
+                                   cpref, val, best_inl);
+          if (lane == 0) {
+            rc->inl[m] = inl[0]; rc->pix[m] = px[0]; rc->val[m] = val[0];
+            rc->inl[m + 1] = inl[1]; rc->pix[m + 1] = px[1]; rc->val[m + 1] = val[1];
+          }
+        }
+        if (m < nm) {
           int inl, px;
           double val;
           n_skipped += score_warp(sp, N, rc->models + 12 * m, sq_trunc, bits, lane, &inl, &px, cpref, &val, best_inl);
@@ -2164,7 +2255,7 @@ fit_kernel(Workspace ws, epos_fit_params prm, const int* __restrict__ offsets, d
 constexpr size_t SMEM_POINTS = 5 * NMAX * 8 + NMAX * 2;
 constexpr size_t SMEM_PREP = 5 * NMAX * 4 + 8192 * 8 + 64 * 4 + 8192 * 2 + 64;
 static_assert(sizeof(PassRecord) <= 464 && CHUNK == 80, "workspace_layout reserves 80 x 464 bytes of pass records");
-constexpr size_t SMEM_MAIN = SMEM_POINTS + WARPS * (NMAX / 32) * 4 + 12 * 8 + CHUNK * (4 * 8 + 4 * 4 + 4 + 4) + 64;
+constexpr size_t SMEM_MAIN = SMEM_POINTS + 2 * WARPS * (NMAX / 32) * 4 + 12 * 8 + CHUNK * (4 * 8 + 4 * 4 + 4 + 4) + 64;
 constexpr size_t SMEM_CUT = SMEM_CUT_DYN;
 static_assert(FIT_SCRATCH_DOUBLES * 8 >= (NMAX / 32) * 4, "bitset must fit in the fit scratch");
 constexpr size_t SMEM_TRIALS = SMEM_POINTS + MAX_TRIALS * sizeof(TrialRecord) +
