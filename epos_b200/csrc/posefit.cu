@@ -356,42 +356,50 @@ prep_kernel(Workspace ws, const double* __restrict__ c2d, const double* __restri
   __syncthreads();
   for (int i = tid; i < N; i += PT) { int cx, cy; cell_of(i, &cx, &cy); sorted[atomicSub(&cursor[cy * gw + cx], 1) - 1] = (unsigned short)i; }
   __syncthreads();
-  for (int i = tid; i < N; i += PT) {
-    float bd[MAXNB];
-    int bj[MAXNB];
+  auto knn = [&](auto kn_tag) {
+    // KEEP = entries kept per point: the compile-time neighbour count (default 5) or MAXNB for any other setting.  Only
+    // the KN nearest are written, and once KEEP are known a candidate that does not beat the worst of them -- most of
+    // them, in the dense many-to-many neighbourhoods -- costs two comparisons instead of a walk over the list.
+    constexpr int KEEP = decltype(kn_tag)::value;
+    for (int i = tid; i < N; i += PT) {
+      float bd[KEEP];
+      int bj[KEEP];
 #pragma unroll
-    for (int k = 0; k < MAXNB; ++k) { bd[k] = INFINITY; bj[k] = -1; }
-    const float a0 = q[i], a1 = q[NMAX + i], a2 = q[2 * NMAX + i], a3 = q[3 * NMAX + i], a4 = q[4 * NMAX + i];
-    int cx, cy;
-    cell_of(i, &cx, &cy);
-    for (int yy = max(cy - 1, 0); yy <= min(cy + 1, gh - 1); ++yy) {
-      const int c0 = yy * gw + max(cx - 1, 0), c1 = yy * gw + min(cx + 1, gw - 1);
-      for (int s_ = cell_start[c0]; s_ < cell_start[c1 + 1]; ++s_) {      // the <= 3 cells of a row are contiguous
-        const int j = sorted[s_];
-        float e, d = 0.f;
-        e = a0 - q[j]; d = __fmaf_rn(e, e, d);
-        e = a1 - q[NMAX + j]; d = __fmaf_rn(e, e, d);
-        e = a2 - q[2 * NMAX + j]; d = __fmaf_rn(e, e, d);
-        e = a3 - q[3 * NMAX + j]; d = __fmaf_rn(e, e, d);
-        e = a4 - q[4 * NMAX + j]; d = __fmaf_rn(e, e, d);
-        if (j == i || !(d <= r2)) continue;
-        // insert keeping (d, j) ascending lexicographically
-        float cd = d; int cj = j;
-        bool ins = false;
+      for (int k = 0; k < KEEP; ++k) { bd[k] = INFINITY; bj[k] = -1; }
+      const float a0 = q[i], a1 = q[NMAX + i], a2 = q[2 * NMAX + i], a3 = q[3 * NMAX + i], a4 = q[4 * NMAX + i];
+      int cx, cy;
+      cell_of(i, &cx, &cy);
+      for (int yy = max(cy - 1, 0); yy <= min(cy + 1, gh - 1); ++yy) {
+        const int c0 = yy * gw + max(cx - 1, 0), c1 = yy * gw + min(cx + 1, gw - 1);
+        for (int s_ = cell_start[c0]; s_ < cell_start[c1 + 1]; ++s_) {      // the <= 3 cells of a row are contiguous
+          const int j = sorted[s_];
+          float e, d = 0.f;
+          e = a0 - q[j]; d = __fmaf_rn(e, e, d);
+          e = a1 - q[NMAX + j]; d = __fmaf_rn(e, e, d);
+          e = a2 - q[2 * NMAX + j]; d = __fmaf_rn(e, e, d);
+          e = a3 - q[3 * NMAX + j]; d = __fmaf_rn(e, e, d);
+          e = a4 - q[4 * NMAX + j]; d = __fmaf_rn(e, e, d);
+          if (j == i || !(d <= r2)) continue;
+          if (bj[KEEP - 1] >= 0 && !(d < bd[KEEP - 1] || (d == bd[KEEP - 1] && j < bj[KEEP - 1]))) continue;
+          // insert keeping (d, j) ascending lexicographically
+          float cd = d; int cj = j;
+          bool ins = false;
 #pragma unroll
-        for (int k = 0; k < MAXNB; ++k) {
-          if (ins || bj[k] < 0 || cd < bd[k] || (cd == bd[k] && cj < bj[k])) {
-            const float td = bd[k]; const int tj = bj[k];
-            bd[k] = cd; bj[k] = cj; cd = td; cj = tj;
-            ins = true;
-            if (cj < 0) break;
+          for (int k = 0; k < KEEP; ++k) {
+            if (ins || bj[k] < 0 || cd < bd[k] || (cd == bd[k] && cj < bj[k])) {
+              const float td = bd[k]; const int tj = bj[k];
+              bd[k] = cd; bj[k] = cj; cd = td; cj = tj;
+              ins = true;
+              if (cj < 0) break;
+            }
           }
         }
       }
-    }
 #pragma unroll
-    for (int k = 0; k < MAXNB; ++k) nbr[(size_t)i * MAXNB + k] = (short)((k < KN) ? bj[k] : -1);
-  }
+      for (int k = 0; k < MAXNB; ++k) nbr[(size_t)i * MAXNB + k] = (short)((k < KN && k < KEEP) ? bj[k < KEEP ? k : 0] : -1);
+    }
+  };
+  if (KN == 5) knn(std::integral_constant<int, 5>{}); else knn(std::integral_constant<int, MAXNB>{});
   __syncthreads();
   // ---- edge ownership + reverse adjacency (GCRANSAC.h:864-907: each undirected pair is added once, by the first
   // endpoint that lists it in ascending point order) ----
