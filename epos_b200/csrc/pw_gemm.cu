@@ -20,7 +20,12 @@
 //               split-bf16 stores through a per-warp smem transpose (coalesced); double-buffered accumulators
 //               (2 x BLOCK_N TMEM columns) overlap the epilogue of tile i with the main loop of tile i+1
 // Work is handed out dynamically (PieceMap + a global counter); PAIR = true runs the same roles on a cluster of two
-// CTAs with tcgen05.mma.cta_group::2 (M = 256, each CTA holds half of the W tile).
+// CTAs with tcgen05.mma.cta_group::2 (M = 256, each CTA holds half of the W tile): the leader CTA issues the MMAs and owns
+// the barriers; the peer's producer signals the leader's "stage full" barrier (plain remote arrive + its TMA's complete_tx),
+// tcgen05.commit multicasts "stage empty" / "accumulator full" to both CTAs, the piece index reaches the peer by st.async.
+// Cross-CTA signals carry no .release.cluster (that is a MEMBAR.ALL.GPU per arrive); the one signal that follows a read of
+// shared memory ("queue slot consumed") is predicated on the value read, because a remote arrive does not wait for an
+// earlier LDS of the same thread.
 #include <cuda.h>
 #include <stdlib.h>
 #include "common.cuh"
