@@ -455,6 +455,38 @@ def test_graph_engine_equals_eager_engine(pipelined):
         assert np.array_equal(outs[-1]['poses'].cpu().numpy(), ref_dev[-1]), ('back to back', graphs)
 
 
+def test_full_size_pipelined_graph_engine_is_deterministic_under_overlap():
+    """The benchmark configuration (8 x 480 x 640, 21 objects x 64 fragments, CUDA graphs, pose fitting of batch i under
+    the CNN of batch i + 1): the same batch fed 10 times back to back must give bit-identical head maps every time --
+    the CTA-pair GEMMs take their tiles from a queue while the fit kernel's CTAs come and go on the same SMs -- and the
+    records of a second engine fed the same sequence must be identical (same seeds per batch index)."""
+    from epos_b200 import engine, model, synthetic, weights as W
+    O, F, B = 21, 64, 8
+    w = W.random_init(O, F, seed=0, logits_std=300.0)
+    store, K = synthetic.model_store(O, F), synthetic.default_K()
+    img = torch.from_numpy(W.synthetic_images(B, seed=3)).to(DEV)
+    runs = []
+    for rep in range(2):
+        eng = engine.Engine(w, O, F, DEV, stages=engine.STAGES_FULL, model_store=store, K=K, max_correspondences=4096,
+                            seed=99, pipelined=True, graphs=True)
+        maps, recs = [], []
+        outs = [eng.run_device(img) for _ in range(10)]          # back to back: fit of batch i overlaps CNN of batch i + 1
+        eng.join()
+        torch.cuda.synchronize()
+        # the two buffer sets hold the maps of the last two batches; every batch's records were cloned
+        for o in outs[-2:]:
+            maps.append((o[model.PRED_OBJ_CONF].clone(), o[model.PRED_FRAG_CONF].clone()))
+        assert torch.equal(maps[0][0], maps[1][0]) and torch.equal(maps[0][1], maps[1][1])
+        eng2_first = eng.run_device(img)                         # one more, alone (nothing overlapping its CNN)
+        eng.join()
+        torch.cuda.synchronize()
+        assert torch.equal(eng2_first[model.PRED_OBJ_CONF], maps[0][0]) and torch.equal(eng2_first[model.PRED_FRAG_CONF], maps[0][1])
+        runs.append([o['poses'].cpu().numpy().copy() for o in outs])
+    for i, (a, b) in enumerate(zip(*runs)):
+        assert np.array_equal(a, b), i
+    assert sum(float(r[..., 14].sum()) for r in runs[0]) > 0
+
+
 def test_graph_engine_cnn_only():
     from epos_b200 import engine, model, weights as W
     O, F, B = 2, 8, 2
