@@ -46,6 +46,7 @@ _SIGS = {
     'epos_global_mean': (i32, [vp, vp, i32, i32, i32, vp]),
     'epos_resize_bilinear': (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
     'epos_softmax_rows': (i32, [vp, vp, sz, i32, vp]),
+    'epos_softmax_rows_masked': (i32, [vp, vp, sz, i32, i32, f32, vp]),
     'epos_preprocess_u8': (i32, [vp, i32, i32, sz, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
     'epos_corresp': (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, f64, f32, f32, i32, i32,
                            vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),

@@ -479,6 +479,32 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x
   }
 }
 
+// The same softmax over the F fragment confidences of a (pixel, object) pair, only for the pairs the correspondence
+// extraction will read: those whose object confidence exceeds its threshold (corresp.py:46-60).  Other rows keep their
+// logits.  Engine path only (model.predict materialises the whole tensor); identical arithmetic per row.
+__global__ void __launch_bounds__(256) softmax_rows_masked_kernel(float* __restrict__ x, const float* __restrict__ obj_conf,
+                                                                  long long pixels, int O, int F, float min_obj_conf) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long rows = pixels * O;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const long long p = r / O;
+    const int o = (int)(r - p * O);
+    if (!(__ldg(obj_conf + p * (O + 1) + o + 1) > min_obj_conf)) continue;
+    float* row = x + r * F;
+    float m = -INFINITY;
+    for (int i = lane; i < F; i += 32) m = fmaxf(m, row[i]);
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o2));
+    float s = 0.f;
+    for (int i = lane; i < F; i += 32) s += expf(row[i] - m);
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
+    for (int i = lane; i < F; i += 32) row[i] = expf(row[i] - m) / s;
+  }
+}
+
 // Tiny-M fp32 GEMM (M <= 16: the image-pooling branch has M = batch): one warp per output column, lanes stride over K
 // (coalesced W rows), the M accumulators live in registers and are reduced with shuffles.
 constexpr int SMALLM_MAX = 16;
@@ -689,6 +715,16 @@ int epos_softmax_rows(float* x, int64_t* labels, size_t rows, int n, void* strea
   const long long blocks = ((long long)rows + 7) / 8;
   softmax_rows_kernel<<<(int)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, (cudaStream_t)stream>>>(
       x, labels, (long long)rows, n);
+  EPOS_LAUNCH_CHECK();
+  return EPOS_OK;
+}
+
+int epos_softmax_rows_masked(float* x, const float* obj_conf, size_t pixels, int num_objs, int num_frags, float min_obj_conf,
+                             void* stream) {
+  EPOS_CHECK_ARG(x && obj_conf && pixels > 0 && num_objs > 0 && num_frags > 0);
+  const long long blocks = ((long long)pixels * num_objs + 7) / 8;
+  softmax_rows_masked_kernel<<<(int)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+      x, obj_conf, (long long)pixels, num_objs, num_frags, min_obj_conf);
   EPOS_LAUNCH_CHECK();
   return EPOS_OK;
 }

@@ -37,6 +37,8 @@ class Engine:
         # full path: pred_frag_loc is evaluated only at the surviving correspondences (model.EposNet.heads); the CNN-only
         # stage keeps the materialising mode = the output contract of model.predict
         self.lazy_loc = bool(lazy_loc) and stages == STAGES_FULL
+        # with it, the fragment softmax (when not fused into the GEMM) runs only on the (pixel, object) pairs above min_obj_conf
+        self.sparse_conf = float(min_obj_conf) if self.lazy_loc else None
         self.pipelined = bool(pipelined) and stages == STAGES_FULL
         self._side = torch.cuda.Stream(device=self.dev) if self.pipelined else None
         self._copy = torch.cuda.Stream(device=self.dev) if self.pipelined else None    # H2D of the next batch
@@ -81,7 +83,7 @@ class Engine:
         cap = torch.cuda.Stream(device=self.dev)
         cap.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(cap):
-            out = self.net.predict(warm, lazy_loc=self.lazy_loc)
+            out = self.net.predict(warm, lazy_loc=self.lazy_loc, sparse_conf=self.sparse_conf)
             if self._fitter is not None:
                 self._fitter.fit(out)
         cap.synchronize()
@@ -92,7 +94,7 @@ class Engine:
             g = torch.cuda.CUDAGraph()
             l0 = lib.epos_launch_count()
             with torch.cuda.graph(g, pool=pool, stream=cap, capture_error_mode='thread_local'):
-                gs['out'] = self.net.predict(gs['x'], lazy_loc=self.lazy_loc)
+                gs['out'] = self.net.predict(gs['x'], lazy_loc=self.lazy_loc, sparse_conf=self.sparse_conf)
             gs['cnn'] = g
             gs['cnn_launches'] = int(lib.epos_launch_count() - l0)
             # Serial engine: the two CNN graphs replay strictly one after the other, so they may share a private pool.
@@ -177,7 +179,7 @@ class Engine:
         instance of the Progressive-X problems."""
         if self.graphs and num_instances is None:
             return self._run_graph(images_dev, K)
-        out = self.net.predict(images_dev, lazy_loc=self.lazy_loc)
+        out = self.net.predict(images_dev, lazy_loc=self.lazy_loc, sparse_conf=self.sparse_conf)
         if self._fitter is None:
             return out
         if not self.pipelined:

@@ -437,12 +437,14 @@ class EposNet:
         self.end_points['decoder'] = (y1, dh_, dw_, 256)
         return y1s, B, dh_, dw_
 
-    def heads(self, feat_split, B, h, w, lazy_loc=False):
+    def heads(self, feat_split, B, h, w, lazy_loc=False, sparse_conf=None):
         """Logit heads + softmax/argmax (model.py:448-456, 676-685).  Materialising mode (the drop-in contract of
         model.predict) writes all four maps.  lazy_loc=True (engine path) skips the pred_frag_loc GEMM -- 3 O F columns,
         2.4 GB per image at O = 30 / F = 256, read back at <= max_correspondences rows per object -- and returns the
         decoder features and the f32 logit weights instead; corresp.CorrespExtractor evaluates the head at the
-        surviving rows only."""
+        surviving rows only.  sparse_conf = min_obj_conf (engine path, F != 64): the fragment softmax runs only on the
+        (pixel, object) pairs whose object confidence exceeds it -- the pairs establish_many_to_many reads; the other
+        rows of pred_frag_conf keep their logits."""
         M = B * h * w
         O, F = self.O, self.F
         obj, _ = self.gemm(feat_split, self.p['logits/' + PRED_OBJ_CONF], M, relu=False, pad_f32=False)
@@ -452,7 +454,10 @@ class EposNet:
         fc, _ = self.gemm(feat_split, self.p['logits/' + PRED_FRAG_CONF], M, relu=2 if fused else False, pad_f32=False)
         labels = torch.empty((M,), dtype=torch.int64, device=self.dev)
         _lib.check(self.lib.epos_softmax_rows(obj.data_ptr(), labels.data_ptr(), M, O + 1, self._s()), 'epos_softmax_rows')
-        if not fused:
+        if not fused and sparse_conf is not None:
+            _lib.check(self.lib.epos_softmax_rows_masked(fc.data_ptr(), obj.data_ptr(), M, O, F, float(sparse_conf), self._s()),
+                       'epos_softmax_rows_masked')
+        elif not fused:
             _lib.check(self.lib.epos_softmax_rows(fc.data_ptr(), None, M * O, F, self._s()), 'epos_softmax_rows')
         out = {PRED_OBJ_CONF: obj.view(B, h, w, O + 1), PRED_OBJ_LABEL: labels.view(B, h, w),
                PRED_FRAG_CONF: fc.view(B, h, w, O, F)}
@@ -464,9 +469,9 @@ class EposNet:
             out[PRED_FRAG_LOC] = fl.view(B, h, w, O, F, 3)
         return out
 
-    def predict(self, images, lazy_loc=False):
+    def predict(self, images, lazy_loc=False, sparse_conf=None):
         feat, B, h, w = self.forward_features(images)
-        return self.heads(feat, B, h, w, lazy_loc)
+        return self.heads(feat, B, h, w, lazy_loc, sparse_conf)
 
 
 _NETS = {}

@@ -137,6 +137,12 @@ int epos_resize_bilinear(const float* x, float* y, int ldy, int B, int Hi, int W
  * argmax as int64 (model.py:683). */
 int epos_softmax_rows(float* x, int64_t* labels, size_t rows, int n, void* stream);
 
+/* Engine path: tf.nn.softmax over the fragment axis (model.py:676-678) of x [pixels][num_objs][num_frags] (in place) only for
+ * the (pixel, object) pairs with obj_conf [pixels][num_objs + 1] (softmaxed, channel 0 = background) above min_obj_conf --
+ * the pairs establish_many_to_many reads (corresp.py:46-60).  Other rows keep their logits. */
+int epos_softmax_rows_masked(float* x, const float* obj_conf, size_t pixels, int num_objs, int num_frags, float min_obj_conf,
+                             void* stream);
+
 /* Input side (datagen.py:424-476 _parse_and_preprocess, misc.py:75-91 resize_image_tf, misc.py:110-147 crop_image): a
  * decoded uint8 RGB image src [in_h][src_pitch bytes] (device) is resized so that its height is
  * min(max_height_before_crop, in_h) -- tf.image.resize_area(align_corners=True) when not enlarged, resize_bilinear

@@ -320,6 +320,27 @@ def test_resize_mean_softmax(env):
         assert (lab == ref.argmax(-1)).float().mean() > 0.999
 
 
+def test_softmax_rows_masked(env):
+    """Engine path: the fragment softmax only where the object confidence passes -- bit-identical to the full row softmax
+    on those rows, logits untouched elsewhere."""
+    from epos_b200 import _lib
+    lib, dev = env
+    s = torch.cuda.current_stream().cuda_stream
+    for P, O, F, thr in ((5000, 30, 256, 0.1), (777, 3, 128, 0.3), (64, 21, 20, 0.0)):
+        g = torch.Generator(device='cpu').manual_seed(P + O)
+        x = (torch.randn(P, O, F, generator=g) * 4).to(dev)
+        oc = torch.softmax(torch.randn(P, O + 1, generator=g) * 3, -1).to(dev).contiguous()
+        full = x.clone()
+        _lib.check(lib.epos_softmax_rows(full.data_ptr(), None, P * O, F, s), 'sm')
+        y = x.clone()
+        _lib.check(lib.epos_softmax_rows_masked(y.data_ptr(), oc.data_ptr(), P, O, F, float(thr), s), 'smm')
+        torch.cuda.synchronize()
+        mask = oc[:, 1:] > np.float32(thr)
+        assert 0 < int(mask.sum()) < P * O or thr == 0.0
+        assert torch.equal(y[mask], full[mask])
+        assert torch.equal(y[~mask], x[~mask])
+
+
 def _net_parity(B, H, W, O, F, seed, check_simt=False, variant='xception_65', multi_grid=None, logits_std=0.5):
     from epos_b200 import model, weights as Wt
     from oracle import cnn
