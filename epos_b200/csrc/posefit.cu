@@ -134,7 +134,7 @@ static size_t workspace_layout(int P, void* base, Workspace* w, bool multi = fal
   p = take((size_t)P * NMAX * 4); if (w) w->dist = (int*)p;
   p = take((size_t)P * (NMAX + 2) * 4); if (w) w->lstart = (int*)p;
   p = take((size_t)P * NMAX * 2); if (w) w->order = (unsigned short*)p;
-  p = take((size_t)P * 80 * 464); if (w) w->recs = (PassRecord*)p;
+  p = take((size_t)P * 160 * 464); if (w) w->recs = (PassRecord*)p;
   p = take((size_t)P * TRACE_ROUNDS * TRACE_COLS * 4); if (w) w->trace = (int*)p;
   if (w) { w->ms = nullptr; w->fin_model = nullptr; w->fin_inl = nullptr; w->models = nullptr; w->pref = nullptr;
            w->compound = nullptr; w->r2tab = nullptr; w->labels = nullptr; w->cr = nullptr; w->af = nullptr;
@@ -665,7 +665,7 @@ struct PassRecord {
   double val[4];
 };
 
-constexpr int CHUNK = 80;            // RANSAC passes evaluated per chunk (a multiple of the 20 warps) (records survive LO rounds in the workspace)
+constexpr int CHUNK = 160;           // RANSAC passes evaluated per chunk at most (a multiple of the 20 warps; records survive LO rounds in the workspace)
 
 __device__ __noinline__ void phase_main(const Workspace& ws, const epos_fit_params& prm, int p, unsigned char* smem_raw,
                                         bool& pts_loaded) {
@@ -714,8 +714,16 @@ __device__ __noinline__ void phase_main(const Workspace& ws, const epos_fit_para
     long long t0 = clock64();
     if (pass >= chunk_base + chunk_n) {
       // ---- phase A: one THREAD per pass: sample until a valid sample gives >= 1 admissible P3P pose ----
-      chunk_base = pass; chunk_n = CHUNK;
-      if (tid < CHUNK) {
+      // a pass consumes at least one iteration, so no more than max_iters - iter passes can still run: the chunk is
+      // clipped to that (400 iterations = 160 + 160 + 80 passes), rounded up to whole rounds of the 20 warps
+      chunk_base = pass;
+      {
+        const unsigned long long room = max_iters > iter ? max_iters - iter : 1ull;
+        int c = room < (unsigned long long)CHUNK ? (int)room : CHUNK;
+        c = ((c + WARPS - 1) / WARPS) * WARPS;
+        chunk_n = c < CHUNK ? c : CHUNK;
+      }
+      if (tid < chunk_n) {
         PassRecord* rc = recs + tid;
         const int my_pass = chunk_base + tid;
         int fails = -1, nm = 0;
@@ -742,7 +750,7 @@ __device__ __noinline__ void phase_main(const Workspace& ws, const epos_fit_para
       __syncthreads();
       t_sample += clock64() - t0; t0 = clock64();
       // ---- phase B: one WARP per pass (round-robin): score every solution over all N points ----
-      for (int k = warp; k < CHUNK; k += WARPS) {
+      for (int k = warp; k < chunk_n; k += WARPS) {
         PassRecord* rc = recs + k;
         const int nm = rc->nm;
         int m = 0;
@@ -766,7 +774,7 @@ __device__ __noinline__ void phase_main(const Workspace& ws, const epos_fit_para
       __syncthreads();
       stage_chunk();
       __syncthreads();
-      if (tid == 0) { int sc = 0; for (int k = 0; k < CHUNK; ++k) sc += s_nm[k]; n_scored += sc; }
+      if (tid == 0) { int sc = 0; for (int k = 0; k < chunk_n; ++k) sc += s_nm[k]; n_scored += sc; }
       t_score += clock64() - t0; t0 = clock64();
     }
     // ---- in-order replay: warp 0 walks the chunk's records (scalar code, every lane the same), the other 19 warps wait;
@@ -2262,7 +2270,7 @@ fit_kernel(Workspace ws, epos_fit_params prm, const int* __restrict__ offsets, d
 
 constexpr size_t SMEM_POINTS = 5 * NMAX * 8 + NMAX * 2;
 constexpr size_t SMEM_PREP = 5 * NMAX * 4 + 8192 * 8 + 64 * 4 + 8192 * 2 + 64;
-static_assert(sizeof(PassRecord) <= 464 && CHUNK == 80, "workspace_layout reserves 80 x 464 bytes of pass records");
+static_assert(sizeof(PassRecord) <= 464 && CHUNK == 160, "workspace_layout reserves 160 x 464 bytes of pass records");
 constexpr size_t SMEM_MAIN = SMEM_POINTS + 2 * WARPS * (NMAX / 32) * 4 + 12 * 8 + CHUNK * (4 * 8 + 4 * 4 + 4 + 4) + 64;
 constexpr size_t SMEM_CUT = SMEM_CUT_DYN;
 static_assert(FIT_SCRATCH_DOUBLES * 8 >= (NMAX / 32) * 4, "bitset must fit in the fit scratch");
