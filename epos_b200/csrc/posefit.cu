@@ -564,6 +564,7 @@ __device__ inline int score_warp(const SmemPoints& sp, int N, const double* mode
 // point of shared-memory reads as by the FP64 pipe.  Same per-point arithmetic, same counting and summation order per
 // model as score_warp; bitsA / bitsB: two per-warp bitsets.  Returns the points not visited (both models, when neither can
 // reach floor_inl any more).
+template <bool CP>                 // CP: compound (Progressive-X) score; cpref is ignored otherwise
 __device__ inline int score_warp2(const SmemPoints& sp, int N, const double* modelA, const double* modelB, double sq_trunc,
                                   unsigned int* bitsA, unsigned int* bitsB, int lane, int* inl_out, int* pix_out,
                                   const double* __restrict__ cpref, double* val_out, int floor_inl) {
@@ -572,7 +573,7 @@ __device__ inline int score_warp2(const SmemPoints& sp, int N, const double* mod
   for (int k = 0; k < 12; ++k) { ma[k] = modelA[k]; mb[k] = modelB[k]; }
   for (int k = lane; k < NMAX / 32; k += 32) { bitsA[k] = 0u; bitsB[k] = 0u; }
   __syncwarp();
-  int inlA = 0, inlB = 0;
+  int cntA = 0, cntB = 0;            // per-lane inlier counts; summed over the warp every fourth block and at the end
   double sharedA = 0.0, sharedB = 0.0;
   for (int base = 0; base < N; base += 64) {
     bool ia[2], ib[2];
@@ -593,7 +594,7 @@ __device__ inline int score_warp2(const SmemPoints& sp, int N, const double* mod
         const unsigned int pid = sp.pix[i];
         if (ia[u]) atomicOr(&bitsA[pid >> 5], 1u << (pid & 31));
         if (ib[u]) atomicOr(&bitsB[pid >> 5], 1u << (pid & 31));
-        if (cpref) {
+        if (CP) {
           const double c = cpref[i];
           if (ia[u]) {
             double pref = 1.0 - sq_residual(sp.un[i], sp.vn[i], sp.x[i], sp.y[i], sp.z[i], ma) / sq_trunc;
@@ -607,16 +608,20 @@ __device__ inline int score_warp2(const SmemPoints& sp, int N, const double* mod
           }
         }
       }
-      inlA += __popc(__ballot_sync(0xffffffffu, ia[u]));
-      inlB += __popc(__ballot_sync(0xffffffffu, ib[u]));
+      cntA += ia[u] ? 1 : 0;
+      cntB += ib[u] ? 1 : 0;
     }
     const int left = N - base - 64;
-    if (left > 0 && inlA + left + 1 < floor_inl && inlB + left + 1 < floor_inl) {
-      inl_out[0] = inl_out[1] = 0; pix_out[0] = pix_out[1] = 0; val_out[0] = val_out[1] = 0.0;
-      return 2 * left;
+    if (floor_inl > 0 && left > 0 && (base & 192) == 192) {          // every 256 points: can either model still matter?
+      const int inlA = __reduce_add_sync(0xffffffffu, cntA), inlB = __reduce_add_sync(0xffffffffu, cntB);
+      if (inlA + left + 1 < floor_inl && inlB + left + 1 < floor_inl) {
+        inl_out[0] = inl_out[1] = 0; pix_out[0] = pix_out[1] = 0; val_out[0] = val_out[1] = 0.0;
+        return 2 * left;
+      }
     }
   }
   __syncwarp();
+  const int inlA = __reduce_add_sync(0xffffffffu, cntA), inlB = __reduce_add_sync(0xffffffffu, cntB);
   int pxA = 0, pxB = 0;
   for (int k = lane; k < NMAX / 32; k += 32) { pxA += __popc(bitsA[k]); pxB += __popc(bitsB[k]); }
 #pragma unroll
@@ -626,7 +631,7 @@ __device__ inline int score_warp2(const SmemPoints& sp, int N, const double* mod
   }
   inl_out[0] = inlA; inl_out[1] = inlB; pix_out[0] = pxA; pix_out[1] = pxB;
   double vA = (double)pxA, vB = (double)pxB;
-  if (cpref) {
+  if (CP) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       sharedA += __shfl_xor_sync(0xffffffffu, sharedA, o);
@@ -757,8 +762,10 @@ __device__ __noinline__ void phase_main(const Workspace& ws, const epos_fit_para
         for (; m + 1 < nm; m += 2) {                                 // two solutions per sweep over the points
           int inl[2], px[2];
           double val[2];
-          n_skipped += score_warp2(sp, N, rc->models + 12 * m, rc->models + 12 * (m + 1), sq_trunc, bits, bits2, lane, inl, px,
-                                   cpref, val, best_inl);
+          n_skipped += cpref ? score_warp2<true>(sp, N, rc->models + 12 * m, rc->models + 12 * (m + 1), sq_trunc, bits, bits2,
+                                                 lane, inl, px, cpref, val, best_inl)
+                             : score_warp2<false>(sp, N, rc->models + 12 * m, rc->models + 12 * (m + 1), sq_trunc, bits, bits2,
+                                                  lane, inl, px, cpref, val, best_inl);
           if (lane == 0) {
             rc->inl[m] = inl[0]; rc->pix[m] = px[0]; rc->val[m] = val[0];
             rc->inl[m + 1] = inl[1]; rc->pix[m + 1] = px[1]; rc->val[m + 1] = val[1];
