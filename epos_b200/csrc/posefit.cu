@@ -575,10 +575,10 @@ __device__ inline int score_warp2(const SmemPoints& sp, int N, const double* mod
   __syncwarp();
   int cntA = 0, cntB = 0;            // per-lane inlier counts; summed over the warp every fourth block and at the end
   double sharedA = 0.0, sharedB = 0.0;
-  for (int base = 0; base < N; base += 64) {
-    bool ia[2], ib[2];
+  for (int base = 0; base < N; base += 96) {
+    bool ia[3], ib[3];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < 3; ++u) {
       const int i = base + u * 32 + lane;
       ia[u] = ib[u] = false;
       if (i < N) {
@@ -588,7 +588,7 @@ __device__ inline int score_warp2(const SmemPoints& sp, int N, const double* mod
       }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < 3; ++u) {
       const int i = base + u * 32 + lane;
       if (ia[u] || ib[u]) {
         const unsigned int pid = sp.pix[i];
@@ -611,8 +611,8 @@ __device__ inline int score_warp2(const SmemPoints& sp, int N, const double* mod
       cntA += ia[u] ? 1 : 0;
       cntB += ib[u] ? 1 : 0;
     }
-    const int left = N - base - 64;
-    if (floor_inl > 0 && left > 0 && (base & 192) == 192) {          // every 256 points: can either model still matter?
+    const int left = N - base - 96;
+    if (floor_inl > 0 && left > 0 && (base % 288) == 192) {          // every 288 points: can either model still matter?
       const int inlA = __reduce_add_sync(0xffffffffu, cntA), inlB = __reduce_add_sync(0xffffffffu, cntB);
       if (inlA + left + 1 < floor_inl && inlB + left + 1 < floor_inl) {
         inl_out[0] = inl_out[1] = 0; pix_out[0] = pix_out[1] = 0; val_out[0] = val_out[1] = 0.0;
