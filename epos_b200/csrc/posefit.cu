@@ -8,9 +8,12 @@
 //
 //   prep_kernel   points (u_n, v_n, x, y, z), dense pixel ids, k-nearest neighbour graph (f32, 5-D), reverse adjacency
 //   fit_kernel    ONE PERSISTENT CTA PER PROBLEM runs the whole state machine, re-carving its shared memory per phase:
-//     main     80 RANSAC passes at a time: a thread per pass samples until a valid sample gives an admissible Kneip P3P pose,
-//              a warp per pass scores every solution over all N points (ballot counting, per-warp pixel bitset), then an
-//              in-order replay of the chunk applies the reference's update / early-out / LO-trigger / termination rules
+//     main     up to 160 RANSAC passes at a time (never more than the iteration budget still allows): a thread per pass
+//              samples until a valid sample gives an admissible Kneip P3P pose; a warp per pass scores its solutions
+//              over all N points, two solutions per sweep (per-lane inlier counts, per-warp pixel bitsets, early exit
+//              when neither can reach the early-out bound); then warp 0 replays the chunk in order -- lanes test 32
+//              passes at once for "stops the loop / accepts a model", only such a pass runs the scalar update /
+//              early-out / LO-trigger / termination code of the reference
 //     cut      graph-cut labeling (GCRANSAC.h:812-920): f64 preflow-push in waves + reverse BFS = nodes that can still
 //              reach the sink, which is what the reference's BK max-flow labels SINK (graph.h:112-115,478-488)
 //     trials   the <= 20 inner fits of graphCutLocalOptimization (GCRANSAC.h:737-792), one warp per trial
