@@ -22,7 +22,10 @@ def pieces(m_tiles, N, block_n, tile_m, ctas):
     (300, 728, 256, 128, 148),      # middle flow at B = 8: 900 tiles = 6.08 waves -> remainder of 12 tiles is split
     (150, 728, 256, 256, 74),       # the same layer on CTA pairs
     (300, 1536, 256, 128, 148), (1200, 4032, 256, 128, 148), (1200, 22, 32, 128, 148), (1200, 48, 64, 128, 148),
-    (38, 728, 256, 128, 148), (1, 64, 64, 128, 1), (5, 1000, 256, 128, 7), (300, 128, 128, 128, 148), (19, 2048, 256, 256, 74)])
+    (38, 728, 256, 128, 148), (1, 64, 64, 128, 1), (5, 1000, 256, 128, 7), (300, 128, 128, 128, 148), (19, 2048, 256, 256, 74),
+    # CTA pairs on every layer wider than 128 columns (round 2): decoder / heads at B = 8, ResNet, odd tile counts
+    (600, 256, 256, 256, 74), (600, 1344, 256, 256, 74), (600, 4032, 256, 256, 74), (150, 1024, 256, 256, 74),
+    (1200, 7680, 256, 256, 74), (2, 728, 256, 256, 74), (3, 136, 256, 256, 1)])
 def test_pieces_tile_the_output_exactly_once(m_tiles, N, block_n, tile_m, ctas):
     p = pieces(m_tiles, N, block_n, tile_m, ctas)
     cover = np.zeros((m_tiles, N), np.int32)
